@@ -1,0 +1,261 @@
+"""ctypes binding of the C ABI in ``include/erasor_b200.h`` (``erasor_b200/_lib/liberasor_b200.so``).
+
+The library is CUDA-only: importing this module without the built ``.so`` raises, and
+``Handle(...)`` raises when there is no CUDA device.  There is no CPU fallback anywhere in the
+package (the CPU oracle lives under ``oracle/`` and is test infrastructure).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_size_t, c_uint8, c_uint32, c_uint64, c_void_p
+
+import numpy as np
+
+from .params import ErasorParams, ErasorParamsC
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "liberasor_b200.so")
+
+PTR_HOST, PTR_DEVICE = 0, 1
+CLOUD_MAP, CLOUD_QUERY = 0, 1
+OK, E_INVALID, E_CUDA, E_STATE, E_CAPACITY, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+
+EXPORTS = [
+    "erasor_create", "erasor_destroy", "erasor_last_error", "erasor_abi_version", "erasor_stream", "erasor_synchronize",
+    "erasor_set_inputs", "erasor_compare", "erasor_get_output_sizes", "erasor_get_static_estimate", "erasor_get_outliers",
+    "erasor_get_max_range", "erasor_get_bins", "erasor_get_status", "erasor_get_planes", "erasor_get_static_mask",
+    "erasor_get_fence_counts", "erasor_process_frames", "erasor_get_frame_stats", "erasor_kernel_launch_count",
+    "erasor_get_kernel_time_ms", "erasor_reset_kernel_times",
+]
+
+
+class ErasorError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"erasor_b200 error {code}: {msg}")
+        self.code = code
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with erasor_b200/csrc/build.sh (or __graft_entry__.build()). "
+            "erasor_b200 has no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    fp = POINTER(c_float)
+    L.erasor_create.restype = c_int
+    L.erasor_create.argtypes = [POINTER(ErasorParamsC), c_int, POINTER(c_void_p)]
+    L.erasor_destroy.restype = None
+    L.erasor_destroy.argtypes = [c_void_p]
+    L.erasor_last_error.restype = c_char_p
+    L.erasor_last_error.argtypes = [c_void_p]
+    L.erasor_abi_version.restype = c_int
+    L.erasor_stream.restype = c_void_p
+    L.erasor_stream.argtypes = [c_void_p]
+    L.erasor_synchronize.argtypes = [c_void_p]
+    L.erasor_set_inputs.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_int]
+    L.erasor_compare.argtypes = [c_void_p, c_int, c_int]
+    L.erasor_get_output_sizes.argtypes = [c_void_p, POINTER(c_size_t), POINTER(c_size_t), POINTER(c_size_t), POINTER(c_size_t)]
+    L.erasor_get_static_estimate.argtypes = [c_void_p, c_void_p, c_size_t, POINTER(c_size_t), c_void_p, c_size_t, POINTER(c_size_t), c_int]
+    L.erasor_get_outliers.argtypes = [c_void_p, c_void_p, c_size_t, POINTER(c_size_t), c_void_p, c_size_t, POINTER(c_size_t), c_int]
+    L.erasor_get_max_range.restype = c_double
+    L.erasor_get_max_range.argtypes = [c_void_p]
+    L.erasor_get_bins.argtypes = [c_void_p, c_int, POINTER(c_int32), fp, fp, POINTER(c_uint32)]
+    L.erasor_get_status.argtypes = [c_void_p, fp]
+    L.erasor_get_planes.argtypes = [c_void_p, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), POINTER(c_double),
+                                    POINTER(c_double), POINTER(c_int32), POINTER(c_size_t)]
+    L.erasor_get_static_mask.argtypes = [c_void_p, POINTER(c_uint8), POINTER(c_uint8)]
+    L.erasor_get_fence_counts.argtypes = [c_void_p, POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint64)]
+    L.erasor_process_frames.argtypes = [c_void_p, c_void_p, POINTER(c_uint64), c_void_p, POINTER(c_uint64), c_int, c_void_p, c_int]
+    L.erasor_get_frame_stats.argtypes = [c_void_p, POINTER(c_uint32), POINTER(c_uint32)]
+    L.erasor_kernel_launch_count.restype = c_uint64
+    L.erasor_kernel_launch_count.argtypes = [c_void_p]
+    L.erasor_get_kernel_time_ms.argtypes = [c_void_p, c_int, POINTER(c_double), POINTER(c_uint64)]
+    L.erasor_reset_kernel_times.argtypes = [c_void_p, c_int]
+    return L
+
+
+_L = None
+
+
+def lib():
+    global _L
+    if _L is None:
+        _L = _load()
+    return _L
+
+
+def _cloud(a) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.size == 0:
+        return a.reshape(0, 4)
+    if a.ndim != 2 or a.shape[1] != 4:
+        raise ValueError("clouds are float32 [n,4] = x,y,z,intensity")
+    return a
+
+
+class Handle:
+    """One ``erasor_handle_t``: one CUDA device, one stream, fixed parameters."""
+
+    def __init__(self, params: ErasorParams, device: int = 0):
+        self.L = lib()
+        self.params = params
+        self._pc = params.to_c()
+        h = c_void_p()
+        rc = self.L.erasor_create(ctypes.byref(self._pc), device, ctypes.byref(h))
+        if rc != OK:
+            raise ErasorError(rc, (self.L.erasor_last_error(None) or b"").decode())
+        self.h = h
+        self.n_map = 0
+        self.n_query = 0
+        self._keep = []   # keeps host arrays alive while the library may still read them
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _ck(self, rc: int):
+        if rc != OK:
+            raise ErasorError(rc, (self.L.erasor_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.erasor_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def stream(self) -> int:
+        return self.L.erasor_stream(self.h) or 0
+
+    def synchronize(self):
+        self._ck(self.L.erasor_synchronize(self.h))
+
+    # -- the per-frame path ---------------------------------------------------------------
+    def set_inputs(self, map_voi, query_voi):
+        m, q = _cloud(map_voi), _cloud(query_voi)
+        self._keep = [m, q]
+        self.n_map, self.n_query = len(m), len(q)
+        self._ck(self.L.erasor_set_inputs(self.h, m.ctypes.data, len(m), q.ctypes.data, len(q), PTR_HOST))
+
+    def set_inputs_device(self, map_ptr: int, n_map: int, query_ptr: int, n_query: int):
+        self.n_map, self.n_query = n_map, n_query
+        self._ck(self.L.erasor_set_inputs(self.h, c_void_p(map_ptr), n_map, c_void_p(query_ptr), n_query, PTR_DEVICE))
+
+    def compare(self, version: int | None = None, frame: int = 0):
+        self._ck(self.L.erasor_compare(self.h, self.params.version if version is None else version, frame))
+
+    def output_sizes(self):
+        a, c, m, q = c_size_t(), c_size_t(), c_size_t(), c_size_t()
+        self._ck(self.L.erasor_get_output_sizes(self.h, ctypes.byref(a), ctypes.byref(c), ctypes.byref(m), ctypes.byref(q)))
+        return a.value, c.value, m.value, q.value
+
+    def get_static_estimate(self):
+        na, nc, _, _ = self.output_sizes()
+        arr = np.empty((na, 4), dtype=np.float32)
+        cmp_ = np.empty((nc, 4), dtype=np.float32)
+        a, c = c_size_t(), c_size_t()
+        self._ck(self.L.erasor_get_static_estimate(self.h, arr.ctypes.data, na, ctypes.byref(a), cmp_.ctypes.data, nc, ctypes.byref(c), PTR_HOST))
+        return arr, cmp_
+
+    def get_outliers(self):
+        _, _, nm, nq = self.output_sizes()
+        mr = np.empty((nm, 4), dtype=np.float32)
+        cr = np.empty((nq, 4), dtype=np.float32)
+        a, c = c_size_t(), c_size_t()
+        self._ck(self.L.erasor_get_outliers(self.h, mr.ctypes.data, nm, ctypes.byref(a), cr.ctypes.data, nq, ctypes.byref(c), PTR_HOST))
+        return mr, cr
+
+    def get_max_range(self) -> float:
+        return self.L.erasor_get_max_range(self.h)
+
+    # -- parity taps ---------------------------------------------------------------------------
+    def get_bins(self, which: int):
+        B = self.params.num_bins
+        n = self.n_map if which == CLOUD_MAP else self.n_query
+        bop = np.empty(n, dtype=np.int32)
+        mn, mx = np.empty(B, dtype=np.float32), np.empty(B, dtype=np.float32)
+        cnt = np.empty(B, dtype=np.uint32)
+        self._ck(self.L.erasor_get_bins(self.h, which, bop.ctypes.data_as(POINTER(c_int32)), mn.ctypes.data_as(POINTER(c_float)),
+                                        mx.ctypes.data_as(POINTER(c_float)), cnt.ctypes.data_as(POINTER(c_uint32))))
+        return bop, mn, mx, cnt
+
+    def get_status(self) -> np.ndarray:
+        st = np.empty(self.params.num_bins, dtype=np.float32)
+        self._ck(self.L.erasor_get_status(self.h, st.ctypes.data_as(POINTER(c_float))))
+        return st
+
+    def get_planes(self):
+        n = c_size_t(0)
+        self._ck(self.L.erasor_get_planes(self.h, None, None, None, None, None, None, ctypes.byref(n)))
+        k, it = n.value, self.params.gf_iter
+        bins, npts, nseeds = (np.zeros(k, dtype=np.int32) for _ in range(3))
+        lpr = np.zeros(k)
+        nd = np.zeros((k, it, 4))
+        ng = np.zeros((k, it), dtype=np.int32)
+        cap = c_size_t(k)
+        if k:
+            self._ck(self.L.erasor_get_planes(self.h, bins.ctypes.data_as(POINTER(c_int32)), npts.ctypes.data_as(POINTER(c_int32)),
+                                              nseeds.ctypes.data_as(POINTER(c_int32)), lpr.ctypes.data_as(POINTER(c_double)),
+                                              nd.ctypes.data_as(POINTER(c_double)), ng.ctypes.data_as(POINTER(c_int32)), ctypes.byref(cap)))
+        return [dict(bin=int(bins[i]), n_points=int(npts[i]), n_seeds=int(nseeds[i]), lpr=float(lpr[i]), normal_d=nd[i], n_ground=ng[i])
+                for i in range(k)]
+
+    def get_static_mask(self):
+        keep = np.empty(self.n_map, dtype=np.uint8)
+        gnd = np.empty(self.n_map, dtype=np.uint8)
+        self._ck(self.L.erasor_get_static_mask(self.h, keep.ctypes.data_as(POINTER(c_uint8)), gnd.ctypes.data_as(POINTER(c_uint8))))
+        return keep, gnd
+
+    def fence_counts(self):
+        a, b, c = c_uint64(), c_uint64(), c_uint64()
+        self._ck(self.L.erasor_get_fence_counts(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return dict(negzero_points=a.value, empty_plane_fits=b.value, ambiguous_sector=c.value)
+
+    # -- batch mode ---------------------------------------------------------------------------
+    def process_frames(self, map_xyzi, map_offsets, query_xyzi, query_offsets) -> np.ndarray:
+        """Host-buffer batch call: returns keep mask (uint8) over all map points of all frames."""
+        m, q = _cloud(map_xyzi), _cloud(query_xyzi)
+        mo = np.ascontiguousarray(map_offsets, dtype=np.uint64)
+        qo = np.ascontiguousarray(query_offsets, dtype=np.uint64)
+        F = len(mo) - 1
+        keep = np.empty(int(mo[-1]), dtype=np.uint8)
+        self._ck(self.L.erasor_process_frames(self.h, m.ctypes.data, mo.ctypes.data_as(POINTER(c_uint64)), q.ctypes.data,
+                                              qo.ctypes.data_as(POINTER(c_uint64)), F, keep.ctypes.data, PTR_HOST))
+        self.n_frames = F
+        return keep
+
+    def process_frames_ptr(self, map_ptr: int, map_offsets: np.ndarray, query_ptr: int, query_offsets: np.ndarray, keep_ptr: int, ptr_kind: int):
+        """Raw-pointer batch call (device tensors or pinned host memory); offsets are host uint64 arrays."""
+        mo = np.ascontiguousarray(map_offsets, dtype=np.uint64)
+        qo = np.ascontiguousarray(query_offsets, dtype=np.uint64)
+        F = len(mo) - 1
+        self._ck(self.L.erasor_process_frames(self.h, c_void_p(map_ptr), mo.ctypes.data_as(POINTER(c_uint64)), c_void_p(query_ptr),
+                                              qo.ctypes.data_as(POINTER(c_uint64)), F, c_void_p(keep_ptr), ptr_kind))
+        self.n_frames = F
+
+    def frame_stats(self):
+        F = self.n_frames
+        nf, nr = np.zeros(F, dtype=np.uint32), np.zeros(F, dtype=np.uint32)
+        self._ck(self.L.erasor_get_frame_stats(self.h, nf.ctypes.data_as(POINTER(c_uint32)), nr.ctypes.data_as(POINTER(c_uint32))))
+        return nf, nr
+
+    # -- instrumentation ------------------------------------------------------------------------
+    def kernel_launch_count(self) -> int:
+        return int(self.L.erasor_kernel_launch_count(self.h))
+
+    def reset_kernel_times(self, enable: bool):
+        self._ck(self.L.erasor_reset_kernel_times(self.h, 1 if enable else 0))
+
+    def kernel_time_ms(self, kernel_id: int):
+        t, n = c_double(), c_uint64()
+        self._ck(self.L.erasor_get_kernel_time_ms(self.h, kernel_id, ctypes.byref(t), ctypes.byref(n)))
+        return t.value, n.value

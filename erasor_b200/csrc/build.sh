@@ -1,0 +1,16 @@
+#!/bin/bash
+# build.sh -- compiles the product library for sm_100a (nvcc cross-compiles without a GPU).
+#   erasor_b200/_lib/liberasor_b200.so            the C-ABI library (include/erasor_b200.h)
+#   erasor_b200/_lib/liberasor_b200_hostcheck.so  host-only build of binning.h for the CPU test-suite
+set -euo pipefail
+cd "$(dirname "$0")"
+mkdir -p ../_lib ../_build
+NVCC=${NVCC:-nvcc}
+ARCH="-gencode arch=compute_100a,code=sm_100a"
+CXXF="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC"
+$NVCC $ARCH $CXXF -Xptxas -v -c kernels.cu -o ../_build/kernels.o 2> ../_build/kernels.ptxas.log
+$NVCC $ARCH $CXXF -c erasor_capi.cu -o ../_build/erasor_capi.o
+g++ -O2 -std=c++17 -fPIC -ffp-contract=off -c binning_tables.cpp -o ../_build/binning_tables.o
+$NVCC $ARCH -shared -o ../_lib/liberasor_b200.so ../_build/kernels.o ../_build/erasor_capi.o ../_build/binning_tables.o -lquadmath -lcudart
+g++ -O2 -std=c++17 -fPIC -shared -ffp-contract=off -o ../_lib/liberasor_b200_hostcheck.so host_selftest.cpp binning_tables.cpp -lquadmath
+echo "built: $(ls ../_lib)"

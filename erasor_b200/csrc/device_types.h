@@ -1,0 +1,61 @@
+// device_types.h -- shared host/device structs of the path's HBM layout.
+#pragma once
+#include <cstdint>
+
+#include "binning.h"
+
+namespace erasor {
+
+constexpr uint32_t kSkip      = 0xFFFFFFFFu;   // dst_start value of a bin that is not scattered
+constexpr uint16_t kNoBin16   = 0xFFFFu;       // bin id of a point that failed the z window / range test
+constexpr int      kMaxIter   = 8;             // gf_iter upper bound for the tap arrays
+
+// status codes held on the device (values published through erasor_get_status)
+enum : uint8_t { ST_LITTLE = 0, ST_MERGE = 1, ST_MAP_HIGH = 2, ST_BLOCKED = 3, ST_CURR_HIGH = 4 };
+// what the selected bin is made of (erasor.cpp:493-563 / 346-427)
+enum : uint8_t { ACT_MAP = 0, ACT_FLAG = 1, ACT_MERGE = 2, ACT_CURR = 3, ACT_NONE = 4, ACT_CURR_REJECTED_BIT = 0x10 };
+
+// One contiguous run of points of one cloud of one frame, processed by one CTA of K1 / one warp of K2.
+struct ChunkDesc {
+    uint32_t begin;        // first point (index into the concatenated cloud array)
+    uint32_t len;          // points in this chunk
+    uint32_t frame;        // frame index
+    uint32_t cloud;        // 0 map, 1 query
+    uint32_t frame_begin;  // first point of this frame's cloud
+    uint32_t pad_[3];
+};
+
+struct SrtParams {
+    double scan_ratio_threshold;
+    double th_bin_max_h;
+    int    minimum_num_pts;
+    int    version;
+    int    R, S, B;
+    int    scatter_mode;       // 0: every bin (cloud outputs), 1: flagged bins only (mask outputs)
+};
+
+struct GpfParams {
+    double th_dist;            // gf_dist_thr
+    double th_seeds;           // gf_th_seeds_height
+    int    num_lowest_pts;
+    int    num_lpr;
+    int    iters;
+    int    cov_mode;
+};
+
+// Per flagged bin record written by K3 and completed by K4
+struct FlagRec {
+    uint32_t frame;
+    uint32_t bin;
+    uint32_t slot;             // index among the frame's flagged bins (bin order)
+    uint32_t n_points;
+    uint32_t src_begin;        // offset of the bin's points in the scattered map array (absolute)
+    uint32_t n_seeds;
+    uint32_t n_empty_fits;
+    uint32_t n_ground_final;
+    double   lpr_height;
+    double   normal_d[kMaxIter][4];
+    uint32_t n_ground[kMaxIter];
+};
+
+}  // namespace erasor

@@ -1,0 +1,681 @@
+// erasor_capi.cu -- the extern "C" boundary (include/erasor_b200.h): context, HBM buffers, launch order.
+// There is no host compute path in this file: every entry point either launches the sm_100a kernels of
+// kernels.cu or fails with an error code.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/erasor_b200.h"
+#include "binning_tables.h"
+#include "device_types.h"
+#include "kernels.h"
+
+using namespace erasor;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void*  p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+    void*  p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+constexpr int kNumTimers = 6;   // 0 whole pipeline, 1..5 = K1..K5
+
+struct Timer {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    double   total_ms = 0;
+    uint64_t launches = 0;
+};
+
+}  // namespace
+
+struct erasor_ctx {
+    erasor_params_t p{};
+    int             device = 0;
+    cudaStream_t    stream = nullptr;
+    int             sm_count = 148;
+    std::string     err;
+    HostBinTables   tables;
+    DevBuf          d_ring, d_pos, d_neg;
+    BinTablesView   view{};
+    int             B = 0;
+
+    // per-batch buffers
+    DevBuf d_map_in, d_qry_in;                 // staging when the caller's clouds are host memory
+    DevBuf d_bin_map, d_bin_qry;               // uint16 bin id per point
+    DevBuf d_chunks, d_chunk_range, d_frame_off;
+    DevBuf d_chcnt, d_zmin, d_zmax, d_cnt, d_dst_start, d_status, d_action, d_flag_slot, d_nflag;
+    DevBuf d_recs, d_nrecs, d_frame_rej;
+    DevBuf d_map_sorted, d_map_src, d_qry_sorted, d_qry_src, d_part, d_scratch;
+    DevBuf d_keep, d_ground;
+    DevBuf d_arranged, d_map_rej, d_curr_rej, d_jobs, d_out_sizes, d_k5tmp;
+    DevBuf d_vox, d_vox_cnt, d_vox_start, d_vox_scratch;
+    DevBuf d_fence;                            // 4 x u64: negzero, empty fits, ambiguous, slow-path points
+    PinnedBuf h_stage;
+
+    // batch geometry of the last run
+    int      F = 0;
+    size_t   NM = 0, NQ = 0;
+    uint32_t n_chunks_map = 0, n_chunks_qry = 0;
+    uint32_t rec_capacity = 0;
+    const float4* cur_map = nullptr;
+    const float4* cur_qry = nullptr;
+    std::vector<uint64_t> map_off, qry_off;
+
+    // single-frame state machine
+    int      stage = 0;                        // 0: nothing, 1: inputs set, 2: compared
+    uint32_t out_sizes[4] = {0, 0, 0, 0};
+    uint32_t complement_start = 0;
+    uint32_t n_recs_host = 0;
+
+    uint64_t launches = 0;
+    bool     timing = false;
+    Timer    timers[kNumTimers];
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e__);                          \
+            return ERASOR_E_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+struct Scope {   // optional CUDA-event bracket around a kernel (timing == true only)
+    erasor_ctx* h; int id; cudaEvent_t a = nullptr, b = nullptr;
+    Scope(erasor_ctx* h_, int id_) : h(h_), id(id_) {
+        if (h->timing) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, h->stream); }
+    }
+    ~Scope() {
+        if (h->timing) { cudaEventRecord(b, h->stream); h->timers[id].pending.emplace_back(a, b); }
+    }
+};
+
+void drain_timers(erasor_ctx* h) {
+    for (int i = 0; i < kNumTimers; ++i) {
+        for (auto& pr : h->timers[i].pending) {
+            cudaEventSynchronize(pr.second);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, pr.first, pr.second);
+            h->timers[i].total_ms += ms;
+            h->timers[i].launches += 1;
+            cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+        }
+        h->timers[i].pending.clear();
+    }
+}
+
+uint32_t choose_chunk(const erasor_ctx* h, size_t total_points) {
+    // Chunk = one CTA of K1 / one warp of K2.  Dense per-chunk count rows cost 4*(B+1) bytes, so keep the chunk
+    // at >= 5*B points (<= 5 % extra traffic); otherwise aim at ~8 chunks per SM.
+    const size_t target = total_points / ((size_t)h->sm_count * 8) + 1;
+    size_t ch = std::max<size_t>(target, std::max<size_t>(2048, (size_t)5 * h->B));
+    ch = std::min<size_t>(ch, 65536);
+    ch = (ch + 127) & ~(size_t)127;
+    return (uint32_t)ch;
+}
+
+// Build chunk descriptors + per-frame chunk ranges + frame offsets, upload them, size every buffer.
+int prepare_batch(erasor_ctx* h, const uint64_t* map_off, const uint64_t* qry_off, int F, int mode) {
+    if (F <= 0) { h->err = "n_frames must be positive"; return ERASOR_E_INVALID; }
+    const size_t NM = map_off[F], NQ = qry_off[F];
+    if (NM >= 0xFFFFFFF0ull || NQ >= 0xFFFFFFF0ull) { h->err = "batch exceeds 2^32 points; split it"; return ERASOR_E_INVALID; }
+    for (int f = 0; f < F; ++f)
+        if (map_off[f + 1] < map_off[f] || qry_off[f + 1] < qry_off[f]) { h->err = "offsets must be non-decreasing"; return ERASOR_E_INVALID; }
+    const int B = h->B;
+    h->F = F; h->NM = NM; h->NQ = NQ;
+    h->map_off.assign(map_off, map_off + F + 1);
+    h->qry_off.assign(qry_off, qry_off + F + 1);
+    const uint32_t CH = choose_chunk(h, NM + NQ);
+
+    std::vector<ChunkDesc> chunks;
+    std::vector<uint32_t>  range(2 * (size_t)(F + 1)), foff(2 * (size_t)(F + 1));
+    chunks.reserve((NM + NQ) / CH + 2 * (size_t)F + 2);
+    for (int c = 0; c < 2; ++c) {
+        const uint64_t* off = c == 0 ? map_off : qry_off;
+        for (int f = 0; f < F; ++f) {
+            range[(size_t)c * (F + 1) + f] = (uint32_t)chunks.size();
+            foff[(size_t)c * (F + 1) + f]  = (uint32_t)off[f];
+            for (uint64_t b = off[f]; b < off[f + 1]; b += CH) {
+                ChunkDesc d{};
+                d.begin = (uint32_t)b; d.len = (uint32_t)std::min<uint64_t>(CH, off[f + 1] - b);
+                d.frame = (uint32_t)f; d.cloud = (uint32_t)c; d.frame_begin = (uint32_t)off[f];
+                chunks.push_back(d);
+            }
+        }
+        range[(size_t)c * (F + 1) + F] = (uint32_t)chunks.size();
+        foff[(size_t)c * (F + 1) + F]  = (uint32_t)off[F];
+        if (c == 0) h->n_chunks_map = (uint32_t)chunks.size();
+    }
+    h->n_chunks_qry = (uint32_t)chunks.size() - h->n_chunks_map;
+    const size_t n_chunks = chunks.size();
+
+    // device buffers
+    CK(h->d_chunks.ensure(sizeof(ChunkDesc) * std::max<size_t>(n_chunks, 1)));
+    CK(h->d_chunk_range.ensure(sizeof(uint32_t) * range.size()));
+    CK(h->d_frame_off.ensure(sizeof(uint32_t) * foff.size()));
+    CK(h->d_bin_map.ensure(sizeof(uint16_t) * std::max<size_t>(NM, 1)));
+    CK(h->d_bin_qry.ensure(sizeof(uint16_t) * std::max<size_t>(NQ, 1)));
+    CK(h->d_chcnt.ensure(sizeof(uint32_t) * std::max<size_t>(n_chunks, 1) * (B + 1)));
+    CK(h->d_zmin.ensure(sizeof(uint32_t) * 2 * (size_t)F * B));
+    CK(h->d_zmax.ensure(sizeof(uint32_t) * 2 * (size_t)F * B));
+    CK(h->d_cnt.ensure(sizeof(uint32_t) * 2 * (size_t)F * (B + 1)));
+    CK(h->d_dst_start.ensure(sizeof(uint32_t) * 2 * (size_t)F * (B + 2)));
+    CK(h->d_status.ensure((size_t)F * B));
+    CK(h->d_action.ensure((size_t)F * B));
+    CK(h->d_flag_slot.ensure(sizeof(uint32_t) * (size_t)F * B));
+    CK(h->d_nflag.ensure(sizeof(uint32_t) * (size_t)F));
+    CK(h->d_frame_rej.ensure(sizeof(uint32_t) * (size_t)F));
+    h->rec_capacity = (uint32_t)std::min<size_t>((size_t)F * B, (size_t)1 << 21);
+    CK(h->d_recs.ensure(sizeof(FlagRec) * (size_t)h->rec_capacity));
+    CK(h->d_nrecs.ensure(sizeof(uint32_t) * 4));
+    CK(h->d_map_sorted.ensure(sizeof(float4) * std::max<size_t>(NM, 1)));
+    CK(h->d_map_src.ensure(sizeof(uint32_t) * std::max<size_t>(NM, 1)));
+    CK(h->d_scratch.ensure((size_t)24 * std::max<size_t>(NM, 1) + 64));
+    if (mode == 0) {
+        CK(h->d_qry_sorted.ensure(sizeof(float4) * std::max<size_t>(NQ, 1)));
+        CK(h->d_qry_src.ensure(sizeof(uint32_t) * std::max<size_t>(NQ, 1)));
+        CK(h->d_part.ensure(sizeof(float4) * std::max<size_t>(NM, 1)));
+    }
+
+    // upload descriptors through pinned staging
+    const size_t b0 = sizeof(ChunkDesc) * n_chunks, b1 = sizeof(uint32_t) * range.size(), b2 = sizeof(uint32_t) * foff.size();
+    CK(cudaStreamSynchronize(h->stream));   // staging may still be in flight from the previous call
+    CK(h->h_stage.ensure(b0 + b1 + b2 + 64));
+    unsigned char* st = h->h_stage.as<unsigned char>();
+    if (b0) std::memcpy(st, chunks.data(), b0);
+    std::memcpy(st + b0, range.data(), b1);
+    std::memcpy(st + b0 + b1, foff.data(), b2);
+    if (b0) CK(cudaMemcpyAsync(h->d_chunks.p, st, b0, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_chunk_range.p, st + b0, b1, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_frame_off.p, st + b0 + b1, b2, cudaMemcpyHostToDevice, h->stream));
+    return ERASOR_OK;
+}
+
+int stage_inputs(erasor_ctx* h, const float* map_xyzi, const float* qry_xyzi, int ptr_kind) {
+    if (ptr_kind == ERASOR_PTR_DEVICE) {
+        h->cur_map = reinterpret_cast<const float4*>(map_xyzi);
+        h->cur_qry = reinterpret_cast<const float4*>(qry_xyzi);
+        if ((h->NM && (reinterpret_cast<uintptr_t>(map_xyzi) & 15)) || (h->NQ && (reinterpret_cast<uintptr_t>(qry_xyzi) & 15))) {
+            h->err = "device clouds must be 16-byte aligned (float4)"; return ERASOR_E_INVALID;
+        }
+        return ERASOR_OK;
+    }
+    CK(h->d_map_in.ensure(sizeof(float4) * std::max<size_t>(h->NM, 1)));
+    CK(h->d_qry_in.ensure(sizeof(float4) * std::max<size_t>(h->NQ, 1)));
+    if (h->NM) CK(cudaMemcpyAsync(h->d_map_in.p, map_xyzi, sizeof(float4) * h->NM, cudaMemcpyHostToDevice, h->stream));
+    if (h->NQ) CK(cudaMemcpyAsync(h->d_qry_in.p, qry_xyzi, sizeof(float4) * h->NQ, cudaMemcpyHostToDevice, h->stream));
+    h->cur_map = h->d_map_in.as<float4>();
+    h->cur_qry = h->d_qry_in.as<float4>();
+    return ERASOR_OK;
+}
+
+int run_k1(erasor_ctx* h) {
+    const int B = h->B, F = h->F;
+    {
+        h->launches++;
+        CK(launch_init_tables(h->stream, h->d_zmin.as<uint32_t>(), h->d_zmax.as<uint32_t>(), 2 * (size_t)F * B,
+                              h->d_nrecs.as<uint32_t>(), h->d_frame_rej.as<uint32_t>(), F));
+    }
+    {
+        Scope s(h, 1);
+        if (h->n_chunks_map + h->n_chunks_qry) h->launches++;
+        CK(launch_k1(h->stream, h->view, h->cur_map, h->cur_qry, h->d_chunks.as<ChunkDesc>(), (int)(h->n_chunks_map + h->n_chunks_qry),
+                     h->d_bin_map.as<uint16_t>(), h->d_bin_qry.as<uint16_t>(), h->d_chcnt.as<uint32_t>(), h->d_zmin.as<uint32_t>(),
+                     h->d_zmax.as<uint32_t>(), B, F, h->d_fence.as<unsigned long long>()));
+    }
+    return ERASOR_OK;
+}
+
+// K3 -> K2 -> K4 ; mode 0: every bin scattered + partitioned copies (cloud outputs), mode 1: flagged only + masks
+int run_compare(erasor_ctx* h, int version, int mode, uint8_t* keep_mask, uint8_t* ground_mask) {
+    const int B = h->B, F = h->F;
+    SrtParams sp{};
+    sp.scan_ratio_threshold = h->p.scan_ratio_threshold;
+    sp.th_bin_max_h = h->p.th_bin_max_h;
+    sp.minimum_num_pts = h->p.minimum_num_pts;
+    sp.version = version; sp.R = h->p.num_rings; sp.S = h->p.num_sectors; sp.B = B; sp.scatter_mode = mode;
+    {
+        Scope s(h, 3);
+        h->launches++;
+        CK(launch_k3(h->stream, sp, F, h->d_chunk_range.as<uint32_t>(), h->d_chcnt.as<uint32_t>(), h->d_zmin.as<uint32_t>(),
+                     h->d_zmax.as<uint32_t>(), h->d_frame_off.as<uint32_t>(), h->d_cnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>(),
+                     h->d_status.as<uint8_t>(), h->d_action.as<uint8_t>(), h->d_flag_slot.as<uint32_t>(), h->d_nflag.as<uint32_t>(),
+                     h->d_recs.as<FlagRec>(), h->d_nrecs.as<uint32_t>(), h->rec_capacity));
+    }
+    {
+        Scope s(h, 2);
+        if (h->n_chunks_map) h->launches++;
+        CK(launch_k2(h->stream, h->d_chunks.as<ChunkDesc>(), 0u, h->n_chunks_map, F, h->d_bin_map.as<uint16_t>(), h->cur_map,
+                     h->d_chcnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>(), h->d_map_sorted.as<float4>(), h->d_map_src.as<uint32_t>(), B));
+        if (mode == 0) {
+            if (h->n_chunks_qry) h->launches++;
+            CK(launch_k2(h->stream, h->d_chunks.as<ChunkDesc>(), h->n_chunks_map, h->n_chunks_qry, F, h->d_bin_qry.as<uint16_t>(), h->cur_qry,
+                         h->d_chcnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>() + (size_t)F * (B + 2), h->d_qry_sorted.as<float4>(),
+                         h->d_qry_src.as<uint32_t>(), B));
+        }
+    }
+    {
+        Scope s(h, 4);
+        GpfParams gp{};
+        gp.th_dist = h->p.gf_dist_thr; gp.th_seeds = h->p.gf_th_seeds_height; gp.num_lowest_pts = h->p.num_lowest_pts;
+        gp.num_lpr = h->p.gf_num_lpr; gp.iters = std::min(h->p.gf_iter, kMaxIter); gp.cov_mode = h->p.cov_mode;
+        h->launches++;
+        CK(launch_k4(h->stream, gp, h->d_recs.as<FlagRec>(), h->d_nrecs.as<uint32_t>(), h->rec_capacity, h->d_map_sorted.as<float4>(),
+                     h->d_map_src.as<uint32_t>(), h->d_frame_off.as<uint32_t>(), mode == 0 ? h->d_part.as<float4>() : nullptr,
+                     keep_mask, ground_mask, h->d_frame_rej.as<uint32_t>(), h->d_scratch.as<unsigned char>(), h->sm_count * 3,
+                     h->d_fence.as<unsigned long long>()));
+    }
+    return ERASOR_OK;
+}
+
+int copy_out(erasor_ctx* h, const void* dev_src, void* user_dst, size_t bytes, int ptr_kind) {
+    if (!bytes) return ERASOR_OK;
+    CK(cudaMemcpyAsync(user_dst, dev_src, bytes, ptr_kind == ERASOR_PTR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+    return ERASOR_OK;
+}
+
+float status_value(uint8_t code) {
+    switch (code) {
+        case ST_MERGE: return ERASOR_STATUS_MERGE_BINS;
+        case ST_MAP_HIGH: return ERASOR_STATUS_MAP_IS_HIGHER;
+        case ST_BLOCKED: return ERASOR_STATUS_BLOCKED;
+        case ST_CURR_HIGH: return ERASOR_STATUS_CURR_IS_HIGHER;
+        default: return ERASOR_STATUS_LITTLE_NUM;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int erasor_abi_version(void) { return ERASOR_B200_ABI_VERSION; }
+
+const char* erasor_last_error(erasor_handle_t h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int erasor_create(const erasor_params_t* params, int device, erasor_handle_t* out) {
+    if (!params || !out) { g_create_error = "null argument"; return ERASOR_E_INVALID; }
+    *out = nullptr;
+    const erasor_params_t& p = *params;
+    const long long Bll = (long long)p.num_rings * (long long)p.num_sectors;
+    if (p.num_rings < 1 || p.num_sectors < 1 || Bll > 65534) { g_create_error = "num_rings*num_sectors must be in [1, 65534]"; return ERASOR_E_INVALID; }
+    if (p.version != 2 && p.version != 3) { g_create_error = "Other version is not implemented!"; return ERASOR_E_INVALID; }   // OfflineMapUpdater.cpp:274
+    if (p.sort_mode != 1) { g_create_error = "sort_mode must be 1 (stable z order)"; return ERASOR_E_UNSUPPORTED; }
+    if (p.gf_iter > kMaxIter) { g_create_error = "gf_iter above the tap capacity (8)"; return ERASOR_E_UNSUPPORTED; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                         " (this library has no CPU path)";
+        return ERASOR_E_CUDA;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "bad device index"; return ERASOR_E_INVALID; }
+    erasor_ctx* h = new erasor_ctx();
+    h->p = p; h->device = device; h->B = (int)Bll;
+    std::string terr;
+    if (build_bin_tables(p, h->tables, terr) != 0) { g_create_error = terr; delete h; return ERASOR_E_INVALID; }
+    auto fail = [&](const char* what, cudaError_t ce) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(ce);
+        erasor_destroy(h);
+        return ERASOR_E_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
+    h->sm_count = prop.multiProcessorCount;
+    const size_t need = std::max(k1_smem_bytes(p.num_rings, h->B), k3_smem_bytes(h->B));
+    if (need > (size_t)prop.sharedMemPerBlockOptin) {
+        g_create_error = "num_rings*num_sectors too large for the per-CTA shared-memory bin table";
+        erasor_destroy(h);
+        return ERASOR_E_UNSUPPORTED;
+    }
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    const size_t rb = sizeof(double) * h->tables.ring_thr.size(), sb = sizeof(SectorBoundary) * h->tables.sec_pos.size();
+    if ((e = h->d_ring.ensure(rb)) != cudaSuccess || (e = h->d_pos.ensure(sb)) != cudaSuccess || (e = h->d_neg.ensure(sb)) != cudaSuccess ||
+        (e = h->d_fence.ensure(sizeof(unsigned long long) * 4)) != cudaSuccess)
+        return fail("cudaMalloc", e);
+    if ((e = cudaMemcpy(h->d_ring.p, h->tables.ring_thr.data(), rb, cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy", e);
+    if ((e = cudaMemcpy(h->d_pos.p, h->tables.sec_pos.data(), sb, cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy", e);
+    if ((e = cudaMemcpy(h->d_neg.p, h->tables.sec_neg.data(), sb, cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy", e);
+    if ((e = cudaMemset(h->d_fence.p, 0, sizeof(unsigned long long) * 4)) != cudaSuccess) return fail("cudaMemset", e);
+    h->view = h->tables.view(h->d_ring.as<double>(), h->d_pos.as<SectorBoundary>(), h->d_neg.as<SectorBoundary>());
+    *out = h;
+    return ERASOR_OK;
+}
+
+void erasor_destroy(erasor_handle_t h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    drain_timers(h);
+    DevBuf* bufs[] = {&h->d_ring, &h->d_pos, &h->d_neg, &h->d_map_in, &h->d_qry_in, &h->d_bin_map, &h->d_bin_qry, &h->d_chunks,
+                      &h->d_chunk_range, &h->d_frame_off, &h->d_chcnt, &h->d_zmin, &h->d_zmax, &h->d_cnt, &h->d_dst_start, &h->d_status,
+                      &h->d_action, &h->d_flag_slot, &h->d_nflag, &h->d_recs, &h->d_nrecs, &h->d_frame_rej, &h->d_map_sorted, &h->d_map_src,
+                      &h->d_qry_sorted, &h->d_qry_src, &h->d_part, &h->d_scratch, &h->d_keep, &h->d_ground, &h->d_arranged, &h->d_map_rej,
+                      &h->d_curr_rej, &h->d_jobs, &h->d_out_sizes, &h->d_k5tmp, &h->d_fence, &h->d_vox, &h->d_vox_cnt, &h->d_vox_start,
+                      &h->d_vox_scratch};
+    for (DevBuf* b : bufs) b->release();
+    h->h_stage.release();
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+void* erasor_stream(erasor_handle_t h) { return h ? (void*)h->stream : nullptr; }
+
+int erasor_synchronize(erasor_handle_t h) {
+    if (!h) return ERASOR_E_INVALID;
+    CK(cudaStreamSynchronize(h->stream));
+    return ERASOR_OK;
+}
+
+double erasor_get_max_range(erasor_handle_t h) { return h ? h->p.max_range : 0.0; }
+
+int erasor_set_inputs(erasor_handle_t h, const float* map_voi_xyzi, size_t n_map, const float* query_voi_xyzi, size_t n_query, int ptr_kind) {
+    if (!h) return ERASOR_E_INVALID;
+    if ((n_map && !map_voi_xyzi) || (n_query && !query_voi_xyzi)) { h->err = "null cloud"; return ERASOR_E_INVALID; }
+    CK(cudaSetDevice(h->device));
+    h->stage = 0;
+    const uint64_t mo[2] = {0, n_map}, qo[2] = {0, n_query};
+    int rc = prepare_batch(h, mo, qo, 1, 0);
+    if (rc) return rc;
+    if ((rc = stage_inputs(h, map_voi_xyzi, query_voi_xyzi, ptr_kind))) return rc;
+    if ((rc = run_k1(h))) return rc;
+    h->stage = 1;
+    return ERASOR_OK;
+}
+
+int erasor_compare(erasor_handle_t h, int version, int frame) {
+    (void)frame;   // the reference uses it only for a commented-out csv dump (erasor.cpp:341-343)
+    if (!h) return ERASOR_E_INVALID;
+    if (h->stage < 1) { h->err = "erasor_compare before erasor_set_inputs"; return ERASOR_E_STATE; }
+    if (version != 2 && version != 3) { h->err = "Other version is not implemented!"; return ERASOR_E_INVALID; }
+    CK(cudaSetDevice(h->device));
+    const int B = h->B;
+    const size_t NM = h->NM, NQ = h->NQ;
+    CK(h->d_keep.ensure(std::max<size_t>(NM, 1)));
+    CK(h->d_ground.ensure(std::max<size_t>(NM, 1)));
+    CK(cudaMemsetAsync(h->d_keep.p, 1, std::max<size_t>(NM, 1), h->stream));
+    CK(cudaMemsetAsync(h->d_ground.p, 0, std::max<size_t>(NM, 1), h->stream));
+    int rc = run_compare(h, version, 0, h->d_keep.as<uint8_t>(), h->d_ground.as<uint8_t>());
+    if (rc) return rc;
+    const bool vox = (version == 3) && !h->p.skip_voxelize;
+    if (vox) {
+        CK(h->d_vox.ensure(sizeof(float4) * (NM + NQ + 1)));
+        CK(h->d_vox_cnt.ensure(sizeof(uint32_t) * (size_t)B));
+        CK(h->d_vox_start.ensure(sizeof(uint32_t) * (size_t)B));
+        CK(h->d_vox_scratch.ensure((size_t)32 * (NM + NQ + 1) + 64));
+        Scope s(h, 4);
+        h->launches++;
+        CK(launch_k4b(h->stream, (float)h->p.map_voxel_size, B, h->d_recs.as<FlagRec>(), h->d_nrecs.as<uint32_t>(), h->rec_capacity,
+                      h->d_cnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>(), h->d_qry_sorted.as<float4>(), h->d_part.as<float4>(),
+                      h->d_vox.as<float4>(), h->d_vox_cnt.as<uint32_t>(), h->d_vox_start.as<uint32_t>(),
+                      h->d_vox_scratch.as<unsigned char>(), h->sm_count * 3));
+    }
+    // output assembly
+    CK(h->d_arranged.ensure(sizeof(float4) * (2 * NM + NQ + 1)));
+    CK(h->d_map_rej.ensure(sizeof(float4) * std::max<size_t>(NM, 1)));
+    CK(h->d_curr_rej.ensure(sizeof(float4) * std::max<size_t>(NQ, 1)));
+    CK(h->d_jobs.ensure(sizeof(CopyJob) * 5 * (size_t)B));
+    CK(h->d_out_sizes.ensure(sizeof(uint32_t) * 8));
+    CK(h->d_k5tmp.ensure(sizeof(uint32_t) * 3 * (size_t)(B + 1)));
+    {
+        Scope s(h, 5);
+        h->launches += 2;
+        CK(launch_k5(h->stream, B, version, h->p.skip_voxelize, h->d_cnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>(), h->d_action.as<uint8_t>(),
+                     h->d_flag_slot.as<uint32_t>(), h->d_recs.as<FlagRec>(), h->d_nrecs.as<uint32_t>(),
+                     vox ? h->d_vox_cnt.as<uint32_t>() : nullptr, vox ? h->d_vox_start.as<uint32_t>() : nullptr,
+                     h->d_map_sorted.as<float4>(), h->d_qry_sorted.as<float4>(), h->d_part.as<float4>(),
+                     vox ? h->d_vox.as<float4>() : nullptr, h->d_arranged.as<float4>(),
+                     h->d_map_rej.as<float4>(), h->d_curr_rej.as<float4>(), h->d_jobs.as<CopyJob>(), h->d_out_sizes.as<uint32_t>(),
+                     h->d_k5tmp.as<uint32_t>(), h->sm_count * 4));
+    }
+    CK(cudaMemcpyAsync(h->out_sizes, h->d_out_sizes.p, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&h->complement_start, h->d_dst_start.as<uint32_t>() + B, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&h->n_recs_host, h->d_nrecs.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->stage = 2;
+    return ERASOR_OK;
+}
+
+int erasor_get_output_sizes(erasor_handle_t h, size_t* n_arranged, size_t* n_complement, size_t* n_map_rejected, size_t* n_curr_rejected) {
+    if (!h) return ERASOR_E_INVALID;
+    if (h->stage < 2) { h->err = "no compare result"; return ERASOR_E_STATE; }
+    if (n_arranged) *n_arranged = h->out_sizes[0];
+    if (n_complement) *n_complement = h->out_sizes[1];
+    if (n_map_rejected) *n_map_rejected = h->out_sizes[2];
+    if (n_curr_rejected) *n_curr_rejected = h->out_sizes[3];
+    return ERASOR_OK;
+}
+
+int erasor_get_static_estimate(erasor_handle_t h, float* arranged_xyzi, size_t cap_arranged, size_t* n_arranged,
+                               float* complement_xyzi, size_t cap_complement, size_t* n_complement, int ptr_kind) {
+    if (!h) return ERASOR_E_INVALID;
+    if (h->stage < 2) { h->err = "erasor_get_static_estimate before erasor_compare"; return ERASOR_E_STATE; }
+    if (n_arranged) *n_arranged = h->out_sizes[0];
+    if (n_complement) *n_complement = h->out_sizes[1];
+    if ((arranged_xyzi && cap_arranged < h->out_sizes[0]) || (complement_xyzi && cap_complement < h->out_sizes[1])) {
+        h->err = "output buffer too small"; return ERASOR_E_CAPACITY;
+    }
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if (arranged_xyzi && (rc = copy_out(h, h->d_arranged.p, arranged_xyzi, sizeof(float4) * h->out_sizes[0], ptr_kind))) return rc;
+    if (complement_xyzi && (rc = copy_out(h, h->d_map_sorted.as<float4>() + h->complement_start, complement_xyzi,
+                                          sizeof(float4) * h->out_sizes[1], ptr_kind))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return ERASOR_OK;
+}
+
+int erasor_get_outliers(erasor_handle_t h, float* map_rejected_xyzi, size_t cap_map, size_t* n_map_rejected,
+                        float* curr_rejected_xyzi, size_t cap_curr, size_t* n_curr_rejected, int ptr_kind) {
+    if (!h) return ERASOR_E_INVALID;
+    if (h->stage < 2) { h->err = "erasor_get_outliers before erasor_compare"; return ERASOR_E_STATE; }
+    if (n_map_rejected) *n_map_rejected = h->out_sizes[2];
+    if (n_curr_rejected) *n_curr_rejected = h->out_sizes[3];
+    if ((map_rejected_xyzi && cap_map < h->out_sizes[2]) || (curr_rejected_xyzi && cap_curr < h->out_sizes[3])) {
+        h->err = "output buffer too small"; return ERASOR_E_CAPACITY;
+    }
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if (map_rejected_xyzi && (rc = copy_out(h, h->d_map_rej.p, map_rejected_xyzi, sizeof(float4) * h->out_sizes[2], ptr_kind))) return rc;
+    if (curr_rejected_xyzi && (rc = copy_out(h, h->d_curr_rej.p, curr_rejected_xyzi, sizeof(float4) * h->out_sizes[3], ptr_kind))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return ERASOR_OK;
+}
+
+int erasor_get_bins(erasor_handle_t h, int which_cloud, int32_t* bin_of_point, float* min_h, float* max_h, uint32_t* count) {
+    if (!h) return ERASOR_E_INVALID;
+    if (h->stage < 1 || h->F != 1) { h->err = "erasor_get_bins needs a single-frame erasor_set_inputs"; return ERASOR_E_STATE; }
+    if (which_cloud != 0 && which_cloud != 1) { h->err = "which_cloud"; return ERASOR_E_INVALID; }
+    CK(cudaSetDevice(h->device));
+    const int B = h->B;
+    const size_t n = which_cloud == 0 ? h->NM : h->NQ;
+    CK(cudaStreamSynchronize(h->stream));
+    if (bin_of_point && n) {
+        std::vector<uint16_t> tmp(n);
+        CK(cudaMemcpy(tmp.data(), which_cloud == 0 ? h->d_bin_map.p : h->d_bin_qry.p, sizeof(uint16_t) * n, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; ++i) bin_of_point[i] = tmp[i] == kNoBin16 ? -1 : (int32_t)tmp[i];
+    }
+    if (min_h || max_h || count) {
+        std::vector<uint32_t> mn(B), mx(B);
+        CK(cudaMemcpy(mn.data(), h->d_zmin.as<uint32_t>() + (size_t)which_cloud * B, sizeof(uint32_t) * B, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(mx.data(), h->d_zmax.as<uint32_t>() + (size_t)which_cloud * B, sizeof(uint32_t) * B, cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> c(B, 0);
+        if (h->stage >= 2) {
+            CK(cudaMemcpy(c.data(), h->d_cnt.as<uint32_t>() + (size_t)which_cloud * (B + 1), sizeof(uint32_t) * B, cudaMemcpyDeviceToHost));
+        } else {
+            // before compare the totals are still per-chunk rows: sum them here (parity tap only)
+            const uint32_t c0 = which_cloud == 0 ? 0 : h->n_chunks_map;
+            const uint32_t c1 = which_cloud == 0 ? h->n_chunks_map : h->n_chunks_map + h->n_chunks_qry;
+            std::vector<uint32_t> rows((size_t)(c1 - c0) * (B + 1));
+            if (!rows.empty())
+                CK(cudaMemcpy(rows.data(), h->d_chcnt.as<uint32_t>() + (size_t)c0 * (B + 1), sizeof(uint32_t) * rows.size(), cudaMemcpyDeviceToHost));
+            for (uint32_t k = 0; k < c1 - c0; ++k)
+                for (int b = 0; b < B; ++b) c[b] += rows[(size_t)k * (B + 1) + b];
+        }
+        const float nan = std::numeric_limits<float>::quiet_NaN();
+        for (int b = 0; b < B; ++b) {
+            const bool empty = mn[b] == 0xFFFFFFFFu && mx[b] == 0u;
+            if (min_h) min_h[b] = empty ? nan : ordered_to_float(mn[b]);
+            if (max_h) max_h[b] = empty ? nan : ordered_to_float(mx[b]);
+            if (count) count[b] = c[b];
+        }
+    }
+    return ERASOR_OK;
+}
+
+int erasor_get_status(erasor_handle_t h, float* status) {
+    if (!h || !status) return ERASOR_E_INVALID;
+    if (h->stage < 2) { h->err = "erasor_get_status before erasor_compare"; return ERASOR_E_STATE; }
+    CK(cudaSetDevice(h->device));
+    std::vector<uint8_t> st(h->B);
+    CK(cudaMemcpy(st.data(), h->d_status.p, h->B, cudaMemcpyDeviceToHost));
+    for (int b = 0; b < h->B; ++b) status[b] = status_value(st[b]);
+    return ERASOR_OK;
+}
+
+int erasor_get_planes(erasor_handle_t h, int32_t* bin_ids, int32_t* n_points, int32_t* n_seeds, double* lpr_height,
+                      double* normal_d, int32_t* n_ground, size_t* n_planes) {
+    if (!h || !n_planes) return ERASOR_E_INVALID;
+    if (h->stage < 2) { h->err = "erasor_get_planes before erasor_compare"; return ERASOR_E_STATE; }
+    CK(cudaSetDevice(h->device));
+    const size_t n = h->n_recs_host, cap = *n_planes;
+    *n_planes = n;
+    if (!bin_ids && !n_points && !n_seeds && !lpr_height && !normal_d && !n_ground) return ERASOR_OK;
+    if (cap < n) { h->err = "plane buffer too small"; return ERASOR_E_CAPACITY; }
+    std::vector<FlagRec> recs(n);
+    if (n) CK(cudaMemcpy(recs.data(), h->d_recs.p, sizeof(FlagRec) * n, cudaMemcpyDeviceToHost));
+    const int it = std::min(h->p.gf_iter, kMaxIter);
+    for (size_t i = 0; i < n; ++i) {
+        const FlagRec& r = recs[i];   // single frame: record index == slot == processing order (bin order)
+        if (bin_ids) bin_ids[i] = (int32_t)r.bin;
+        if (n_points) n_points[i] = (int32_t)r.n_points;
+        if (n_seeds) n_seeds[i] = (int32_t)r.n_seeds;
+        if (lpr_height) lpr_height[i] = r.lpr_height;
+        for (int k = 0; k < it; ++k) {
+            if (normal_d) for (int c = 0; c < 4; ++c) normal_d[(i * it + k) * 4 + c] = r.normal_d[k][c];
+            if (n_ground) n_ground[i * it + k] = (int32_t)r.n_ground[k];
+        }
+    }
+    return ERASOR_OK;
+}
+
+int erasor_get_static_mask(erasor_handle_t h, uint8_t* keep_map, uint8_t* is_ground) {
+    if (!h) return ERASOR_E_INVALID;
+    if (h->stage < 2) { h->err = "erasor_get_static_mask before erasor_compare"; return ERASOR_E_STATE; }
+    CK(cudaSetDevice(h->device));
+    if (keep_map && h->NM) CK(cudaMemcpy(keep_map, h->d_keep.p, h->NM, cudaMemcpyDeviceToHost));
+    if (is_ground && h->NM) CK(cudaMemcpy(is_ground, h->d_ground.p, h->NM, cudaMemcpyDeviceToHost));
+    return ERASOR_OK;
+}
+
+int erasor_get_fence_counts(erasor_handle_t h, uint64_t* negzero_points, uint64_t* empty_plane_fits, uint64_t* ambiguous_sector) {
+    if (!h) return ERASOR_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    unsigned long long v[4];
+    CK(cudaMemcpy(v, h->d_fence.p, sizeof(v), cudaMemcpyDeviceToHost));
+    if (negzero_points) *negzero_points = v[0];
+    if (empty_plane_fits) *empty_plane_fits = v[1];
+    if (ambiguous_sector) *ambiguous_sector = v[2];
+    return ERASOR_OK;
+}
+
+int erasor_process_frames(erasor_handle_t h, const float* map_xyzi, const uint64_t* map_offsets, const float* query_xyzi,
+                          const uint64_t* query_offsets, int n_frames, uint8_t* keep_mask, int ptr_kind) {
+    if (!h || !map_offsets || !query_offsets || !keep_mask) { if (h) h->err = "null argument"; return ERASOR_E_INVALID; }
+    CK(cudaSetDevice(h->device));
+    h->stage = 0;
+    int rc = prepare_batch(h, map_offsets, query_offsets, n_frames, 1);
+    if (rc) return rc;
+    if ((h->NM && !map_xyzi) || (h->NQ && !query_xyzi)) { h->err = "null cloud"; return ERASOR_E_INVALID; }
+    {
+        Scope whole(h, 0);
+        if ((rc = stage_inputs(h, map_xyzi, query_xyzi, ptr_kind))) return rc;
+        uint8_t* d_keep = keep_mask;
+        if (ptr_kind != ERASOR_PTR_DEVICE) {
+            CK(h->d_keep.ensure(std::max<size_t>(h->NM, 1)));
+            d_keep = h->d_keep.as<uint8_t>();
+        }
+        if (h->NM) CK(cudaMemsetAsync(d_keep, 1, h->NM, h->stream));
+        if ((rc = run_k1(h))) return rc;
+        if ((rc = run_compare(h, h->p.version, 1, d_keep, nullptr))) return rc;
+        if (ptr_kind != ERASOR_PTR_DEVICE && h->NM)
+            CK(cudaMemcpyAsync(keep_mask, d_keep, h->NM, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(&h->n_recs_host, h->d_nrecs.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->n_recs_host > h->rec_capacity) { h->err = "flagged-bin records overflowed; split the batch"; return ERASOR_E_CAPACITY; }
+    return ERASOR_OK;
+}
+
+int erasor_get_frame_stats(erasor_handle_t h, uint32_t* n_flagged_bins, uint32_t* n_rejected_points) {
+    if (!h) return ERASOR_E_INVALID;
+    if (h->F <= 0) { h->err = "no batch has run"; return ERASOR_E_STATE; }
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    if (n_flagged_bins) CK(cudaMemcpy(n_flagged_bins, h->d_nflag.p, sizeof(uint32_t) * h->F, cudaMemcpyDeviceToHost));
+    if (n_rejected_points) CK(cudaMemcpy(n_rejected_points, h->d_frame_rej.p, sizeof(uint32_t) * h->F, cudaMemcpyDeviceToHost));
+    return ERASOR_OK;
+}
+
+uint64_t erasor_kernel_launch_count(erasor_handle_t h) { return h ? h->launches : 0; }
+
+int erasor_reset_kernel_times(erasor_handle_t h, int enable_timing) {
+    if (!h) return ERASOR_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    drain_timers(h);
+    for (auto& t : h->timers) { t.total_ms = 0; t.launches = 0; }
+    h->timing = enable_timing != 0;
+    return ERASOR_OK;
+}
+
+int erasor_get_kernel_time_ms(erasor_handle_t h, int kernel_id, double* total_ms, uint64_t* launches) {
+    if (!h || kernel_id < 0 || kernel_id >= kNumTimers) return ERASOR_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    drain_timers(h);
+    if (total_ms) *total_ms = h->timers[kernel_id].total_ms;
+    if (launches) *launches = h->timers[kernel_id].launches;
+    return ERASOR_OK;
+}
+
+}  // extern "C"

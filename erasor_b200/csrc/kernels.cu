@@ -1,0 +1,1085 @@
+// kernels.cu -- the sm_100a kernels of the R-POD -> Scan Ratio Test -> R-GPF path.
+//
+//   K1  k1_rpod_bin     polar index + per-bin min/max z and count, query and map in one launch
+//                       (ERASOR::voi2r_pod x2 + pt2r_pod, reference erasor.cpp:87-144)
+//   K3  k3_srt          per-bin totals, Scan Ratio Test, status / action codes, v3 neighbour pass,
+//                       scatter offsets, flagged-bin work list
+//                       (compare_vois_and_revert_ground[_w_block], erasor.cpp:346-427, 448-563, 573-595)
+//   K2  k2_scatter      stable counting-sort scatter of points into bin order (the per-bin
+//                       pcl::PointCloud push_back, erasor.cpp:89) -- all bins or flagged bins only
+//   K4  k4_rgpf         Region-wise Ground Plane Fitting per flagged bin
+//                       (extract_ground / extract_initial_seeds_ / estimate_plane_, erasor.cpp:183-294)
+//   K5  k5_plan/k5_copy output assembly in the reference's order (r_pod2pc, get_static_estimate,
+//                       get_outliers, erasor.cpp:309-327, 612-626)
+//
+// No tensor cores anywhere: the path is bandwidth-bound indexing and reduction.
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cstdint>
+
+#include "device_types.h"
+#include "kernels.h"
+
+namespace erasor {
+
+#define FULL_MASK 0xFFFFFFFFu
+
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+// ============================================================================================
+// K1
+// ============================================================================================
+// Warp-level pre-aggregation of (bin, z) into the CTA's shared tables.  Input clouds are spatially
+// coherent (voxel-key order, or bin order after the first frame), so most warps hold 1-3 runs of equal bins:
+// one REDUX pair + three shared atomics per run instead of three atomics per point.
+__device__ __forceinline__ void k1_aggregate(int key, uint32_t zenc, int lane, uint32_t* s_cnt, uint32_t* s_mn, uint32_t* s_mx, int B) {
+    // key: bin id in [0,B), B for "not binned", -2 for an out-of-range lane
+    const int key0 = __shfl_sync(FULL_MASK, key, 0);
+    if (__all_sync(FULL_MASK, key == key0)) {
+        if (key0 >= 0) {
+            if (key0 < B) {
+                const uint32_t mn = __reduce_min_sync(FULL_MASK, zenc);
+                const uint32_t mx = __reduce_max_sync(FULL_MASK, zenc);
+                if (lane == 0) {
+                    atomicMin(&s_mn[key0], mn);
+                    atomicMax(&s_mx[key0], mx);
+                    atomicAdd(&s_cnt[key0], 32u);
+                }
+            } else if (lane == 0) {
+                atomicAdd(&s_cnt[B], 32u);
+            }
+        }
+        return;
+    }
+    const int      prev  = __shfl_up_sync(FULL_MASK, key, 1);
+    const bool     head  = (lane == 0) || (key != prev);
+    const unsigned heads = __ballot_sync(FULL_MASK, head);
+    const unsigned le    = (2u << lane) - 1u;                 // lanes <= lane (lane 31: 0 - 1 = all ones)
+    const int      h     = 31 - __clz(heads & le);
+    const unsigned above = heads & ~le;
+    const int      e     = above ? (__ffs(above) - 1) : 32;
+    const unsigned run   = ((e == 32) ? FULL_MASK : ((1u << e) - 1u)) & ~((1u << h) - 1u);
+    if (key >= 0) {
+        if (key < B) {
+            const uint32_t mn = __reduce_min_sync(run, zenc);
+            const uint32_t mx = __reduce_max_sync(run, zenc);
+            if (lane == h) {
+                atomicMin(&s_mn[key], mn);
+                atomicMax(&s_mx[key], mx);
+                atomicAdd(&s_cnt[key], (uint32_t)(e - h));
+            }
+        } else if (lane == h) {
+            atomicAdd(&s_cnt[B], (uint32_t)(e - h));
+        }
+    }
+}
+
+template <int THREADS, int UNROLL>
+__global__ void __launch_bounds__(THREADS)
+k1_rpod_bin(BinTablesView T, const float4* __restrict__ map_pts, const float4* __restrict__ qry_pts,
+            const ChunkDesc* __restrict__ chunks, uint16_t* __restrict__ bin_map, uint16_t* __restrict__ bin_qry,
+            uint32_t* __restrict__ ch_cnt, uint32_t* __restrict__ zmin, uint32_t* __restrict__ zmax,
+            int B, int F, unsigned long long* __restrict__ fence) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double*   s_ring = reinterpret_cast<double*>(smem_raw);
+    uint32_t* s_cnt  = reinterpret_cast<uint32_t*>(s_ring + ((T.R + 2) & ~1));
+    uint32_t* s_mn   = s_cnt + (B + 1);
+    uint32_t* s_mx   = s_mn + B;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = THREADS / 32;
+    const ChunkDesc cd = chunks[blockIdx.x];
+
+    for (int i = tid; i <= T.R; i += THREADS) s_ring[i] = T.ring_thr[i];
+    for (int i = tid; i <= B; i += THREADS) s_cnt[i] = 0u;
+    for (int i = tid; i < B; i += THREADS) { s_mn[i] = 0xFFFFFFFFu; s_mx[i] = 0u; }
+    __syncthreads();
+
+    const float4* __restrict__ src = (cd.cloud == 0 ? map_pts : qry_pts) + cd.begin;
+    uint16_t* __restrict__     dst = (cd.cloud == 0 ? bin_map : bin_qry) + cd.begin;
+    BinFenceCounters fc{0u, 0u, 0u};
+
+    for (uint32_t base = warp * (32u * UNROLL); base < cd.len; base += NW * (32u * UNROLL)) {
+        float4 p[UNROLL];
+        bool   ok[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const uint32_t i = base + u * 32u + lane;
+            ok[u] = i < cd.len;
+            p[u]  = ok[u] ? ld_stream_f4(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const uint32_t i = base + u * 32u + lane;
+            int key = -2;
+            if (ok[u]) {
+                const int b = bin_of_point(T, s_ring, p[u].x, p[u].y, p[u].z, &fc);
+                dst[i] = (b < 0) ? kNoBin16 : (uint16_t)b;
+                key    = (b < 0) ? B : b;
+            }
+            k1_aggregate(key, float_to_ordered(p[u].z), lane, s_cnt, s_mn, s_mx, B);
+        }
+    }
+    __syncthreads();
+
+    // flush: dense per-chunk counts (consumed by K3's prefix and K2's stable scatter), min/max by RED to the frame table
+    uint32_t* __restrict__ row = ch_cnt + (size_t)blockIdx.x * (B + 1);
+    const size_t ft = ((size_t)cd.cloud * F + cd.frame) * B;
+    for (int i = tid; i <= B; i += THREADS) {
+        const uint32_t c = s_cnt[i];
+        row[i] = c;
+        if (c != 0u && i < B) {
+            atomicMin(&zmin[ft + i], s_mn[i]);
+            atomicMax(&zmax[ft + i], s_mx[i]);
+        }
+    }
+    if (fc.negzero) atomicAdd(&fence[0], (unsigned long long)fc.negzero);
+    if (fc.ambiguous) atomicAdd(&fence[2], (unsigned long long)fc.ambiguous);
+    if (fc.slow) atomicAdd(&fence[3], (unsigned long long)fc.slow);
+}
+
+size_t k1_smem_bytes(int R, int B) {
+    return sizeof(double) * ((R + 2) & ~1) + sizeof(uint32_t) * ((size_t)(B + 1) + 2 * (size_t)B);
+}
+
+cudaError_t launch_k1(cudaStream_t st, const BinTablesView& T, const float4* map_pts, const float4* qry_pts,
+                      const ChunkDesc* chunks, int n_chunks, uint16_t* bin_map, uint16_t* bin_qry, uint32_t* ch_cnt,
+                      uint32_t* zmin, uint32_t* zmax, int B, int F, unsigned long long* fence) {
+    if (n_chunks == 0) return cudaSuccess;
+    constexpr int THREADS = 256, UNROLL = 4;
+    const size_t smem = k1_smem_bytes(T.R, B);
+    auto kern = k1_rpod_bin<THREADS, UNROLL>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, B, F, fence);
+    return cudaGetLastError();
+}
+
+// ============================================================================================
+// K3
+// ============================================================================================
+// exclusive scan of in[0..n) into out[0..n) (may alias); every thread returns the total.
+__device__ uint32_t block_excl_scan(const uint32_t* in, uint32_t* out, int n, uint32_t* s_part /*[34]*/) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    const int seg = (n + nt - 1) / nt;
+    const int b0 = min(n, tid * seg), b1 = min(n, b0 + seg);
+    uint32_t sum = 0;
+    for (int i = b0; i < b1; ++i) sum += in[i];
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(FULL_MASK, incl, o);
+        if (lane >= o) incl += v;
+    }
+    __syncthreads();                     // s_part may still be read from a previous call
+    if (lane == 31) s_part[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = lane < nw ? s_part[lane] : 0u;
+        uint32_t wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(FULL_MASK, wi, o);
+            if (lane >= o) wi += v;
+        }
+        if (lane < nw) s_part[lane] = wi - w;
+        if (lane == 31) s_part[33] = wi;
+    }
+    __syncthreads();
+    uint32_t run = s_part[warp] + incl - sum;
+    const uint32_t total = s_part[33];
+    for (int i = b0; i < b1; ++i) {
+        const uint32_t v = in[i];
+        out[i] = run;
+        run += v;
+    }
+    __syncthreads();
+    return total;
+}
+
+__device__ __forceinline__ double std_min_d(double a, double b) { return (b < a) ? b : a; }   // std::min, NaN-faithful (App. B-4)
+
+__global__ void __launch_bounds__(1024)
+k3_srt(SrtParams P, int F, const uint32_t* __restrict__ chunk_range /*[2][F+1]*/, uint32_t* __restrict__ ch_cnt,
+       const uint32_t* __restrict__ zmin, const uint32_t* __restrict__ zmax, const uint32_t* __restrict__ frame_off /*[2][F+1]*/,
+       uint32_t* __restrict__ cnt /*[2][F][B+1]*/, uint32_t* __restrict__ dst_start /*[2][F][B+2]*/,
+       uint8_t* __restrict__ status /*[F][B]*/, uint8_t* __restrict__ action /*[F][B]*/,
+       uint32_t* __restrict__ flag_slot /*[F][B]*/, uint32_t* __restrict__ n_flagged /*[F]*/,
+       FlagRec* __restrict__ recs, uint32_t* __restrict__ n_recs, uint32_t rec_capacity) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int B = P.B, R = P.R, S = P.S;
+    uint32_t* s_sz   = reinterpret_cast<uint32_t*>(smem_raw);          // B+2
+    uint32_t* s_part = s_sz + (B + 2);                                 // 34
+    uint8_t*  s_st   = reinterpret_cast<uint8_t*>(s_part + 34);        // B
+    __shared__ uint32_t s_rec_base;
+    const int f = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+
+    // phase 0: totals per bin and in-place exclusive prefix over the frame's chunks (both clouds)
+    for (int c = 0; c < 2; ++c) {
+        const uint32_t c0 = chunk_range[c * (F + 1) + f], c1 = chunk_range[c * (F + 1) + f + 1];
+        for (int b = tid; b <= B; b += nt) {
+            uint32_t run = 0;
+            for (uint32_t k = c0; k < c1; ++k) {
+                uint32_t* p = ch_cnt + (size_t)k * (B + 1) + b;
+                const uint32_t v = *p;
+                *p = run;
+                run += v;
+            }
+            cnt[((size_t)c * F + f) * (B + 1) + b] = run;
+        }
+    }
+    __syncthreads();
+    const uint32_t* cm = cnt + ((size_t)0 * F + f) * (B + 1);
+    const uint32_t* cq = cnt + ((size_t)1 * F + f) * (B + 1);
+    const uint32_t* mnm = zmin + ((size_t)0 * F + f) * B; const uint32_t* mxm = zmax + ((size_t)0 * F + f) * B;
+    const uint32_t* mnq = zmin + ((size_t)1 * F + f) * B; const uint32_t* mxq = zmax + ((size_t)1 * F + f) * B;
+    uint8_t* st_out  = status + (size_t)f * B;
+    uint8_t* act_out = action + (size_t)f * B;
+    const bool min_pts_neg = P.minimum_num_pts < 0;     // size_t < int comparison wraps (App. B-9)
+
+    if (P.version == 3) {
+        // pass 1 (erasor.cpp:448-486)
+        for (int b = tid; b < B; b += nt) {
+            const uint32_t mc = cm[b], qc = cq[b];
+            uint8_t st = ST_LITTLE;
+            if (mc != 0u && !(min_pts_neg || qc < (uint32_t)P.minimum_num_pts)) {
+                // empty curr bin keeps the reference's sentinels: max_h = -INF, min_h = +INF (erasor.h:3)
+                const double map_dh  = (double)ordered_to_float(mxm[b]) - (double)ordered_to_float(mnm[b]);
+                const double curr_dh = (qc != 0u) ? (double)ordered_to_float(mxq[b]) - (double)ordered_to_float(mnq[b])
+                                                  : (-10000000000000.0 - 10000000000000.0);
+                const double ratio   = std_min_d(map_dh / curr_dh, curr_dh / map_dh);
+                if (qc != 0u) {
+                    if (ratio < P.scan_ratio_threshold) {
+                        if (map_dh >= curr_dh) st = ST_MAP_HIGH;
+                        else if (map_dh <= curr_dh) st = ST_CURR_HIGH;
+                    } else {
+                        st = ST_MERGE;
+                    }
+                }
+            }
+            s_st[b] = st;
+        }
+        __syncthreads();
+        // pass 2 (erasor.cpp:493-563)
+        for (int b = tid; b < B; b += nt) {
+            const int theta = b / R, r = b - theta * R;
+            const uint8_t s1 = s_st[b];
+            uint8_t st = s1, act = ACT_MAP;
+            if (s1 == ST_MAP_HIGH) {
+                const double map_dh = (double)ordered_to_float(mxm[b]) - (double)ordered_to_float(mnm[b]);
+                if (map_dh > 0.5) act = ACT_FLAG; else st = ST_LITTLE;       // NOT_ASSIGNED == 0.0 == LITTLE_NUM
+            } else if (s1 == ST_MERGE) {
+                // is_dynamic_obj_close(r_pod_selected, r, theta, 1, 1), wrap with num_rings (sic, App. B-2)
+                bool close = false;
+                for (int j = theta - 1; j <= theta + 1; ++j) {
+                    int tj = j;
+                    if (j < 0) tj = j + R; else if (j >= S) tj = j - R;
+                    if (tj < 0 || tj >= S) continue;                       // fence: reference indexes out of range here
+                    const int r0 = max(0, r - 1), r1 = min(r + 1, R - 1);
+                    for (int rr = r0; rr <= r1; ++rr) {
+                        if (rr == r && tj == theta) continue;
+                        if (s_st[tj * R + rr] == ST_CURR_HIGH) close = true;
+                    }
+                }
+                st = close ? ST_BLOCKED : ST_MERGE;
+            }
+            st_out[b] = st; act_out[b] = act;
+        }
+    } else {
+        // version 2 (erasor.cpp:346-427)
+        for (int b = tid; b < B; b += nt) {
+            const uint32_t mc = cm[b], qc = cq[b];
+            uint8_t st = ST_LITTLE, act = ACT_NONE;
+            if (min_pts_neg || qc < (uint32_t)P.minimum_num_pts) {
+                act = ACT_MAP; st = ST_LITTLE;
+            } else if (qc != 0u && mc != 0u) {
+                const double map_max = (double)ordered_to_float(mxm[b]), cur_max = (double)ordered_to_float(mxq[b]);
+                const double map_dh  = map_max - (double)ordered_to_float(mnm[b]);
+                const double curr_dh = cur_max - (double)ordered_to_float(mnq[b]);
+                const double ratio   = std_min_d(map_dh / curr_dh, curr_dh / map_dh);
+                if (ratio < P.scan_ratio_threshold) {
+                    if (map_dh >= curr_dh) {
+                        st = ST_MAP_HIGH;
+                        act = (map_max > P.th_bin_max_h) ? ACT_FLAG : ACT_MAP;
+                    } else if (map_dh <= curr_dh) {
+                        st = ST_CURR_HIGH;
+                        act = ACT_MAP;
+                        if (cur_max > P.th_bin_max_h) act |= ACT_CURR_REJECTED_BIT;
+                    }
+                } else {
+                    st = ST_MERGE; act = ACT_MERGE;
+                }
+            } else if (qc != 0u) {
+                act = ACT_CURR;
+            } else if (mc != 0u) {
+                act = ACT_MAP;
+            }
+            st_out[b] = st; act_out[b] = act;
+        }
+    }
+    __syncthreads();
+
+    // flagged bins, in bin order
+    uint32_t* slot_out = flag_slot + (size_t)f * B;
+    for (int b = tid; b < B; b += nt) s_sz[b] = ((act_out[b] & 0x0F) == ACT_FLAG) ? 1u : 0u;
+    __syncthreads();
+    const uint32_t nflag = block_excl_scan(s_sz, s_sz, B, s_part);
+    if (tid == 0) {
+        n_flagged[f] = nflag;
+        s_rec_base   = nflag ? atomicAdd(n_recs, nflag) : 0u;
+    }
+    for (int b = tid; b < B; b += nt) slot_out[b] = ((act_out[b] & 0x0F) == ACT_FLAG) ? s_sz[b] : kSkip;
+    __syncthreads();
+    const uint32_t rec_base = s_rec_base;
+
+    // scatter offsets, map cloud: every bin + complement (mode 0) or flagged bins only (mode 1)
+    uint32_t* dsm = dst_start + ((size_t)0 * F + f) * (B + 2);
+    uint32_t* dsq = dst_start + ((size_t)1 * F + f) * (B + 2);
+    for (int b = tid; b <= B; b += nt) {
+        const bool take = (P.scatter_mode == 0) || (b < B && (act_out[b] & 0x0F) == ACT_FLAG);
+        s_sz[b] = take ? cm[b] : 0u;
+    }
+    __syncthreads();
+    const uint32_t tot_m = block_excl_scan(s_sz, s_sz, B + 1, s_part);
+    for (int b = tid; b <= B; b += nt) {
+        const bool take = (P.scatter_mode == 0) || (b < B && (act_out[b] & 0x0F) == ACT_FLAG);
+        dsm[b] = take ? s_sz[b] : kSkip;
+    }
+    if (tid == 0) dsm[B + 1] = tot_m;
+    __syncthreads();
+    // flagged-bin records for K4
+    for (int b = tid; b < B; b += nt) {
+        if ((act_out[b] & 0x0F) == ACT_FLAG) {
+            const uint32_t slot = slot_out[b];
+            const uint32_t ri   = rec_base + slot;
+            if (ri < rec_capacity) {
+                FlagRec& rc = recs[ri];
+                rc.frame = f; rc.bin = b; rc.slot = slot; rc.n_points = cm[b];
+                rc.src_begin = frame_off[f] + s_sz[b];
+                rc.n_seeds = 0; rc.n_empty_fits = 0; rc.n_ground_final = 0; rc.lpr_height = 0.0;
+            }
+        }
+    }
+    __syncthreads();
+    // query cloud: all binned points (mode 0) or nothing (mode 1)
+    for (int b = tid; b <= B; b += nt) s_sz[b] = (P.scatter_mode == 0 && b < B) ? cq[b] : 0u;
+    __syncthreads();
+    const uint32_t tot_q = block_excl_scan(s_sz, s_sz, B + 1, s_part);
+    for (int b = tid; b <= B; b += nt) dsq[b] = (P.scatter_mode == 0 && b < B) ? s_sz[b] : kSkip;
+    if (tid == 0) dsq[B + 1] = tot_q;
+}
+
+size_t k3_smem_bytes(int B) { return sizeof(uint32_t) * ((size_t)B + 2 + 34) + (size_t)B + 16; }
+
+cudaError_t launch_k3(cudaStream_t st, const SrtParams& P, int F, const uint32_t* chunk_range, uint32_t* ch_cnt,
+                      const uint32_t* zmin, const uint32_t* zmax, const uint32_t* frame_off, uint32_t* cnt, uint32_t* dst_start,
+                      uint8_t* status, uint8_t* action, uint32_t* flag_slot, uint32_t* n_flagged, FlagRec* recs,
+                      uint32_t* n_recs, uint32_t rec_capacity) {
+    const size_t smem = k3_smem_bytes(P.B);
+    cudaError_t e = cudaFuncSetAttribute(k3_srt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k3_srt<<<F, 1024, smem, st>>>(P, F, chunk_range, ch_cnt, zmin, zmax, frame_off, cnt, dst_start, status, action,
+                                  flag_slot, n_flagged, recs, n_recs, rec_capacity);
+    return cudaGetLastError();
+}
+
+// ============================================================================================
+// K2
+// ============================================================================================
+// One warp per chunk.  Stable: a point's slot is  dst_start[bin] + (points of the bin in earlier chunks of the
+// frame) + (points of the bin earlier in this chunk), the last term kept as a running offset in shared memory
+// and advanced 32 points at a time with match_any ranks.
+__global__ void __launch_bounds__(32)
+k2_scatter(const ChunkDesc* __restrict__ chunks, uint32_t chunk_base, int F, const uint16_t* __restrict__ bin_ids,
+           const float4* __restrict__ pts, const uint32_t* __restrict__ ch_cnt, const uint32_t* __restrict__ dst_start /*[F][B+2] of this cloud*/,
+           float4* __restrict__ out_pts, uint32_t* __restrict__ out_src, int B) {
+    extern __shared__ uint32_t s_off[];   // B+1
+    const int lane = threadIdx.x;
+    const uint32_t row = chunk_base + blockIdx.x;
+    const ChunkDesc cd = chunks[row];
+    const uint32_t* ds   = dst_start + (size_t)cd.frame * (B + 2);
+    const uint32_t* pref = ch_cnt + (size_t)row * (B + 1);
+    for (int b = lane; b <= B; b += 32) {
+        const uint32_t d = ds[b];
+        const uint32_t v = (d == kSkip) ? kSkip : d + pref[b];
+        s_off[b] = v;
+    }
+    __syncwarp();
+    const uint32_t local0 = cd.begin - cd.frame_begin;
+    for (uint32_t i0 = 0; i0 < cd.len; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const bool valid = i < cd.len;
+        const unsigned vmask = __ballot_sync(FULL_MASK, valid);
+        if (valid) {
+            const uint16_t id  = bin_ids[cd.begin + i];
+            const int      key = (id == kNoBin16) ? B : (int)id;
+            const unsigned peers = __match_any_sync(vmask, key);
+            const uint32_t base  = s_off[key];
+            __syncwarp(vmask);
+            const int leader = __ffs(peers) - 1;
+            if (base != kSkip) {
+                const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+                if (lane == leader) s_off[key] = base + __popc(peers);
+                const float4 p = pts[cd.begin + i];
+                const size_t o = (size_t)cd.frame_begin + base + rank;
+                out_pts[o] = p;
+                out_src[o] = local0 + i;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_k2(cudaStream_t st, const ChunkDesc* chunks, uint32_t chunk_base, uint32_t n_chunks, int F,
+                      const uint16_t* bin_ids, const float4* pts, const uint32_t* ch_cnt, const uint32_t* dst_start,
+                      float4* out_pts, uint32_t* out_src, int B) {
+    if (n_chunks == 0) return cudaSuccess;
+    const size_t smem = sizeof(uint32_t) * ((size_t)B + 1);
+    cudaError_t e = cudaFuncSetAttribute(k2_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k2_scatter<<<n_chunks, 32, smem, st>>>(chunks, chunk_base, F, bin_ids, pts, ch_cnt, dst_start, out_pts, out_src, B);
+    return cudaGetLastError();
+}
+
+// ============================================================================================
+// K4  R-GPF
+// ============================================================================================
+// All float arithmetic below is spelled with round-to-nearest intrinsics so that nvcc cannot contract
+// a*b+c into an FMA: the reference's x86-64 build (no -march, CMakeLists.txt:3-4) has none, and the
+// unshifted covariance of PCL<=1.10 is so ill-conditioned that a single different rounding moves the plane.
+#define FM(a, b) __fmul_rn((a), (b))
+#define FA(a, b) __fadd_rn((a), (b))
+#define FS(a, b) __fsub_rn((a), (b))
+#define FD(a, b) __fdiv_rn((a), (b))
+#define FSQ(a)   __fsqrt_rn((a))
+
+struct Rot { float c, s; };
+
+__device__ __forceinline__ void apply_rot(float* x, int incx, float* y, int incy, int n, Rot j) {
+    if (j.c == 1.0f && j.s == 0.0f) return;
+    for (int i = 0; i < n; ++i) {
+        const float xi = x[i * incx], yi = y[i * incy];
+        x[i * incx] = FA(FM(j.c, xi), FM(j.s, yi));
+        y[i * incy] = FA(FM(-j.s, xi), FM(j.c, yi));
+    }
+}
+
+// Eigen 3.3 JacobiSVD<MatrixXf>(A, ComputeFullU) on a 3x3 (two-sided Jacobi, no preconditioner); returns U.col(2).
+__device__ __noinline__ void jacobi_svd_normal(const float* A, float* normal) {
+    const float precision = 2.0f * FLT_EPSILON, considerAsZero = FLT_MIN;
+    float W[9], U[9], sv[3];
+    float scale = 0.0f;
+    for (int i = 0; i < 9; ++i) { const float a = fabsf(A[i]); scale = (a > scale) ? a : scale; }
+    if (scale == 0.0f) scale = 1.0f;
+    for (int i = 0; i < 9; ++i) W[i] = FD(A[i], scale);
+    for (int i = 0; i < 9; ++i) U[i] = (i % 4 == 0) ? 1.0f : 0.0f;
+    float maxDiag = 0.0f;
+    for (int i = 0; i < 3; ++i) { const float a = fabsf(W[i * 4]); maxDiag = (a > maxDiag) ? a : maxDiag; }
+    bool finished = false;
+    int sweeps = 0;
+    while (!finished && sweeps < 1000) {
+        finished = true;
+        ++sweeps;
+        for (int p = 1; p < 3; ++p) {
+            for (int q = 0; q < p; ++q) {
+                const float pm = FM(precision, maxDiag);
+                const float threshold = (considerAsZero < pm) ? pm : considerAsZero;     // std::max(considerAsZero, pm)
+                if (fabsf(W[p * 3 + q]) > threshold || fabsf(W[q * 3 + p]) > threshold) {
+                    finished = false;
+                    // real_2x2_jacobi_svd
+                    float m[4] = {W[p * 3 + p], W[p * 3 + q], W[q * 3 + p], W[q * 3 + q]};
+                    Rot rot1;
+                    const float t = FA(m[0], m[3]);
+                    const float d = FS(m[2], m[1]);
+                    if (fabsf(d) < FLT_MIN) {
+                        rot1.s = 0.0f; rot1.c = 1.0f;
+                    } else {
+                        const float u   = FD(t, d);
+                        const float tmp = FSQ(FA(1.0f, FM(u, u)));
+                        rot1.s = FD(1.0f, tmp);
+                        rot1.c = FD(u, tmp);
+                    }
+                    apply_rot(&m[0], 1, &m[2], 1, 2, rot1);
+                    Rot jr;
+                    {   // makeJacobi(m00, m01, m11)
+                        const float x = m[0], y = m[1], z = m[3];
+                        const float deno = FM(2.0f, fabsf(y));
+                        if (deno < FLT_MIN) {
+                            jr.c = 1.0f; jr.s = 0.0f;
+                        } else {
+                            const float tau = FD(FS(x, z), deno);
+                            const float w   = FSQ(FA(FM(tau, tau), 1.0f));
+                            float tt;
+                            if (tau > 0.0f) tt = FD(1.0f, FA(tau, w));
+                            else            tt = FD(1.0f, FS(tau, w));
+                            const float sign_t = tt > 0.0f ? 1.0f : -1.0f;
+                            const float n = FD(1.0f, FSQ(FA(FM(tt, tt), 1.0f)));
+                            jr.s = FM(FM(FM(-sign_t, FD(y, fabsf(y))), fabsf(tt)), n);
+                            jr.c = n;
+                        }
+                    }
+                    // j_left = rot1 * j_right.transpose()
+                    const Rot jrt{jr.c, -jr.s};
+                    const Rot jl{FS(FM(rot1.c, jrt.c), FM(rot1.s, jrt.s)), FA(FM(rot1.c, jrt.s), FM(rot1.s, jrt.c))};
+                    apply_rot(&W[p * 3], 1, &W[q * 3], 1, 3, jl);      // W.applyOnTheLeft(p,q,j_left)
+                    apply_rot(&U[p], 3, &U[q], 3, 3, jl);              // U.applyOnTheRight(p,q,j_left.transpose())
+                    apply_rot(&W[p], 3, &W[q], 3, 3, jrt);             // W.applyOnTheRight(p,q,j_right)
+                    const float a = fabsf(W[p * 4]), b = fabsf(W[q * 4]);
+                    const float ab = (a < b) ? b : a;
+                    maxDiag = (maxDiag < ab) ? ab : maxDiag;
+                }
+            }
+        }
+    }
+    for (int i = 0; i < 3; ++i) {
+        const float a = W[i * 4];
+        sv[i] = fabsf(a);
+        if (a < 0.0f) for (int r = 0; r < 3; ++r) U[r * 3 + i] = -U[r * 3 + i];
+    }
+    for (int i = 0; i < 3; ++i) sv[i] = FM(sv[i], scale);
+    for (int i = 0; i < 3; ++i) {
+        int pos = 0;
+        float mx = sv[i];
+        for (int k = i + 1; k < 3; ++k) if (sv[k] > mx) { mx = sv[k]; pos = k - i; }
+        if (mx == 0.0f) break;
+        if (pos) {
+            pos += i;
+            const float tsv = sv[i]; sv[i] = sv[pos]; sv[pos] = tsv;
+            for (int r = 0; r < 3; ++r) { const float tu = U[r * 3 + pos]; U[r * 3 + pos] = U[r * 3 + i]; U[r * 3 + i] = tu; }
+        }
+    }
+    normal[0] = U[2]; normal[1] = U[5]; normal[2] = U[8];
+}
+
+constexpr int K4_THREADS = 256;
+constexpr uint32_t K4_PAD = 0xFFFFFFFFu;
+
+// "a sorts after b" for the (z, source position) order -- std::stable_sort by z of the bin's points
+__device__ __forceinline__ bool k4_after(const float* Z, uint32_t a, uint32_t b) {
+    if (a == K4_PAD) return b != K4_PAD;
+    if (b == K4_PAD) return false;
+    const float za = Z[a], zb = Z[b];
+    return (za > zb) || (za == zb && a > b);
+}
+
+// ordered compaction of indices i in [0,n) with pred(i) into out[]; returns count (all threads).
+template <class Pred>
+__device__ uint32_t k4_compact(uint32_t n, uint32_t* out, uint32_t* s_warp /*[K4_THREADS/32 + 1]*/, Pred pred) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = K4_THREADS / 32;
+    uint32_t total = 0;
+    for (uint32_t base = 0; base < n; base += K4_THREADS) {
+        const uint32_t i = base + tid;
+        const bool g = (i < n) && pred(i);
+        const unsigned bal = __ballot_sync(FULL_MASK, g);
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t off = total;
+        for (int w = 0; w < warp; ++w) off += s_warp[w];
+        uint32_t round = 0;
+        for (int w = 0; w < NW; ++w) round += s_warp[w];
+        if (g) out[off + __popc(bal & ((1u << lane) - 1u))] = i;
+        total += round;
+        __syncthreads();
+    }
+    return total;
+}
+
+__global__ void __launch_bounds__(K4_THREADS)
+k4_rgpf(GpfParams P, FlagRec* __restrict__ recs, const uint32_t* __restrict__ n_recs, uint32_t rec_capacity,
+        const float4* __restrict__ sorted_pts, const uint32_t* __restrict__ sorted_src,
+        const uint32_t* __restrict__ frame_off /*map cloud [F+1]*/, float4* __restrict__ part_pts /*nullable*/,
+        uint8_t* __restrict__ keep_mask /*nullable*/, uint8_t* __restrict__ ground_mask /*nullable*/,
+        uint32_t* __restrict__ frame_rejected /*[F] nullable*/,
+        unsigned char* __restrict__ gscratch, uint32_t smem_cap_points, unsigned long long* __restrict__ fence) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float    s_normal[3];
+    __shared__ double   s_thd;
+    __shared__ double   s_seed_thr;
+    __shared__ uint32_t s_warp[K4_THREADS / 32 + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t nrec = min(*n_recs, rec_capacity);
+
+    for (uint32_t w = blockIdx.x; w < nrec; w += gridDim.x) {
+        FlagRec& rc = recs[w];
+        const uint32_t n = rc.n_points, src_begin = rc.src_begin;
+        uint32_t np2 = 1; while (np2 < n) np2 <<= 1;
+        // working arrays: shared memory if the bin fits, else this bin's private slice of the global scratch
+        unsigned char* base = (n <= smem_cap_points) ? smem_raw : (gscratch + (size_t)src_begin * 24u);
+        float*    X   = reinterpret_cast<float*>(base);
+        float*    Y   = X + n;
+        float*    Z   = Y + n;
+        uint32_t* ORD = reinterpret_cast<uint32_t*>(Z + n);
+        uint8_t*  FLG = reinterpret_cast<uint8_t*>(ORD + np2);
+
+        for (uint32_t i = tid; i < n; i += K4_THREADS) {
+            const float4 p = sorted_pts[src_begin + i];
+            X[i] = p.x; Y[i] = p.y; Z[i] = p.z; ORD[i] = i;
+        }
+        for (uint32_t i = n + tid; i < np2; i += K4_THREADS) ORD[i] = K4_PAD;
+        __syncthreads();
+
+        // bitonic sort of ORD by (z, position)
+        for (uint32_t k = 2; k <= np2; k <<= 1) {
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                for (uint32_t t = tid; t < (np2 >> 1); t += K4_THREADS) {
+                    const uint32_t i = ((t / j) * (j << 1)) + (t % j);
+                    const uint32_t l = i + j;
+                    const uint32_t a = ORD[i], b = ORD[l];
+                    const bool asc = ((i & k) == 0);
+                    const bool sw  = asc ? k4_after(Z, a, b) : k4_after(Z, b, a);
+                    if (sw) { ORD[i] = b; ORD[l] = a; }
+                }
+                __syncthreads();
+            }
+        }
+
+        // extract_initial_seeds_ (erasor.cpp:204-231)
+        if (tid == 0) {
+            double sum = 0.0;
+            int    cnt = 0;
+            if (P.num_lowest_pts >= 0) {
+                for (uint32_t i = (uint32_t)P.num_lowest_pts; i < n && cnt < P.num_lpr; ++i) { sum += (double)Z[ORD[i]]; ++cnt; }
+            }
+            const double lpr = cnt != 0 ? sum / cnt : 0.0;
+            rc.lpr_height = lpr;
+            s_seed_thr    = lpr + P.th_seeds;
+        }
+        __syncthreads();
+        const double seed_thr = s_seed_thr;
+        // seeds = sorted prefix with z < lpr + th_seeds; count it
+        uint32_t m;
+        {
+            uint32_t c = 0;
+            for (uint32_t i = tid; i < n; i += K4_THREADS) c += ((double)Z[ORD[i]] < seed_thr) ? 1u : 0u;
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL_MASK, c, o);
+            if (lane == 0) s_warp[warp] = c;
+            __syncthreads();
+            m = 0;
+            for (int ww = 0; ww < K4_THREADS / 32; ++ww) m += s_warp[ww];
+            __syncthreads();
+        }
+        if (tid == 0) rc.n_seeds = m;
+
+        uint32_t n_empty = 0;
+        for (int it = 0; it < P.iters; ++it) {
+            // ---- estimate_plane_ over ORD[0..m) (erasor.cpp:183-198) ----
+            if (warp == 0) {
+                // pcl::computeMeanAndCovarianceMatrix: nine float accumulators walked in list order; lane L owns accu[L]
+                const float* pa = (lane == 0 || lane == 1 || lane == 2 || lane == 6) ? X : (lane == 3 || lane == 4 || lane == 7) ? Y : Z;
+                const float* pb = (lane == 0) ? X : (lane == 1 || lane == 3) ? Y : Z;
+                const bool   unit_b = lane >= 6;
+                float Ka = 0.0f, Kb = 0.0f, K0 = 0.0f, K1 = 0.0f, K2 = 0.0f;
+                if (P.cov_mode == 1 && m > 0) {
+                    const uint32_t f0 = ORD[0];
+                    K0 = X[f0]; K1 = Y[f0]; K2 = Z[f0];
+                    Ka = pa[f0]; Kb = unit_b ? 0.0f : pb[f0];
+                }
+                float acc = 0.0f;
+                if (lane < 9) {
+                    uint32_t i = 0;
+                    for (; i + 4 <= m; i += 4) {
+                        const uint32_t i0 = ORD[i], i1 = ORD[i + 1], i2 = ORD[i + 2], i3 = ORD[i + 3];
+                        const float a0 = FS(pa[i0], Ka), a1 = FS(pa[i1], Ka), a2 = FS(pa[i2], Ka), a3 = FS(pa[i3], Ka);
+                        const float b0 = unit_b ? 1.0f : FS(pb[i0], Kb), b1 = unit_b ? 1.0f : FS(pb[i1], Kb);
+                        const float b2 = unit_b ? 1.0f : FS(pb[i2], Kb), b3 = unit_b ? 1.0f : FS(pb[i3], Kb);
+                        const float q0 = FM(a0, b0), q1 = FM(a1, b1), q2 = FM(a2, b2), q3 = FM(a3, b3);
+                        acc = FA(acc, q0); acc = FA(acc, q1); acc = FA(acc, q2); acc = FA(acc, q3);
+                    }
+                    for (; i < m; ++i) {
+                        const uint32_t i0 = ORD[i];
+                        const float a0 = FS(pa[i0], Ka);
+                        const float b0 = unit_b ? 1.0f : FS(pb[i0], Kb);
+                        acc = FA(acc, FM(a0, b0));
+                    }
+                    if (m != 0) acc = FD(acc, (float)m);
+                }
+                float a[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) a[k] = __shfl_sync(FULL_MASK, acc, k);
+                if (lane == 0) {
+                    float cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, mean[3] = {0, 0, 0};
+                    if (m != 0) {
+                        mean[0] = (P.cov_mode == 1) ? FA(a[6], K0) : a[6];
+                        mean[1] = (P.cov_mode == 1) ? FA(a[7], K1) : a[7];
+                        mean[2] = (P.cov_mode == 1) ? FA(a[8], K2) : a[8];
+                        cov[0] = FS(a[0], FM(a[6], a[6]));
+                        cov[1] = FS(a[1], FM(a[6], a[7]));
+                        cov[2] = FS(a[2], FM(a[6], a[8]));
+                        cov[4] = FS(a[3], FM(a[7], a[7]));
+                        cov[5] = FS(a[4], FM(a[7], a[8]));
+                        cov[8] = FS(a[5], FM(a[8], a[8]));
+                        cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
+                    }
+                    float nrm[3];
+                    jacobi_svd_normal(cov, nrm);
+                    const float dot = FA(FA(FM(nrm[0], mean[0]), FM(nrm[1], mean[1])), FM(nrm[2], mean[2]));
+                    const double d  = (double)(-dot);
+                    s_normal[0] = nrm[0]; s_normal[1] = nrm[1]; s_normal[2] = nrm[2];
+                    s_thd = P.th_dist - d;
+                    if (it < kMaxIter) {
+                        rc.normal_d[it][0] = nrm[0]; rc.normal_d[it][1] = nrm[1]; rc.normal_d[it][2] = nrm[2]; rc.normal_d[it][3] = d;
+                    }
+                }
+            }
+            if (m == 0) ++n_empty;
+            __syncthreads();
+            const float n0 = s_normal[0], n1 = s_normal[1], n2 = s_normal[2];
+            const double thd = s_thd;
+            // ---- classify every point of the bin in source order (erasor.cpp:265-281) ----
+            for (uint32_t i = tid; i < n; i += K4_THREADS) {
+                const float r = FA(FA(FM(X[i], n0), FM(Y[i], n1)), FM(Z[i], n2));
+                FLG[i] = ((double)r < thd) ? 1 : 0;
+            }
+            __syncthreads();
+            m = k4_compact(n, ORD, s_warp, [&](uint32_t i) { return FLG[i] != 0; });
+            if (tid == 0 && it < kMaxIter) rc.n_ground[it] = m;
+        }
+        // with gf_iter == 0 the reference returns the seeds as ground and nothing as outliers... but then
+        // non_ground_pc_ is never filled; FLG must mirror "ground = seeds" in that case.
+        if (P.iters <= 0) {
+            for (uint32_t i = tid; i < n; i += K4_THREADS) FLG[i] = 0;
+            __syncthreads();
+            for (uint32_t i = tid; i < m; i += K4_THREADS) FLG[ORD[i]] = 1;
+            __syncthreads();
+        }
+        if (tid == 0) { rc.n_ground_final = m; rc.n_empty_fits = n_empty; }
+        if (tid == 0 && n_empty) atomicAdd(&fence[1], (unsigned long long)n_empty);
+
+        // ---- outputs ----
+        const uint32_t fbase = frame_off[rc.frame];
+        if (keep_mask || ground_mask) {
+            for (uint32_t i = tid; i < n; i += K4_THREADS) {
+                const uint32_t s = sorted_src[src_begin + i];
+                if (keep_mask && !FLG[i] && P.iters > 0) keep_mask[fbase + s] = 0;
+                if (ground_mask && FLG[i]) ground_mask[fbase + s] = 1;
+            }
+        }
+        if (frame_rejected && tid == 0 && P.iters > 0) atomicAdd(&frame_rejected[rc.frame], n - m);
+        if (part_pts) {
+            // partitioned copy of the bin: [ground, source order][non-ground, source order]
+            for (uint32_t i = tid; i < m; i += K4_THREADS) part_pts[src_begin + i] = sorted_pts[src_begin + ORD[i]];
+            __syncthreads();
+            const uint32_t m2 = k4_compact(n, ORD, s_warp, [&](uint32_t i) { return FLG[i] == 0; });
+            for (uint32_t i = tid; i < m2; i += K4_THREADS) part_pts[src_begin + m + i] = sorted_pts[src_begin + ORD[i]];
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_k4(cudaStream_t st, const GpfParams& P, FlagRec* recs, const uint32_t* n_recs, uint32_t rec_capacity,
+                      const float4* sorted_pts, const uint32_t* sorted_src, const uint32_t* frame_off, float4* part_pts,
+                      uint8_t* keep_mask, uint8_t* ground_mask, uint32_t* frame_rejected, unsigned char* gscratch,
+                      int grid, unsigned long long* fence) {
+    constexpr uint32_t SMEM_BYTES = 72 * 1024;
+    // 12 n (xyz) + 4 np2 (<= 8n, order) + n (flags) <= 21 n + 16
+    const uint32_t cap = (SMEM_BYTES - 64) / 21u;
+    cudaError_t e = cudaFuncSetAttribute(k4_rgpf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    k4_rgpf<<<grid, K4_THREADS, SMEM_BYTES, st>>>(P, recs, n_recs, rec_capacity, sorted_pts, sorted_src, frame_off, part_pts,
+                                                  keep_mask, ground_mask, frame_rejected, gscratch, cap, fence);
+    return cudaGetLastError();
+}
+
+// ============================================================================================
+// K4b  in-bin voxelize_preserving_labels of version 3 (erasor.cpp:526-528, erasor_utils.cpp:80-114):
+//      pcl::VoxelGrid (centroid of all four fields per 'map_voxel_size' voxel, ascending voxel key) followed by
+//      an exact 1-NN into the un-voxelised points to restore an un-averaged label in `intensity`.
+//      Input of a flagged bin = bin_curr's points (source order) then the R-GPF ground points (source order).
+//      Unpinned third-party choices, fixed the same way in the oracle: members of one voxel are summed in input
+//      order; 1-NN ties go to the lowest input index.
+// ============================================================================================
+__device__ __forceinline__ bool k4b_after(const uint32_t* KEY, uint32_t a, uint32_t b) {
+    if (a == K4_PAD) return b != K4_PAD;
+    if (b == K4_PAD) return false;
+    const uint32_t ka = KEY[a], kb = KEY[b];
+    return (ka > kb) || (ka == kb && a > b);
+}
+
+__global__ void __launch_bounds__(K4_THREADS)
+k4b_voxelize(float leaf_f, int B, const FlagRec* __restrict__ recs, const uint32_t* __restrict__ n_recs, uint32_t rec_capacity,
+             const uint32_t* __restrict__ cnt /*[2][1][B+1]*/, const uint32_t* __restrict__ dst_start /*[2][1][B+2]*/,
+             const float4* __restrict__ qry_sorted, const float4* __restrict__ part_pts,
+             float4* __restrict__ vox_pts, uint32_t* __restrict__ vox_cnt, uint32_t* __restrict__ vox_start,
+             unsigned char* __restrict__ gscratch, uint32_t smem_cap_points) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_warp[K4_THREADS / 32 + 1];
+    __shared__ float    s_red[6][K4_THREADS / 32];
+    __shared__ float    s_minmax[6];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t nrec = min(*n_recs, rec_capacity);
+    const float inv = FD(1.0f, leaf_f);
+    const uint32_t* cq  = cnt + (B + 1);
+    const uint32_t* dsm = dst_start;
+    const uint32_t* dsq = dst_start + (B + 2);
+
+    for (uint32_t w = blockIdx.x; w < nrec; w += gridDim.x) {
+        const FlagRec& rc = recs[w];
+        const uint32_t b = rc.bin, qc = cq[b], ng = rc.n_ground_final, n = qc + ng;
+        const uint32_t region = dsq[b] + dsm[b];
+        uint32_t np2 = 1; while (np2 < n) np2 <<= 1;
+        unsigned char* base = (n <= smem_cap_points) ? smem_raw : (gscratch + (size_t)region * 32u);
+        float*    X   = reinterpret_cast<float*>(base);
+        float*    Y   = X + n;
+        float*    Z   = Y + n;
+        float*    I   = Z + n;
+        uint32_t* KEY = reinterpret_cast<uint32_t*>(I + n);
+        uint32_t* VST = KEY + n;                  // voxel start positions (<= n entries) + 1
+        uint32_t* ORD = VST + n + 1;              // np2
+        if (n == 0) {
+            if (tid == 0) { vox_cnt[rc.slot] = 0u; vox_start[rc.slot] = region; }
+            continue;
+        }
+        for (uint32_t i = tid; i < n; i += K4_THREADS) {
+            const float4 p = (i < qc) ? qry_sorted[dsq[b] + i] : part_pts[rc.src_begin + (i - qc)];
+            X[i] = p.x; Y[i] = p.y; Z[i] = p.z; I[i] = p.w; ORD[i] = i;
+        }
+        for (uint32_t i = n + tid; i < np2; i += K4_THREADS) ORD[i] = K4_PAD;
+        __syncthreads();
+        // getMinMax3D
+        {
+            float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+            for (uint32_t i = tid; i < n; i += K4_THREADS) {
+                mn[0] = fminf(mn[0], X[i]); mx[0] = fmaxf(mx[0], X[i]);
+                mn[1] = fminf(mn[1], Y[i]); mx[1] = fmaxf(mx[1], Y[i]);
+                mn[2] = fminf(mn[2], Z[i]); mx[2] = fmaxf(mx[2], Z[i]);
+            }
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                for (int o = 16; o > 0; o >>= 1) {
+                    mn[a] = fminf(mn[a], __shfl_xor_sync(FULL_MASK, mn[a], o));
+                    mx[a] = fmaxf(mx[a], __shfl_xor_sync(FULL_MASK, mx[a], o));
+                }
+                if (lane == 0) { s_red[a][warp] = mn[a]; s_red[3 + a][warp] = mx[a]; }
+            }
+            __syncthreads();
+            if (tid < 6) {
+                float v = s_red[tid][0];
+                for (int ww = 1; ww < K4_THREADS / 32; ++ww) v = (tid < 3) ? fminf(v, s_red[tid][ww]) : fmaxf(v, s_red[tid][ww]);
+                s_minmax[tid] = v;
+            }
+            __syncthreads();
+        }
+        const float mnx = s_minmax[0], mny = s_minmax[1], mnz = s_minmax[2];
+        const float mxx = s_minmax[3], mxy = s_minmax[4], mxz = s_minmax[5];
+        const long long dx = (long long)FM(FS(mxx, mnx), inv) + 1;
+        const long long dy = (long long)FM(FS(mxy, mny), inv) + 1;
+        const long long dz = (long long)FM(FS(mxz, mnz), inv) + 1;
+        const bool overflow = (dx * dy * dz) > 2147483647LL;
+        uint32_t nv;
+        float4* out = vox_pts + region;
+        if (overflow) {
+            // "Leaf size is too small for the input dataset": output = input
+            nv = n;
+            for (uint32_t i = tid; i < n; i += K4_THREADS) out[i] = make_float4(X[i], Y[i], Z[i], I[i]);
+            __syncthreads();
+        } else {
+            const int mb0 = (int)floorf(FM(mnx, inv)), mb1 = (int)floorf(FM(mny, inv)), mb2 = (int)floorf(FM(mnz, inv));
+            const int Mb0 = (int)floorf(FM(mxx, inv)), Mb1 = (int)floorf(FM(mxy, inv));
+            const int div0 = Mb0 - mb0 + 1, div1 = Mb1 - mb1 + 1;
+            const int mul1 = div0, mul2 = div0 * div1;
+            for (uint32_t i = tid; i < n; i += K4_THREADS) {
+                const int ijk0 = (int)FS(floorf(FM(X[i], inv)), (float)mb0);
+                const int ijk1 = (int)FS(floorf(FM(Y[i], inv)), (float)mb1);
+                const int ijk2 = (int)FS(floorf(FM(Z[i], inv)), (float)mb2);
+                KEY[i] = (uint32_t)(ijk0 + ijk1 * mul1 + ijk2 * mul2);
+            }
+            __syncthreads();
+            for (uint32_t k = 2; k <= np2; k <<= 1) {
+                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                    for (uint32_t t = tid; t < (np2 >> 1); t += K4_THREADS) {
+                        const uint32_t i = ((t / j) * (j << 1)) + (t % j);
+                        const uint32_t l = i + j;
+                        const uint32_t a = ORD[i], c = ORD[l];
+                        const bool asc = ((i & k) == 0);
+                        const bool sw  = asc ? k4b_after(KEY, a, c) : k4b_after(KEY, c, a);
+                        if (sw) { ORD[i] = c; ORD[l] = a; }
+                    }
+                    __syncthreads();
+                }
+            }
+            // voxel heads in sorted order
+            nv = k4_compact(n, VST, s_warp, [&](uint32_t i) { return i == 0 || KEY[ORD[i]] != KEY[ORD[i - 1]]; });
+            if (tid == 0) VST[nv] = n;
+            __syncthreads();
+            // centroids: float sums in member order, divided by float(count)  (pcl::CentroidPoint)
+            for (uint32_t v = tid; v < nv; v += K4_THREADS) {
+                const uint32_t a = VST[v], e = VST[v + 1];
+                float sx = 0.0f, sy = 0.0f, sz = 0.0f, si = 0.0f;
+                for (uint32_t li = a; li < e; ++li) {
+                    const uint32_t q = ORD[li];
+                    sx = FA(sx, X[q]); sy = FA(sy, Y[q]); sz = FA(sz, Z[q]); si = FA(si, I[q]);
+                }
+                const float cn = (float)(e - a);
+                out[v] = make_float4(FD(sx, cn), FD(sy, cn), FD(sz, cn), FD(si, cn));
+            }
+            __syncthreads();
+        }
+        // exact 1-NN of every centroid into the bin's points; copy that point's intensity
+        for (uint32_t v = tid; v < nv; v += K4_THREADS) {
+            const float4 c = out[v];
+            float best = __int_as_float(0x7f800000);
+            uint32_t bi = 0;
+            for (uint32_t i = 0; i < n; ++i) {
+                const float ddx = FS(c.x, X[i]), ddy = FS(c.y, Y[i]), ddz = FS(c.z, Z[i]);
+                const float d = FA(FA(FM(ddx, ddx), FM(ddy, ddy)), FM(ddz, ddz));
+                if (d < best) { best = d; bi = i; }
+            }
+            out[v].w = I[bi];
+        }
+        if (tid == 0) { vox_cnt[rc.slot] = nv; vox_start[rc.slot] = region; }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_k4b(cudaStream_t st, float leaf, int B, const FlagRec* recs, const uint32_t* n_recs, uint32_t rec_capacity,
+                       const uint32_t* cnt, const uint32_t* dst_start, const float4* qry_sorted, const float4* part_pts,
+                       float4* vox_pts, uint32_t* vox_cnt, uint32_t* vox_start, unsigned char* gscratch, int grid) {
+    constexpr uint32_t SMEM_BYTES = 72 * 1024;
+    // 16 n (xyzi) + 4 n (key) + 4 (n+1) (voxel starts) + 4 np2 (<= 8n) <= 32 n + 16
+    const uint32_t cap = (SMEM_BYTES - 64) / 32u;
+    cudaError_t e = cudaFuncSetAttribute(k4b_voxelize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    k4b_voxelize<<<grid, K4_THREADS, SMEM_BYTES, st>>>(leaf, B, recs, n_recs, rec_capacity, cnt, dst_start, qry_sorted, part_pts,
+                                                       vox_pts, vox_cnt, vox_start, gscratch, cap);
+    return cudaGetLastError();
+}
+
+// ============================================================================================
+// K5  output assembly (single-frame cloud mode)
+// ============================================================================================
+// Plan: sizes per bin -> exclusive scans -> copy jobs.  Job slots: [0,2B) selected bins (two sources each),
+// [2B,3B) ground_viz per flagged slot, [3B,4B) map_rejected per flagged slot, [4B,5B) curr_rejected per bin.
+__global__ void __launch_bounds__(1024)
+k5_plan(int B, int version, int skip_voxelize, const uint32_t* __restrict__ cnt /*[2][1][B+1]*/,
+        const uint32_t* __restrict__ dst_start /*[2][1][B+2]*/, const uint8_t* __restrict__ action,
+        const uint32_t* __restrict__ flag_slot, const FlagRec* __restrict__ recs, const uint32_t* __restrict__ n_recs,
+        const uint32_t* __restrict__ vox_cnt /*per slot, nullable*/, const uint32_t* __restrict__ vox_start /*per slot*/,
+        const float4* __restrict__ map_sorted, const float4* __restrict__ qry_sorted, const float4* __restrict__ part_pts,
+        const float4* __restrict__ vox_pts,
+        float4* __restrict__ arranged, float4* __restrict__ map_rej, float4* __restrict__ curr_rej,
+        CopyJob* __restrict__ jobs, uint32_t* __restrict__ out_sizes /*[4]: arranged, complement, map_rej, curr_rej*/,
+        uint32_t* __restrict__ tmp /*[3*(B+1)]*/) {
+    __shared__ uint32_t s_part[34];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t* cm = cnt;
+    const uint32_t* cq = cnt + (B + 1);
+    const uint32_t* dsm = dst_start;
+    const uint32_t* dsq = dst_start + (B + 2);
+    uint32_t* sel = tmp;                 // selected size / start per bin
+    uint32_t* gv  = tmp + (B + 1);       // ground size / start per flagged slot
+    uint32_t* rj  = tmp + 2 * (B + 1);   // rejected size / start per flagged slot
+    const uint32_t nflag = *n_recs;      // single frame: records are this frame's, indexed by slot
+    const bool vox = (version == 3) && !skip_voxelize;
+
+    for (int b = tid; b < B; b += nt) {
+        const uint8_t a = action[b] & 0x0F;
+        uint32_t sz = 0;
+        if (a == ACT_MAP) sz = cm[b];
+        else if (a == ACT_FLAG) sz = vox ? vox_cnt[flag_slot[b]] : cq[b] + recs[flag_slot[b]].n_ground_final;
+        else if (a == ACT_MERGE) sz = cq[b] + cm[b];
+        else if (a == ACT_CURR) sz = cq[b];
+        sel[b] = sz;
+    }
+    for (uint32_t s = tid; s < (uint32_t)B; s += nt) {
+        gv[s] = (s < nflag) ? recs[s].n_ground_final : 0u;
+        rj[s] = (s < nflag) ? recs[s].n_points - recs[s].n_ground_final : 0u;
+    }
+    __syncthreads();
+    const uint32_t sel_total = block_excl_scan(sel, sel, B, s_part);
+    const uint32_t gv_total  = block_excl_scan(gv, gv, B, s_part);
+    const uint32_t rj_total  = block_excl_scan(rj, rj, B, s_part);
+    // selected bins
+    for (int b = tid; b < B; b += nt) {
+        const uint8_t a = action[b] & 0x0F;
+        CopyJob j0{nullptr, nullptr, 0u, 0u}, j1{nullptr, nullptr, 0u, 0u};
+        float4* dst = arranged + sel[b];
+        if (a == ACT_MAP) {
+            j0 = CopyJob{map_sorted + dsm[b], dst, cm[b], 0u};
+        } else if (a == ACT_FLAG) {
+            const uint32_t slot = flag_slot[b];
+            if (vox) {
+                j0 = CopyJob{vox_pts + vox_start[slot], dst, vox_cnt[slot], 0u};
+            } else {
+                j0 = CopyJob{qry_sorted + dsq[b], dst, cq[b], 0u};                                           // bin_curr
+                j1 = CopyJob{part_pts + recs[slot].src_begin, dst + cq[b], recs[slot].n_ground_final, 0u};   // += piecewise_ground_
+            }
+        } else if (a == ACT_MERGE) {
+            j0 = CopyJob{qry_sorted + dsq[b], dst, cq[b], 0u};                 // merge_bins: curr first,
+            j1 = CopyJob{map_sorted + dsm[b], dst + cq[b], cm[b], 0u};         // then map (erasor.cpp:301-306)
+        } else if (a == ACT_CURR) {
+            j0 = CopyJob{qry_sorted + dsq[b], dst, cq[b], 0u};
+        }
+        jobs[2 * b] = j0; jobs[2 * b + 1] = j1;
+    }
+    // ground_viz (appended to arranged, erasor.cpp:616) and map_rejected, per flagged slot in processing order
+    for (uint32_t s = tid; s < (uint32_t)B; s += nt) {
+        CopyJob jg{nullptr, nullptr, 0u, 0u}, jr{nullptr, nullptr, 0u, 0u};
+        if (s < nflag) {
+            const FlagRec& rc = recs[s];
+            jg = CopyJob{part_pts + rc.src_begin, arranged + sel_total + gv[s], rc.n_ground_final, 0u};
+            jr = CopyJob{part_pts + rc.src_begin + rc.n_ground_final, map_rej + rj[s], rc.n_points - rc.n_ground_final, 0u};
+        }
+        jobs[2 * B + s] = jg; jobs[3 * B + s] = jr;
+    }
+    __syncthreads();
+    // curr_rejected (version 2 only, erasor.cpp:405-408)
+    for (int b = tid; b < B; b += nt) sel[b] = (action[b] & ACT_CURR_REJECTED_BIT) ? cq[b] : 0u;
+    __syncthreads();
+    const uint32_t cr_total = block_excl_scan(sel, sel, B, s_part);
+    for (int b = tid; b < B; b += nt) {
+        CopyJob j{nullptr, nullptr, 0u, 0u};
+        if (action[b] & ACT_CURR_REJECTED_BIT) j = CopyJob{qry_sorted + dsq[b], curr_rej + sel[b], cq[b], 0u};
+        jobs[4 * B + b] = j;
+    }
+    if (tid == 0) {
+        out_sizes[0] = sel_total + gv_total;
+        out_sizes[1] = cm[B];
+        out_sizes[2] = rj_total;
+        out_sizes[3] = cr_total;
+    }
+}
+
+__global__ void __launch_bounds__(128) k5_copy(const CopyJob* __restrict__ jobs, uint32_t n_jobs) {
+    for (uint32_t j = blockIdx.x; j < n_jobs; j += gridDim.x) {
+        const CopyJob jb = jobs[j];
+        for (uint32_t i = threadIdx.x; i < jb.n; i += 128) jb.dst[i] = jb.src[i];
+    }
+}
+
+cudaError_t launch_k5(cudaStream_t st, int B, int version, int skip_voxelize, const uint32_t* cnt, const uint32_t* dst_start,
+                      const uint8_t* action, const uint32_t* flag_slot, const FlagRec* recs, const uint32_t* n_recs,
+                      const uint32_t* vox_cnt, const uint32_t* vox_start, const float4* map_sorted, const float4* qry_sorted,
+                      const float4* part_pts, const float4* vox_pts, float4* arranged, float4* map_rej, float4* curr_rej,
+                      CopyJob* jobs, uint32_t* out_sizes, uint32_t* tmp, int copy_grid) {
+    k5_plan<<<1, 1024, 0, st>>>(B, version, skip_voxelize, cnt, dst_start, action, flag_slot, recs, n_recs, vox_cnt, vox_start,
+                                map_sorted, qry_sorted, part_pts, vox_pts, arranged, map_rej, curr_rej, jobs, out_sizes, tmp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k5_copy<<<copy_grid, 128, 0, st>>>(jobs, 5u * (uint32_t)B);
+    return cudaGetLastError();
+}
+
+// ============================================================================================
+// small utilities
+// ============================================================================================
+__global__ void k_init_tables(uint32_t* zmin, uint32_t* zmax, size_t n, uint32_t* n_recs, uint32_t* frame_rejected, int F) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { zmin[i] = 0xFFFFFFFFu; zmax[i] = 0u; }
+    if (i == 0) *n_recs = 0u;
+    if (frame_rejected && i < (size_t)F) frame_rejected[i] = 0u;
+}
+cudaError_t launch_init_tables(cudaStream_t st, uint32_t* zmin, uint32_t* zmax, size_t n, uint32_t* n_recs, uint32_t* frame_rejected, int F) {
+    const size_t m = n > (size_t)F ? n : (size_t)F;
+    const int blocks = (int)((m + 255) / 256);
+    k_init_tables<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(zmin, zmax, n, n_recs, frame_rejected, F);
+    return cudaGetLastError();
+}
+
+}  // namespace erasor

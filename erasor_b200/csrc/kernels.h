@@ -1,0 +1,53 @@
+// kernels.h -- launch wrappers of the path's kernels (definitions in kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+#include "device_types.h"
+
+namespace erasor {
+
+struct CopyJob {
+    const float4* src;
+    float4*       dst;
+    uint32_t      n;
+    uint32_t      pad_;
+};
+
+size_t k1_smem_bytes(int R, int B);
+size_t k3_smem_bytes(int B);
+
+cudaError_t launch_init_tables(cudaStream_t st, uint32_t* zmin, uint32_t* zmax, size_t n, uint32_t* n_recs,
+                               uint32_t* frame_rejected, int F);
+
+cudaError_t launch_k1(cudaStream_t st, const BinTablesView& T, const float4* map_pts, const float4* qry_pts,
+                      const ChunkDesc* chunks, int n_chunks, uint16_t* bin_map, uint16_t* bin_qry, uint32_t* ch_cnt,
+                      uint32_t* zmin, uint32_t* zmax, int B, int F, unsigned long long* fence);
+
+cudaError_t launch_k3(cudaStream_t st, const SrtParams& P, int F, const uint32_t* chunk_range, uint32_t* ch_cnt,
+                      const uint32_t* zmin, const uint32_t* zmax, const uint32_t* frame_off, uint32_t* cnt, uint32_t* dst_start,
+                      uint8_t* status, uint8_t* action, uint32_t* flag_slot, uint32_t* n_flagged, FlagRec* recs,
+                      uint32_t* n_recs, uint32_t rec_capacity);
+
+cudaError_t launch_k2(cudaStream_t st, const ChunkDesc* chunks, uint32_t chunk_base, uint32_t n_chunks, int F,
+                      const uint16_t* bin_ids, const float4* pts, const uint32_t* ch_cnt, const uint32_t* dst_start,
+                      float4* out_pts, uint32_t* out_src, int B);
+
+cudaError_t launch_k4(cudaStream_t st, const GpfParams& P, FlagRec* recs, const uint32_t* n_recs, uint32_t rec_capacity,
+                      const float4* sorted_pts, const uint32_t* sorted_src, const uint32_t* frame_off, float4* part_pts,
+                      uint8_t* keep_mask, uint8_t* ground_mask, uint32_t* frame_rejected, unsigned char* gscratch,
+                      int grid, unsigned long long* fence);
+
+cudaError_t launch_k4b(cudaStream_t st, float leaf, int B, const FlagRec* recs, const uint32_t* n_recs, uint32_t rec_capacity,
+                       const uint32_t* cnt, const uint32_t* dst_start, const float4* qry_sorted, const float4* part_pts,
+                       float4* vox_pts, uint32_t* vox_cnt, uint32_t* vox_start, unsigned char* gscratch, int grid);
+
+cudaError_t launch_k5(cudaStream_t st, int B, int version, int skip_voxelize, const uint32_t* cnt, const uint32_t* dst_start,
+                      const uint8_t* action, const uint32_t* flag_slot, const FlagRec* recs, const uint32_t* n_recs,
+                      const uint32_t* vox_cnt, const uint32_t* vox_start, const float4* map_sorted, const float4* qry_sorted,
+                      const float4* part_pts, const float4* vox_pts, float4* arranged, float4* map_rej, float4* curr_rej,
+                      CopyJob* jobs, uint32_t* out_sizes, uint32_t* tmp, int copy_grid);
+
+}  // namespace erasor

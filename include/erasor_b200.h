@@ -1,0 +1,151 @@
+/* ============================================================================
+ * erasor_b200.h -- C ABI of the B200-native R-POD -> Scan Ratio Test -> R-GPF path
+ *
+ * This is the drop-in boundary for the reference's `class ERASOR`
+ * (reference include/erasor/erasor.h:43-147, src/offline_map_updater/src/erasor.cpp)
+ * as used by its single caller OfflineMapUpdater::callback_node
+ * (src/offline_map_updater/src/OfflineMapUpdater.cpp:266-284).  The reference has no
+ * FFI layer of its own; each entry point below names the C++ member it replaces.
+ *
+ * Conventions
+ *   - plain C types only; clouds are float[n][4] = x, y, z, intensity (pcl::PointXYZI's
+ *     four used floats; on the device this is one float4 per point, 16-byte aligned);
+ *   - every function returns 0 (ERASOR_OK) or a negative error code and never throws;
+ *     erasor_last_error() gives the text;
+ *   - one handle <-> one CUDA device + one stream; a handle is not thread-safe;
+ *   - device buffers are owned by the handle, caller buffers by the caller;
+ *     `ptr_kind` says whether caller buffers are host (pageable or pinned) or device memory;
+ *   - bins are indexed  bin = sector * num_rings + ring  (theta outer, r inner: the order
+ *     in which the reference walks and flattens its R-POD, erasor.cpp:309-320);
+ *   - there is no CPU fallback: without a CUDA device erasor_create fails with ERASOR_E_CUDA.
+ * ========================================================================== */
+#ifndef ERASOR_B200_H
+#define ERASOR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ERASOR_B200_ABI_VERSION 1
+
+typedef struct erasor_ctx* erasor_handle_t;
+
+/* The 15 keys ERASOR's constructor reads from /erasor/ (erasor.h:47-61), /erasor/version
+ * (OfflineMapUpdater.cpp:81) and three mode switches that pin choices the reference leaves
+ * to its third-party libraries. */
+typedef struct {
+    double max_range;              /* /erasor/max_range             erasor.h:47 */
+    double min_h;                  /* /erasor/min_h                 erasor.h:51 */
+    double max_h;                  /* /erasor/max_h                 erasor.h:50 */
+    double th_bin_max_h;           /* /erasor/th_bin_max_h          erasor.h:52 (v2 only) */
+    double scan_ratio_threshold;   /* /erasor/scan_ratio_threshold  erasor.h:53 */
+    double rejection_ratio;        /* /erasor/rejection_ratio       erasor.h:56 (unused by the path) */
+    double gf_dist_thr;            /* /erasor/gf_dist_thr           erasor.h:57 */
+    double gf_th_seeds_height;     /* /erasor/gf_th_seeds_height    erasor.h:60 */
+    double map_voxel_size;         /* /erasor/map_voxel_size        erasor.h:61 */
+    int    num_rings;              /* /erasor/num_rings             erasor.h:48 */
+    int    num_sectors;            /* /erasor/num_sectors           erasor.h:49 */
+    int    num_lowest_pts;         /* /erasor/num_lowest_pts        erasor.h:54 */
+    int    minimum_num_pts;        /* /erasor/minimum_num_pts       erasor.h:55 */
+    int    gf_iter;                /* /erasor/gf_iter               erasor.h:58 */
+    int    gf_num_lpr;             /* /erasor/gf_num_lpr            erasor.h:59 */
+    int    version;                /* /erasor/version               OfflineMapUpdater.cpp:81 */
+    int    cov_mode;               /* 0: pcl::computeMeanAndCovarianceMatrix of PCL<=1.10 (default), 1: PCL>=1.11 (shifted) */
+    int    sort_mode;              /* must be 1: R-GPF z-sort ties in source order (std::sort's tie order is unspecified) */
+    int    skip_voxelize;          /* 1: leave out v3's in-bin voxelize_preserving_labels (erasor.cpp:526-528) */
+} erasor_params_t;
+
+enum { ERASOR_PTR_HOST = 0, ERASOR_PTR_DEVICE = 1 };
+enum { ERASOR_CLOUD_MAP = 0, ERASOR_CLOUD_QUERY = 1 };
+
+enum {
+    ERASOR_OK            = 0,
+    ERASOR_E_INVALID     = -1,   /* bad argument / parameter */
+    ERASOR_E_CUDA        = -2,   /* CUDA runtime error, or no device */
+    ERASOR_E_STATE       = -3,   /* call order violated (set_inputs -> compare -> get_*) */
+    ERASOR_E_CAPACITY    = -4,   /* caller buffer too small */
+    ERASOR_E_UNSUPPORTED = -5    /* e.g. num_rings*num_sectors beyond the shared-memory table limit */
+};
+
+/* status values, as the reference publishes them (erasor.h:12-18) */
+#define ERASOR_STATUS_LITTLE_NUM     0.0f
+#define ERASOR_STATUS_MERGE_BINS     0.25f
+#define ERASOR_STATUS_MAP_IS_HIGHER  0.5f
+#define ERASOR_STATUS_BLOCKED        0.8f
+#define ERASOR_STATUS_CURR_IS_HIGHER 1.0f
+
+/* ---- lifetime --------------------------------------------------------------------------- */
+/* replaces ERASOR::ERASOR(ros::NodeHandle*) (erasor.h:46-103): parameters are fixed here. */
+int  erasor_create(const erasor_params_t* params, int device, erasor_handle_t* out);
+void erasor_destroy(erasor_handle_t h);
+const char* erasor_last_error(erasor_handle_t h);   /* h may be NULL: error of the last failed erasor_create */
+int  erasor_abi_version(void);
+/* the handle's CUDA stream (cudaStream_t as void*), so callers can order their own work after it */
+void* erasor_stream(erasor_handle_t h);
+int  erasor_synchronize(erasor_handle_t h);
+
+/* ---- the per-frame path, in the reference's call order ------------------------------------ */
+/* replaces ERASOR::set_inputs(map_voi, query_voi) (erasor.cpp:57-85): both clouds already in the
+ * egocentric body frame.  Builds both R-PODs (bin of every point, per-bin min/max z and count). */
+int erasor_set_inputs(erasor_handle_t h, const float* map_voi_xyzi, size_t n_map,
+                      const float* query_voi_xyzi, size_t n_query, int ptr_kind);
+/* replaces compare_vois_and_revert_ground(frame) [version 2, erasor.cpp:332-434] and
+ * compare_vois_and_revert_ground_w_block(frame) [version 3, erasor.cpp:438-571]:
+ * Scan Ratio Test, status per bin, R-GPF on the flagged bins, selection. */
+int erasor_compare(erasor_handle_t h, int version, int frame);
+/* sizes of the four output clouds of the last compare (so the caller can allocate) */
+int erasor_get_output_sizes(erasor_handle_t h, size_t* n_arranged, size_t* n_complement,
+                            size_t* n_map_rejected, size_t* n_curr_rejected);
+/* replaces ERASOR::get_static_estimate(arranged, complement) (erasor.cpp:612-626); output in the
+ * reference's order: selected bins theta-major / r-minor, then ground_viz; complement in source order. */
+int erasor_get_static_estimate(erasor_handle_t h, float* arranged_xyzi, size_t cap_arranged, size_t* n_arranged,
+                               float* complement_xyzi, size_t cap_complement, size_t* n_complement, int ptr_kind);
+/* replaces ERASOR::get_outliers(map_rejected, curr_rejected) (erasor.cpp:322-327) */
+int erasor_get_outliers(erasor_handle_t h, float* map_rejected_xyzi, size_t cap_map, size_t* n_map_rejected,
+                        float* curr_rejected_xyzi, size_t cap_curr, size_t* n_curr_rejected, int ptr_kind);
+/* replaces ERASOR::get_max_range() (erasor.cpp:628) */
+double erasor_get_max_range(erasor_handle_t h);
+
+/* ---- parity taps (the reference exposes these only as public members / rviz topics) --------- */
+/* r_pod_map / r_pod_curr (erasor.h:143-144): bin of every input point (-1: complement / dropped),
+ * per-bin min z, max z (NaN where the bin is empty) and count.  Any pointer may be NULL. Host buffers. */
+int erasor_get_bins(erasor_handle_t h, int which_cloud, int32_t* bin_of_point, float* min_h, float* max_h, uint32_t* count);
+/* per-bin status of the last compare as published on /SCDR/debug/polygons_marker (erasor.cpp:439-441,570) */
+int erasor_get_status(erasor_handle_t h, float* status);
+/* R-GPF taps: for each bin that ran extract_ground (processing order), its bin id, point count, seed count,
+ * LPR height, and per iteration the plane (nx,ny,nz,d) and the ground count.  *n_planes in: capacity, out: count. */
+int erasor_get_planes(erasor_handle_t h, int32_t* bin_ids, int32_t* n_points, int32_t* n_seeds, double* lpr_height,
+                      double* normal_d /* [n][gf_iter][4] */, int32_t* n_ground /* [n][gf_iter] */, size_t* n_planes);
+/* per map_voi point (source order): keep_map = 0 where the point is rejected as dynamic (non-ground point of a
+ * flagged bin), is_ground = 1 where R-GPF retained it as ground.  Host buffers, either may be NULL. */
+int erasor_get_static_mask(erasor_handle_t h, uint8_t* keep_map, uint8_t* is_ground);
+/* events the reference would have thrown / invoked UB on: points with y == -0.0f and
+ * x <= -0 (fenced to y = +0), plane fits on an empty set (fenced to normal (0,0,1), d = 0), and sector decisions
+ * that stayed ambiguous after double-double arithmetic (never observed). */
+int erasor_get_fence_counts(erasor_handle_t h, uint64_t* negzero_points, uint64_t* empty_plane_fits, uint64_t* ambiguous_sector);
+
+/* ---- frame-independent batch mode (north_star: frames shard across GPUs, masks all-gathered) --- */
+/* Runs the whole path on n_frames independent (map_voi, query_voi) pairs and writes, for every map point of
+ * every frame, keep = 0 where the frame rejects it.  Frame f's map points are
+ * map_xyzi[map_offsets[f] .. map_offsets[f+1]) (offsets in points, n_frames+1 entries, host memory);
+ * likewise the queries.  keep_mask has map_offsets[n_frames] bytes.  Clouds / mask: host or device (ptr_kind). */
+int erasor_process_frames(erasor_handle_t h, const float* map_xyzi, const uint64_t* map_offsets,
+                          const float* query_xyzi, const uint64_t* query_offsets, int n_frames,
+                          uint8_t* keep_mask, int ptr_kind);
+/* per-frame counters of the last erasor_process_frames: flagged bins and rejected points (host arrays of n_frames) */
+int erasor_get_frame_stats(erasor_handle_t h, uint32_t* n_flagged_bins, uint32_t* n_rejected_points);
+
+/* ---- instrumentation ---------------------------------------------------------------------- */
+/* number of kernels this library launched on the handle since creation */
+uint64_t erasor_kernel_launch_count(erasor_handle_t h);
+/* CUDA-event time (ms) spent in the binning kernel (K1) since the last reset, and its launch count */
+int erasor_get_kernel_time_ms(erasor_handle_t h, int kernel_id, double* total_ms, uint64_t* launches);
+int erasor_reset_kernel_times(erasor_handle_t h, int enable_timing);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ERASOR_B200_H */

@@ -714,8 +714,10 @@ void voxelize_preserving_labels(const Cloud& src, Cloud& dst, double leaf_size) 
         int rad = 0;
         scan(0, 0);
         while (true) {
-            const float reach = static_cast<float>(rad) * leaf;     // everything within `reach` has been seen
-            if (best_i != 0xFFFFFFFFu && best_d <= reach * reach) break;
+            // every point closer than `reach` has been seen; the 1e-4 margin keeps the early exit identical to a
+            // brute-force scan even when float rounding puts an unseen point's distance exactly on best_d
+            const float reach = static_cast<float>(rad) * leaf * 0.9999f;
+            if (best_i != 0xFFFFFFFFu && best_d < reach * reach) break;
             ++rad;
             scan(rad, rad);
             if (rad > 64 && best_i != 0xFFFFFFFFu) break;

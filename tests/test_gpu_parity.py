@@ -1,0 +1,155 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Bar (BASELINE.json north_star): bin indices and SRT flags bit-exact; R-GPF plane normals and retained
+point sets within 1e-4.  The CUDA R-GPF reproduces the oracle's float operation order, so these tests
+assert exact equality and, separately, the 1e-4 bar.
+"""
+import numpy as np
+import pytest
+
+from erasor_b200 import params as P
+from erasor_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+PRESETS = ["seq_05", "seq_00", "seq_01", "seq_07", "synthetic_40x360"]
+NORMAL_TOL = 1e-4   # north_star tolerance for plane normals / d
+
+
+def _crop(voi, max_range):
+    r2 = voi[:, 0].astype(np.float64) ** 2 + voi[:, 1].astype(np.float64) ** 2
+    return voi[r2 < (max_range + 5.0) ** 2]
+
+
+def _frame(small_workload, i, p):
+    voi, q, k, idx = small_workload["frames"][i]
+    return _crop(voi, p.max_range), q
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from erasor_b200 import capi as C
+    return C
+
+
+def _run_both(capi, oracle_mod, p, m, q):
+    o = oracle_mod.Oracle(p)
+    o.run(m, q)
+    h = capi.Handle(p)
+    h.set_inputs(m, q)
+    return o, h
+
+
+@pytest.mark.parametrize("name", PRESETS)
+def test_bins_exact_adversarial(capi, oracle_mod, name):
+    p = P.preset(name).replace(skip_voxelize=1)
+    pts = synth.adversarial_points(p, n_random=300000, seed=3)
+    q = synth.adversarial_points(p, n_random=20000, seed=4)
+    o, h = _run_both(capi, oracle_mod, p, pts, q)
+    for which in (0, 1):
+        bop, mn, mx, cnt = h.get_bins(which)
+        ob = o.bin_of_point(which)
+        assert np.array_equal(bop, ob), f"{name} cloud {which}: {np.count_nonzero(bop != ob)} bin ids differ"
+        omn, omx, ocnt, occ = o.bins(which)
+        assert np.array_equal(cnt, ocnt)
+        occ = ocnt > 0
+        assert np.array_equal(mn[occ].astype(np.float64), omn[occ]) and np.array_equal(mx[occ].astype(np.float64), omx[occ])
+        assert np.all(np.isnan(mn[~occ])) and np.all(np.isnan(mx[~occ]))
+    f = h.fence_counts()
+    assert f["ambiguous_sector"] == 0 and f["negzero_points"] == 0
+    h.close()
+
+
+@pytest.mark.parametrize("name", PRESETS)
+@pytest.mark.parametrize("version", [3, 2])
+def test_frame_parity(capi, oracle_mod, small_workload, name, version):
+    p = P.preset(name).replace(skip_voxelize=1, version=version)
+    for fi in (1, 3):
+        m, q = _frame(small_workload, fi, p)
+        o, h = _run_both(capi, oracle_mod, p, m, q)
+        h.compare(version)
+        # bins
+        for which in (0, 1):
+            bop, mn, mx, cnt = h.get_bins(which)
+            assert np.array_equal(bop, o.bin_of_point(which))
+            omn, omx, ocnt, _ = o.bins(which)
+            assert np.array_equal(cnt, ocnt)
+        # status
+        st, _ = o.status()
+        assert np.array_equal(h.get_status().astype(np.float64), st.astype(np.float32).astype(np.float64)), f"{name} v{version} status"
+        # planes
+        gp, op = h.get_planes(), o.planes()
+        assert [g["bin"] for g in gp] == [x["bin"] for x in op]
+        for g, x in zip(gp, op):
+            assert g["n_points"] == x["n_points"] and g["n_seeds"] == x["n_seeds"]
+            assert g["lpr"] == x["lpr"]
+            assert np.allclose(g["normal_d"], x["normal_d"], atol=NORMAL_TOL, rtol=0)
+            assert np.array_equal(g["normal_d"], x["normal_d"]), "plane parameters are expected to be bit-identical"
+            assert np.array_equal(g["n_ground"], x["n_ground"])
+        # retained / rejected sets
+        keep, gnd = h.get_static_mask()
+        rej_xyzi, rej_src = o.cloud(o.MAP_REJECTED)
+        okeep = np.ones(len(m), dtype=np.uint8)
+        okeep[rej_src] = 0
+        assert np.array_equal(keep, okeep)
+        gv_xyzi, gv_src = o.cloud(o.GROUND_VIZ)
+        ognd = np.zeros(len(m), dtype=np.uint8)
+        ognd[gv_src] = 1
+        assert np.array_equal(gnd, ognd)
+        # clouds in the reference's order
+        arr, cmp_ = h.get_static_estimate()
+        oarr, _ = o.cloud(o.ARRANGED)
+        ocmp, _ = o.cloud(o.COMPLEMENT)
+        assert arr.shape == oarr.shape and np.array_equal(arr.view(np.uint32), oarr.view(np.uint32)), f"{name} v{version} arranged"
+        assert cmp_.shape == ocmp.shape and np.array_equal(cmp_.view(np.uint32), ocmp.view(np.uint32))
+        mr, cr = h.get_outliers()
+        ocr, _ = o.cloud(o.CURR_REJECTED)
+        assert mr.shape == rej_xyzi.shape and np.array_equal(mr.view(np.uint32), rej_xyzi.view(np.uint32))
+        assert cr.shape == ocr.shape and np.array_equal(cr.view(np.uint32), ocr.view(np.uint32))
+        h.close()
+
+
+def test_batch_masks(capi, oracle_mod, small_workload):
+    p = P.preset("seq_05").replace(skip_voxelize=1)
+    frames = [_frame(small_workload, i, p) for i in range(6)]
+    mo = np.cumsum([0] + [len(m) for m, _ in frames]).astype(np.uint64)
+    qo = np.cumsum([0] + [len(q) for _, q in frames]).astype(np.uint64)
+    M = np.concatenate([m for m, _ in frames])
+    Q = np.concatenate([q for _, q in frames])
+    h = capi.Handle(p)
+    keep = h.process_frames(M, mo, Q, qo)
+    nf, nr = h.frame_stats()
+    for f, (m, q) in enumerate(frames):
+        o = oracle_mod.Oracle(p)
+        o.run(m, q)
+        _, rej_src = o.cloud(o.MAP_REJECTED)
+        okeep = np.ones(len(m), dtype=np.uint8)
+        okeep[rej_src] = 0
+        assert np.array_equal(keep[int(mo[f]):int(mo[f + 1])], okeep), f"frame {f}"
+        assert nf[f] == len(o.planes()) and nr[f] == len(rej_src)
+    h.close()
+
+
+def test_empty_and_tiny_inputs(capi, oracle_mod):
+    p = P.preset("seq_05").replace(skip_voxelize=1)
+    z = np.zeros((0, 4), dtype=np.float32)
+    one = np.array([[3.0, 4.0, 0.1, 7.0]], dtype=np.float32)
+    for m, q in ((z, z), (one, z), (z, one), (one, one)):
+        o, h = _run_both(capi, oracle_mod, p, m, q)
+        h.compare(3)
+        arr, cmp_ = h.get_static_estimate()
+        oarr, _ = o.cloud(o.ARRANGED)
+        assert arr.shape == oarr.shape
+        assert np.array_equal(h.get_status().astype(np.float64), o.status()[0])
+        h.close()
+
+
+def test_negzero_fence(capi, oracle_mod):
+    """the reference throws on y == -0.0f, x < 0; both sides fence it to y = +0 and count it."""
+    p = P.preset("seq_05").replace(skip_voxelize=1)
+    m = np.array([[-5.0, -0.0, 0.2, 1.0], [-0.0, -0.0, 0.2, 1.0], [5.0, -0.0, 0.2, 1.0], [-5.0, 0.0, 0.2, 1.0]], dtype=np.float32)
+    o, h = _run_both(capi, oracle_mod, p, m, m[:1])
+    bop, *_ = h.get_bins(0)
+    assert np.array_equal(bop, o.bin_of_point(0))
+    assert h.fence_counts()["negzero_points"] == 3 and o.negzero_fenced() == 3   # two map points + one query point
+    h.close()
