@@ -80,7 +80,7 @@ struct erasor_ctx {
     DevBuf d_bin_map, d_bin_qry;               // uint16 bin id per point
     DevBuf d_chunks, d_chunk_range, d_frame_off;
     DevBuf d_chcnt, d_zmin, d_zmax, d_cnt, d_dst_start, d_status, d_action, d_flag_slot, d_nflag;
-    DevBuf d_recs, d_nrecs, d_frame_rej;
+    DevBuf d_recs, d_nrecs, d_frame_rej, d_frame_rec_base;
     DevBuf d_map_sorted, d_map_src, d_qry_sorted, d_qry_src, d_part, d_scratch;
     DevBuf d_keep, d_ground;
     DevBuf d_arranged, d_map_rej, d_curr_rej, d_jobs, d_out_sizes, d_k5tmp;
@@ -194,7 +194,7 @@ int prepare_batch(erasor_ctx* h, const uint64_t* map_off, const uint64_t* qry_of
     CK(h->d_frame_off.ensure(sizeof(uint32_t) * foff.size()));
     CK(h->d_bin_map.ensure(sizeof(uint16_t) * std::max<size_t>(NM, 1)));
     CK(h->d_bin_qry.ensure(sizeof(uint16_t) * std::max<size_t>(NQ, 1)));
-    CK(h->d_chcnt.ensure(sizeof(uint32_t) * std::max<size_t>(n_chunks, 1) * (B + 1)));
+    if (mode == 0) CK(h->d_chcnt.ensure(sizeof(uint32_t) * std::max<size_t>(n_chunks, 1) * (B + 1)));
     CK(h->d_zmin.ensure(sizeof(uint32_t) * 2 * (size_t)F * B));
     CK(h->d_zmax.ensure(sizeof(uint32_t) * 2 * (size_t)F * B));
     CK(h->d_cnt.ensure(sizeof(uint32_t) * 2 * (size_t)F * (B + 1)));
@@ -204,13 +204,14 @@ int prepare_batch(erasor_ctx* h, const uint64_t* map_off, const uint64_t* qry_of
     CK(h->d_flag_slot.ensure(sizeof(uint32_t) * (size_t)F * B));
     CK(h->d_nflag.ensure(sizeof(uint32_t) * (size_t)F));
     CK(h->d_frame_rej.ensure(sizeof(uint32_t) * (size_t)F));
+    CK(h->d_frame_rec_base.ensure(sizeof(uint32_t) * (size_t)F));
     h->rec_capacity = (uint32_t)std::min<size_t>((size_t)F * B, (size_t)1 << 21);
     CK(h->d_recs.ensure(sizeof(FlagRec) * (size_t)h->rec_capacity));
     CK(h->d_nrecs.ensure(sizeof(uint32_t) * 4));
-    CK(h->d_map_sorted.ensure(sizeof(float4) * std::max<size_t>(NM, 1)));
     CK(h->d_map_src.ensure(sizeof(uint32_t) * std::max<size_t>(NM, 1)));
     CK(h->d_scratch.ensure((size_t)24 * std::max<size_t>(NM, 1) + 64));
     if (mode == 0) {
+        CK(h->d_map_sorted.ensure(sizeof(float4) * std::max<size_t>(NM, 1)));
         CK(h->d_qry_sorted.ensure(sizeof(float4) * std::max<size_t>(NQ, 1)));
         CK(h->d_qry_src.ensure(sizeof(uint32_t) * std::max<size_t>(NQ, 1)));
         CK(h->d_part.ensure(sizeof(float4) * std::max<size_t>(NM, 1)));
@@ -248,19 +249,19 @@ int stage_inputs(erasor_ctx* h, const float* map_xyzi, const float* qry_xyzi, in
     return ERASOR_OK;
 }
 
-int run_k1(erasor_ctx* h) {
+int run_k1(erasor_ctx* h, int mode) {
     const int B = h->B, F = h->F;
     {
         h->launches++;
         CK(launch_init_tables(h->stream, h->d_zmin.as<uint32_t>(), h->d_zmax.as<uint32_t>(), 2 * (size_t)F * B,
-                              h->d_nrecs.as<uint32_t>(), h->d_frame_rej.as<uint32_t>(), F));
+                              h->d_cnt.as<uint32_t>(), 2 * (size_t)F * (B + 1), h->d_nrecs.as<uint32_t>(), h->d_frame_rej.as<uint32_t>(), F));
     }
     {
         Scope s(h, 1);
         if (h->n_chunks_map + h->n_chunks_qry) h->launches++;
         CK(launch_k1(h->stream, h->view, h->cur_map, h->cur_qry, h->d_chunks.as<ChunkDesc>(), (int)(h->n_chunks_map + h->n_chunks_qry),
                      h->d_bin_map.as<uint16_t>(), h->d_bin_qry.as<uint16_t>(), h->d_chcnt.as<uint32_t>(), h->d_zmin.as<uint32_t>(),
-                     h->d_zmax.as<uint32_t>(), B, F, h->d_fence.as<unsigned long long>()));
+                     h->d_zmax.as<uint32_t>(), h->d_cnt.as<uint32_t>(), B, F, mode == 0, h->d_fence.as<unsigned long long>()));
     }
     return ERASOR_OK;
 }
@@ -279,18 +280,23 @@ int run_compare(erasor_ctx* h, int version, int mode, uint8_t* keep_mask, uint8_
         CK(launch_k3(h->stream, sp, F, h->d_chunk_range.as<uint32_t>(), h->d_chcnt.as<uint32_t>(), h->d_zmin.as<uint32_t>(),
                      h->d_zmax.as<uint32_t>(), h->d_frame_off.as<uint32_t>(), h->d_cnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>(),
                      h->d_status.as<uint8_t>(), h->d_action.as<uint8_t>(), h->d_flag_slot.as<uint32_t>(), h->d_nflag.as<uint32_t>(),
-                     h->d_recs.as<FlagRec>(), h->d_nrecs.as<uint32_t>(), h->rec_capacity));
+                     h->d_frame_rec_base.as<uint32_t>(), h->d_recs.as<FlagRec>(), h->d_nrecs.as<uint32_t>(), h->rec_capacity));
     }
     {
         Scope s(h, 2);
-        if (h->n_chunks_map) h->launches++;
-        CK(launch_k2(h->stream, h->d_chunks.as<ChunkDesc>(), 0u, h->n_chunks_map, F, h->d_bin_map.as<uint16_t>(), h->cur_map,
-                     h->d_chcnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>(), h->d_map_sorted.as<float4>(), h->d_map_src.as<uint32_t>(), B));
         if (mode == 0) {
+            if (h->n_chunks_map) h->launches++;
+            CK(launch_k2(h->stream, h->d_chunks.as<ChunkDesc>(), 0u, h->n_chunks_map, F, h->d_bin_map.as<uint16_t>(), h->cur_map,
+                         h->d_chcnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>(), h->d_map_sorted.as<float4>(), h->d_map_src.as<uint32_t>(), B));
             if (h->n_chunks_qry) h->launches++;
             CK(launch_k2(h->stream, h->d_chunks.as<ChunkDesc>(), h->n_chunks_map, h->n_chunks_qry, F, h->d_bin_qry.as<uint16_t>(), h->cur_qry,
                          h->d_chcnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>() + (size_t)F * (B + 2), h->d_qry_sorted.as<float4>(),
                          h->d_qry_src.as<uint32_t>(), B));
+        } else {
+            if (h->n_chunks_map) h->launches++;
+            CK(launch_k2_gather(h->stream, h->d_chunks.as<ChunkDesc>(), h->n_chunks_map, B, h->d_bin_map.as<uint16_t>(),
+                                h->d_flag_slot.as<uint32_t>(), h->d_frame_rec_base.as<uint32_t>(), h->d_recs.as<FlagRec>(),
+                                h->rec_capacity, h->d_map_src.as<uint32_t>()));
         }
     }
     {
@@ -298,11 +304,11 @@ int run_compare(erasor_ctx* h, int version, int mode, uint8_t* keep_mask, uint8_
         GpfParams gp{};
         gp.th_dist = h->p.gf_dist_thr; gp.th_seeds = h->p.gf_th_seeds_height; gp.num_lowest_pts = h->p.num_lowest_pts;
         gp.num_lpr = h->p.gf_num_lpr; gp.iters = std::min(h->p.gf_iter, kMaxIter); gp.cov_mode = h->p.cov_mode;
-        h->launches++;
-        CK(launch_k4(h->stream, gp, h->d_recs.as<FlagRec>(), h->d_nrecs.as<uint32_t>(), h->rec_capacity, h->d_map_sorted.as<float4>(),
-                     h->d_map_src.as<uint32_t>(), h->d_frame_off.as<uint32_t>(), mode == 0 ? h->d_part.as<float4>() : nullptr,
-                     keep_mask, ground_mask, h->d_frame_rej.as<uint32_t>(), h->d_scratch.as<unsigned char>(), h->sm_count * 3,
-                     h->d_fence.as<unsigned long long>()));
+        h->launches += k4_num_launches();
+        CK(launch_k4(h->stream, gp, h->d_recs.as<FlagRec>(), h->d_nrecs.as<uint32_t>(), h->rec_capacity,
+                     mode == 0 ? h->d_map_sorted.as<float4>() : nullptr, h->d_map_src.as<uint32_t>(), h->cur_map,
+                     h->d_frame_off.as<uint32_t>(), mode == 0 ? h->d_part.as<float4>() : nullptr, keep_mask, ground_mask,
+                     h->d_frame_rej.as<uint32_t>(), h->d_scratch.as<unsigned char>(), h->sm_count, h->d_fence.as<unsigned long long>()));
     }
     return ERASOR_OK;
 }
@@ -391,7 +397,7 @@ void erasor_destroy(erasor_handle_t h) {
                       &h->d_action, &h->d_flag_slot, &h->d_nflag, &h->d_recs, &h->d_nrecs, &h->d_frame_rej, &h->d_map_sorted, &h->d_map_src,
                       &h->d_qry_sorted, &h->d_qry_src, &h->d_part, &h->d_scratch, &h->d_keep, &h->d_ground, &h->d_arranged, &h->d_map_rej,
                       &h->d_curr_rej, &h->d_jobs, &h->d_out_sizes, &h->d_k5tmp, &h->d_fence, &h->d_vox, &h->d_vox_cnt, &h->d_vox_start,
-                      &h->d_vox_scratch};
+                      &h->d_vox_scratch, &h->d_frame_rec_base};
     for (DevBuf* b : bufs) b->release();
     h->h_stage.release();
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -417,7 +423,7 @@ int erasor_set_inputs(erasor_handle_t h, const float* map_voi_xyzi, size_t n_map
     int rc = prepare_batch(h, mo, qo, 1, 0);
     if (rc) return rc;
     if ((rc = stage_inputs(h, map_voi_xyzi, query_voi_xyzi, ptr_kind))) return rc;
-    if ((rc = run_k1(h))) return rc;
+    if ((rc = run_k1(h, 0))) return rc;
     h->stage = 1;
     return ERASOR_OK;
 }
@@ -538,18 +544,7 @@ int erasor_get_bins(erasor_handle_t h, int which_cloud, int32_t* bin_of_point, f
         CK(cudaMemcpy(mn.data(), h->d_zmin.as<uint32_t>() + (size_t)which_cloud * B, sizeof(uint32_t) * B, cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(mx.data(), h->d_zmax.as<uint32_t>() + (size_t)which_cloud * B, sizeof(uint32_t) * B, cudaMemcpyDeviceToHost));
         std::vector<uint32_t> c(B, 0);
-        if (h->stage >= 2) {
-            CK(cudaMemcpy(c.data(), h->d_cnt.as<uint32_t>() + (size_t)which_cloud * (B + 1), sizeof(uint32_t) * B, cudaMemcpyDeviceToHost));
-        } else {
-            // before compare the totals are still per-chunk rows: sum them here (parity tap only)
-            const uint32_t c0 = which_cloud == 0 ? 0 : h->n_chunks_map;
-            const uint32_t c1 = which_cloud == 0 ? h->n_chunks_map : h->n_chunks_map + h->n_chunks_qry;
-            std::vector<uint32_t> rows((size_t)(c1 - c0) * (B + 1));
-            if (!rows.empty())
-                CK(cudaMemcpy(rows.data(), h->d_chcnt.as<uint32_t>() + (size_t)c0 * (B + 1), sizeof(uint32_t) * rows.size(), cudaMemcpyDeviceToHost));
-            for (uint32_t k = 0; k < c1 - c0; ++k)
-                for (int b = 0; b < B; ++b) c[b] += rows[(size_t)k * (B + 1) + b];
-        }
+        CK(cudaMemcpy(c.data(), h->d_cnt.as<uint32_t>() + (size_t)which_cloud * (B + 1), sizeof(uint32_t) * B, cudaMemcpyDeviceToHost));
         const float nan = std::numeric_limits<float>::quiet_NaN();
         for (int b = 0; b < B; ++b) {
             const bool empty = mn[b] == 0xFFFFFFFFu && mx[b] == 0u;
@@ -635,7 +630,7 @@ int erasor_process_frames(erasor_handle_t h, const float* map_xyzi, const uint64
             d_keep = h->d_keep.as<uint8_t>();
         }
         if (h->NM) CK(cudaMemsetAsync(d_keep, 1, h->NM, h->stream));
-        if ((rc = run_k1(h))) return rc;
+        if ((rc = run_k1(h, 1))) return rc;
         if ((rc = run_compare(h, h->p.version, 1, d_keep, nullptr))) return rc;
         if (ptr_kind != ERASOR_PTR_DEVICE && h->NM)
             CK(cudaMemcpyAsync(keep_mask, d_keep, h->NM, cudaMemcpyDeviceToHost, h->stream));

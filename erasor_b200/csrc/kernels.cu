@@ -57,34 +57,38 @@ __device__ __forceinline__ void k1_aggregate(int key, uint32_t zenc, int lane, u
         }
         return;
     }
+    // runs of equal keys in lane order; segmented min/max towards each run's first lane with shuffles
+    // (partial-mask __reduce_*_sync compiles to a per-lane software loop on sm_100a -- measured 60 % of this
+    //  kernel's instructions -- so it is not used here)
     const int      prev  = __shfl_up_sync(FULL_MASK, key, 1);
     const bool     head  = (lane == 0) || (key != prev);
     const unsigned heads = __ballot_sync(FULL_MASK, head);
-    const unsigned le    = (2u << lane) - 1u;                 // lanes <= lane (lane 31: 0 - 1 = all ones)
-    const int      h     = 31 - __clz(heads & le);
-    const unsigned above = heads & ~le;
-    const int      e     = above ? (__ffs(above) - 1) : 32;
-    const unsigned run   = ((e == 32) ? FULL_MASK : ((1u << e) - 1u)) & ~((1u << h) - 1u);
-    if (key >= 0) {
+    const unsigned above = heads & ~((2u << lane) - 1u);      // run heads at lanes > lane (lane 31: mask 0)
+    const int      e     = above ? (__ffs(above) - 1) : 32;   // my run is [.., e)
+    uint32_t mn = zenc, mx = zenc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t omn = __shfl_down_sync(FULL_MASK, mn, d);
+        const uint32_t omx = __shfl_down_sync(FULL_MASK, mx, d);
+        if (lane + d < e) { mn = min(mn, omn); mx = max(mx, omx); }
+    }
+    if (head && key >= 0) {
+        const int h = lane;
         if (key < B) {
-            const uint32_t mn = __reduce_min_sync(run, zenc);
-            const uint32_t mx = __reduce_max_sync(run, zenc);
-            if (lane == h) {
-                atomicMin(&s_mn[key], mn);
-                atomicMax(&s_mx[key], mx);
-                atomicAdd(&s_cnt[key], (uint32_t)(e - h));
-            }
-        } else if (lane == h) {
+            atomicMin(&s_mn[key], mn);
+            atomicMax(&s_mx[key], mx);
+            atomicAdd(&s_cnt[key], (uint32_t)(e - h));
+        } else {
             atomicAdd(&s_cnt[B], (uint32_t)(e - h));
         }
     }
 }
 
-template <int THREADS, int UNROLL>
+template <int THREADS, int UNROLL, bool ROWS>
 __global__ void __launch_bounds__(THREADS)
 k1_rpod_bin(BinTablesView T, const float4* __restrict__ map_pts, const float4* __restrict__ qry_pts,
             const ChunkDesc* __restrict__ chunks, uint16_t* __restrict__ bin_map, uint16_t* __restrict__ bin_qry,
-            uint32_t* __restrict__ ch_cnt, uint32_t* __restrict__ zmin, uint32_t* __restrict__ zmax,
+            uint32_t* __restrict__ ch_cnt, uint32_t* __restrict__ zmin, uint32_t* __restrict__ zmax, uint32_t* __restrict__ cnt_tab,
             int B, int F, unsigned long long* __restrict__ fence) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double*   s_ring = reinterpret_cast<double*>(smem_raw);
@@ -128,15 +132,20 @@ k1_rpod_bin(BinTablesView T, const float4* __restrict__ map_pts, const float4* _
     }
     __syncthreads();
 
-    // flush: dense per-chunk counts (consumed by K3's prefix and K2's stable scatter), min/max by RED to the frame table
-    uint32_t* __restrict__ row = ch_cnt + (size_t)blockIdx.x * (B + 1);
+    // flush: per-bin count / min / max by RED to the frame tables (non-empty bins only); in cloud mode also the dense
+    // per-chunk count row that K3 turns into prefixes for K2's stable scatter
+    uint32_t* __restrict__ row = ROWS ? ch_cnt + (size_t)blockIdx.x * (B + 1) : nullptr;
     const size_t ft = ((size_t)cd.cloud * F + cd.frame) * B;
+    const size_t ct = ((size_t)cd.cloud * F + cd.frame) * (B + 1);
     for (int i = tid; i <= B; i += THREADS) {
         const uint32_t c = s_cnt[i];
-        row[i] = c;
-        if (c != 0u && i < B) {
-            atomicMin(&zmin[ft + i], s_mn[i]);
-            atomicMax(&zmax[ft + i], s_mx[i]);
+        if (ROWS) row[i] = c;
+        if (c != 0u) {
+            atomicAdd(&cnt_tab[ct + i], c);
+            if (i < B) {
+                atomicMin(&zmin[ft + i], s_mn[i]);
+                atomicMax(&zmax[ft + i], s_mx[i]);
+            }
         }
     }
     if (fc.negzero) atomicAdd(&fence[0], (unsigned long long)fc.negzero);
@@ -150,14 +159,20 @@ size_t k1_smem_bytes(int R, int B) {
 
 cudaError_t launch_k1(cudaStream_t st, const BinTablesView& T, const float4* map_pts, const float4* qry_pts,
                       const ChunkDesc* chunks, int n_chunks, uint16_t* bin_map, uint16_t* bin_qry, uint32_t* ch_cnt,
-                      uint32_t* zmin, uint32_t* zmax, int B, int F, unsigned long long* fence) {
+                      uint32_t* zmin, uint32_t* zmax, uint32_t* cnt_tab, int B, int F, bool rows, unsigned long long* fence) {
     if (n_chunks == 0) return cudaSuccess;
     constexpr int THREADS = 256, UNROLL = 4;
     const size_t smem = k1_smem_bytes(T.R, B);
-    auto kern = k1_rpod_bin<THREADS, UNROLL>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, B, F, fence);
+    cudaError_t e;
+    if (rows) {
+        auto kern = k1_rpod_bin<THREADS, UNROLL, true>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence);
+    } else {
+        auto kern = k1_rpod_bin<THREADS, UNROLL, false>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence);
+    }
     return cudaGetLastError();
 }
 
@@ -208,9 +223,9 @@ __device__ __forceinline__ double std_min_d(double a, double b) { return (b < a)
 __global__ void __launch_bounds__(1024)
 k3_srt(SrtParams P, int F, const uint32_t* __restrict__ chunk_range /*[2][F+1]*/, uint32_t* __restrict__ ch_cnt,
        const uint32_t* __restrict__ zmin, const uint32_t* __restrict__ zmax, const uint32_t* __restrict__ frame_off /*[2][F+1]*/,
-       uint32_t* __restrict__ cnt /*[2][F][B+1]*/, uint32_t* __restrict__ dst_start /*[2][F][B+2]*/,
+       const uint32_t* __restrict__ cnt /*[2][F][B+1]*/, uint32_t* __restrict__ dst_start /*[2][F][B+2]*/,
        uint8_t* __restrict__ status /*[F][B]*/, uint8_t* __restrict__ action /*[F][B]*/,
-       uint32_t* __restrict__ flag_slot /*[F][B]*/, uint32_t* __restrict__ n_flagged /*[F]*/,
+       uint32_t* __restrict__ flag_slot /*[F][B]*/, uint32_t* __restrict__ n_flagged /*[F]*/, uint32_t* __restrict__ frame_rec_base /*[F]*/,
        FlagRec* __restrict__ recs, uint32_t* __restrict__ n_recs, uint32_t rec_capacity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int B = P.B, R = P.R, S = P.S;
@@ -220,21 +235,22 @@ k3_srt(SrtParams P, int F, const uint32_t* __restrict__ chunk_range /*[2][F+1]*/
     __shared__ uint32_t s_rec_base;
     const int f = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
 
-    // phase 0: totals per bin and in-place exclusive prefix over the frame's chunks (both clouds)
-    for (int c = 0; c < 2; ++c) {
-        const uint32_t c0 = chunk_range[c * (F + 1) + f], c1 = chunk_range[c * (F + 1) + f + 1];
-        for (int b = tid; b <= B; b += nt) {
-            uint32_t run = 0;
-            for (uint32_t k = c0; k < c1; ++k) {
-                uint32_t* p = ch_cnt + (size_t)k * (B + 1) + b;
-                const uint32_t v = *p;
-                *p = run;
-                run += v;
+    // phase 0 (cloud mode only): in-place exclusive prefix of the per-chunk count rows over the frame's chunks;
+    // the per-bin totals themselves were accumulated by K1 into cnt[]
+    if (P.scatter_mode == 0) {
+        for (int c = 0; c < 2; ++c) {
+            const uint32_t c0 = chunk_range[c * (F + 1) + f], c1 = chunk_range[c * (F + 1) + f + 1];
+            for (int b = tid; b <= B; b += nt) {
+                uint32_t run = 0;
+                for (uint32_t k = c0; k < c1; ++k) {
+                    uint32_t* p = ch_cnt + (size_t)k * (B + 1) + b;
+                    const uint32_t v = *p;
+                    *p = run;
+                    run += v;
+                }
             }
-            cnt[((size_t)c * F + f) * (B + 1) + b] = run;
         }
     }
-    __syncthreads();
     const uint32_t* cm = cnt + ((size_t)0 * F + f) * (B + 1);
     const uint32_t* cq = cnt + ((size_t)1 * F + f) * (B + 1);
     const uint32_t* mnm = zmin + ((size_t)0 * F + f) * B; const uint32_t* mxm = zmax + ((size_t)0 * F + f) * B;
@@ -333,6 +349,7 @@ k3_srt(SrtParams P, int F, const uint32_t* __restrict__ chunk_range /*[2][F+1]*/
     if (tid == 0) {
         n_flagged[f] = nflag;
         s_rec_base   = nflag ? atomicAdd(n_recs, nflag) : 0u;
+        frame_rec_base[f] = s_rec_base;
     }
     for (int b = tid; b < B; b += nt) slot_out[b] = ((act_out[b] & 0x0F) == ACT_FLAG) ? s_sz[b] : kSkip;
     __syncthreads();
@@ -362,7 +379,7 @@ k3_srt(SrtParams P, int F, const uint32_t* __restrict__ chunk_range /*[2][F+1]*/
                 FlagRec& rc = recs[ri];
                 rc.frame = f; rc.bin = b; rc.slot = slot; rc.n_points = cm[b];
                 rc.src_begin = frame_off[f] + s_sz[b];
-                rc.n_seeds = 0; rc.n_empty_fits = 0; rc.n_ground_final = 0; rc.lpr_height = 0.0;
+                rc.n_seeds = 0; rc.n_empty_fits = 0; rc.n_ground_final = 0; rc.lpr_height = 0.0; rc.cursor = 0u;
             }
         }
     }
@@ -378,14 +395,14 @@ k3_srt(SrtParams P, int F, const uint32_t* __restrict__ chunk_range /*[2][F+1]*/
 size_t k3_smem_bytes(int B) { return sizeof(uint32_t) * ((size_t)B + 2 + 34) + (size_t)B + 16; }
 
 cudaError_t launch_k3(cudaStream_t st, const SrtParams& P, int F, const uint32_t* chunk_range, uint32_t* ch_cnt,
-                      const uint32_t* zmin, const uint32_t* zmax, const uint32_t* frame_off, uint32_t* cnt, uint32_t* dst_start,
-                      uint8_t* status, uint8_t* action, uint32_t* flag_slot, uint32_t* n_flagged, FlagRec* recs,
-                      uint32_t* n_recs, uint32_t rec_capacity) {
+                      const uint32_t* zmin, const uint32_t* zmax, const uint32_t* frame_off, const uint32_t* cnt, uint32_t* dst_start,
+                      uint8_t* status, uint8_t* action, uint32_t* flag_slot, uint32_t* n_flagged, uint32_t* frame_rec_base,
+                      FlagRec* recs, uint32_t* n_recs, uint32_t rec_capacity) {
     const size_t smem = k3_smem_bytes(P.B);
     cudaError_t e = cudaFuncSetAttribute(k3_srt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k3_srt<<<F, 1024, smem, st>>>(P, F, chunk_range, ch_cnt, zmin, zmax, frame_off, cnt, dst_start, status, action,
-                                  flag_slot, n_flagged, recs, n_recs, rec_capacity);
+                                  flag_slot, n_flagged, frame_rec_base, recs, n_recs, rec_capacity);
     return cudaGetLastError();
 }
 
@@ -447,6 +464,38 @@ cudaError_t launch_k2(cudaStream_t st, const ChunkDesc* chunks, uint32_t chunk_b
     return cudaGetLastError();
 }
 
+// K2g (mask mode): append the source index of every map point that lies in a flagged bin to that bin's list, in
+// arbitrary order (one returning atomic per flagged point; flagged points are a few per cent).  K4 restores the
+// source order with a bitonic sort of the indices, so no per-chunk prefix table is needed in this mode.
+__global__ void __launch_bounds__(256)
+k2_gather_flagged(const ChunkDesc* __restrict__ chunks, int B, const uint16_t* __restrict__ bin_ids,
+                  const uint32_t* __restrict__ flag_slot /*[F][B]*/, const uint32_t* __restrict__ frame_rec_base /*[F]*/,
+                  FlagRec* __restrict__ recs, uint32_t rec_capacity, uint32_t* __restrict__ out_src) {
+    const ChunkDesc cd = chunks[blockIdx.x];
+    const uint32_t* slots = flag_slot + (size_t)cd.frame * B;
+    const uint32_t rbase = frame_rec_base[cd.frame];
+    const uint32_t local0 = cd.begin - cd.frame_begin;
+    for (uint32_t i = threadIdx.x; i < cd.len; i += 256) {
+        const uint16_t id = bin_ids[cd.begin + i];
+        if (id == kNoBin16) continue;
+        const uint32_t slot = __ldg(&slots[id]);
+        if (slot == kSkip) continue;
+        const uint32_t ri = rbase + slot;
+        if (ri >= rec_capacity) continue;
+        FlagRec& rc = recs[ri];
+        const uint32_t pos = atomicAdd(&rc.cursor, 1u);
+        out_src[rc.src_begin + pos] = local0 + i;
+    }
+}
+
+cudaError_t launch_k2_gather(cudaStream_t st, const ChunkDesc* chunks, uint32_t n_chunks_map, int B, const uint16_t* bin_ids,
+                             const uint32_t* flag_slot, const uint32_t* frame_rec_base, FlagRec* recs, uint32_t rec_capacity,
+                             uint32_t* out_src) {
+    if (n_chunks_map == 0) return cudaSuccess;
+    k2_gather_flagged<<<n_chunks_map, 256, 0, st>>>(chunks, B, bin_ids, flag_slot, frame_rec_base, recs, rec_capacity, out_src);
+    return cudaGetLastError();
+}
+
 // ============================================================================================
 // K4  R-GPF
 // ============================================================================================
@@ -461,42 +510,48 @@ cudaError_t launch_k2(cudaStream_t st, const ChunkDesc* chunks, uint32_t chunk_b
 
 struct Rot { float c, s; };
 
-__device__ __forceinline__ void apply_rot(float* x, int incx, float* y, int incy, int n, Rot j) {
-    if (j.c == 1.0f && j.s == 0.0f) return;
-    for (int i = 0; i < n; ++i) {
-        const float xi = x[i * incx], yi = y[i * incy];
-        x[i * incx] = FA(FM(j.c, xi), FM(j.s, yi));
-        y[i * incy] = FA(FM(-j.s, xi), FM(j.c, yi));
-    }
-}
+// internal::apply_rotation_in_the_plane on (x, y) pairs held in registers
+#define ROT2(X_, Y_, J_)                                            \
+    do {                                                            \
+        const float xi__ = (X_), yi__ = (Y_);                       \
+        (X_) = FA(FM((J_).c, xi__), FM((J_).s, yi__));              \
+        (Y_) = FA(FM(-(J_).s, xi__), FM((J_).c, yi__));             \
+    } while (0)
 
 // Eigen 3.3 JacobiSVD<MatrixXf>(A, ComputeFullU) on a 3x3 (two-sided Jacobi, no preconditioner); returns U.col(2).
-__device__ __noinline__ void jacobi_svd_normal(const float* A, float* normal) {
+// Everything stays in registers: the (p,q) sweep is unrolled so that all matrix indices are compile-time.
+__device__ __forceinline__ void jacobi_svd_normal(const float (&A)[9], float (&normal)[3]) {
     const float precision = 2.0f * FLT_EPSILON, considerAsZero = FLT_MIN;
-    float W[9], U[9], sv[3];
+    float W[9], U[9];
     float scale = 0.0f;
+#pragma unroll
     for (int i = 0; i < 9; ++i) { const float a = fabsf(A[i]); scale = (a > scale) ? a : scale; }
     if (scale == 0.0f) scale = 1.0f;
+#pragma unroll
     for (int i = 0; i < 9; ++i) W[i] = FD(A[i], scale);
+#pragma unroll
     for (int i = 0; i < 9; ++i) U[i] = (i % 4 == 0) ? 1.0f : 0.0f;
     float maxDiag = 0.0f;
+#pragma unroll
     for (int i = 0; i < 3; ++i) { const float a = fabsf(W[i * 4]); maxDiag = (a > maxDiag) ? a : maxDiag; }
     bool finished = false;
     int sweeps = 0;
     while (!finished && sweeps < 1000) {
         finished = true;
         ++sweeps;
+#pragma unroll
         for (int p = 1; p < 3; ++p) {
+#pragma unroll
             for (int q = 0; q < p; ++q) {
                 const float pm = FM(precision, maxDiag);
                 const float threshold = (considerAsZero < pm) ? pm : considerAsZero;     // std::max(considerAsZero, pm)
                 if (fabsf(W[p * 3 + q]) > threshold || fabsf(W[q * 3 + p]) > threshold) {
                     finished = false;
                     // real_2x2_jacobi_svd
-                    float m[4] = {W[p * 3 + p], W[p * 3 + q], W[q * 3 + p], W[q * 3 + q]};
+                    float m00 = W[p * 3 + p], m01 = W[p * 3 + q], m10 = W[q * 3 + p], m11 = W[q * 3 + q];
                     Rot rot1;
-                    const float t = FA(m[0], m[3]);
-                    const float d = FS(m[2], m[1]);
+                    const float t = FA(m00, m11);
+                    const float d = FS(m10, m01);
                     if (fabsf(d) < FLT_MIN) {
                         rot1.s = 0.0f; rot1.c = 1.0f;
                     } else {
@@ -505,31 +560,37 @@ __device__ __noinline__ void jacobi_svd_normal(const float* A, float* normal) {
                         rot1.s = FD(1.0f, tmp);
                         rot1.c = FD(u, tmp);
                     }
-                    apply_rot(&m[0], 1, &m[2], 1, 2, rot1);
+                    if (!(rot1.c == 1.0f && rot1.s == 0.0f)) { ROT2(m00, m10, rot1); ROT2(m01, m11, rot1); }   // m.applyOnTheLeft(0,1,rot1)
                     Rot jr;
                     {   // makeJacobi(m00, m01, m11)
-                        const float x = m[0], y = m[1], z = m[3];
-                        const float deno = FM(2.0f, fabsf(y));
+                        const float deno = FM(2.0f, fabsf(m01));
                         if (deno < FLT_MIN) {
                             jr.c = 1.0f; jr.s = 0.0f;
                         } else {
-                            const float tau = FD(FS(x, z), deno);
+                            const float tau = FD(FS(m00, m11), deno);
                             const float w   = FSQ(FA(FM(tau, tau), 1.0f));
                             float tt;
                             if (tau > 0.0f) tt = FD(1.0f, FA(tau, w));
                             else            tt = FD(1.0f, FS(tau, w));
                             const float sign_t = tt > 0.0f ? 1.0f : -1.0f;
                             const float n = FD(1.0f, FSQ(FA(FM(tt, tt), 1.0f)));
-                            jr.s = FM(FM(FM(-sign_t, FD(y, fabsf(y))), fabsf(tt)), n);
+                            jr.s = FM(FM(FM(-sign_t, FD(m01, fabsf(m01))), fabsf(tt)), n);
                             jr.c = n;
                         }
                     }
                     // j_left = rot1 * j_right.transpose()
                     const Rot jrt{jr.c, -jr.s};
                     const Rot jl{FS(FM(rot1.c, jrt.c), FM(rot1.s, jrt.s)), FA(FM(rot1.c, jrt.s), FM(rot1.s, jrt.c))};
-                    apply_rot(&W[p * 3], 1, &W[q * 3], 1, 3, jl);      // W.applyOnTheLeft(p,q,j_left)
-                    apply_rot(&U[p], 3, &U[q], 3, 3, jl);              // U.applyOnTheRight(p,q,j_left.transpose())
-                    apply_rot(&W[p], 3, &W[q], 3, 3, jrt);             // W.applyOnTheRight(p,q,j_right)
+                    if (!(jl.c == 1.0f && jl.s == 0.0f)) {
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) ROT2(W[p * 3 + i], W[q * 3 + i], jl);      // W.applyOnTheLeft(p,q,j_left)
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) ROT2(U[i * 3 + p], U[i * 3 + q], jl);      // U.applyOnTheRight(p,q,j_left.transpose())
+                    }
+                    if (!(jrt.c == 1.0f && jrt.s == 0.0f)) {
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) ROT2(W[i * 3 + p], W[i * 3 + q], jrt);     // W.applyOnTheRight(p,q,j_right)
+                    }
                     const float a = fabsf(W[p * 4]), b = fabsf(W[q * 4]);
                     const float ab = (a < b) ? b : a;
                     maxDiag = (maxDiag < ab) ? ab : maxDiag;
@@ -537,27 +598,39 @@ __device__ __noinline__ void jacobi_svd_normal(const float* A, float* normal) {
             }
         }
     }
+    float sv[3];
+#pragma unroll
     for (int i = 0; i < 3; ++i) {
         const float a = W[i * 4];
         sv[i] = fabsf(a);
-        if (a < 0.0f) for (int r = 0; r < 3; ++r) U[r * 3 + i] = -U[r * 3 + i];
+        if (a < 0.0f) { U[0 * 3 + i] = -U[0 * 3 + i]; U[1 * 3 + i] = -U[1 * 3 + i]; U[2 * 3 + i] = -U[2 * 3 + i]; }
     }
+#pragma unroll
     for (int i = 0; i < 3; ++i) sv[i] = FM(sv[i], scale);
-    for (int i = 0; i < 3; ++i) {
-        int pos = 0;
-        float mx = sv[i];
-        for (int k = i + 1; k < 3; ++k) if (sv[k] > mx) { mx = sv[k]; pos = k - i; }
-        if (mx == 0.0f) break;
-        if (pos) {
-            pos += i;
-            const float tsv = sv[i]; sv[i] = sv[pos]; sv[pos] = tsv;
-            for (int r = 0; r < 3; ++r) { const float tu = U[r * 3 + pos]; U[r * 3 + pos] = U[r * 3 + i]; U[r * 3 + i] = tu; }
+    // descending selection sort with "first maximum", stopping at the first zero remainder; only the column that
+    // ends up at position 2 is needed, so track the column permutation in three scalars.
+    int c0 = 0, c1 = 1, c2 = 2;
+    {
+        // i = 0: first maximum of sv[0..2]
+        int pos = 0; float mx = sv[0];
+        if (sv[1] > mx) { mx = sv[1]; pos = 1; }
+        if (sv[2] > mx) { mx = sv[2]; pos = 2; }
+        if (mx != 0.0f) {
+            if (pos == 1) { const float t0 = sv[0]; sv[0] = sv[1]; sv[1] = t0; const int tc = c0; c0 = c1; c1 = tc; }
+            if (pos == 2) { const float t0 = sv[0]; sv[0] = sv[2]; sv[2] = t0; const int tc = c0; c0 = c2; c2 = tc; }
+            // i = 1: first maximum of sv[1..2]
+            if (sv[2] > sv[1]) {
+                if (sv[2] != 0.0f) { const float t1 = sv[1]; sv[1] = sv[2]; sv[2] = t1; const int tc = c1; c1 = c2; c2 = tc; }
+            }
+            // (if max(sv[1], sv[2]) == 0 the loop breaks without swapping: both are 0, so no swap happens above either)
         }
     }
-    normal[0] = U[2]; normal[1] = U[5]; normal[2] = U[8];
+    (void)c0; (void)c1;
+    normal[0] = (c2 == 0) ? U[0] : (c2 == 1) ? U[1] : U[2];
+    normal[1] = (c2 == 0) ? U[3] : (c2 == 1) ? U[4] : U[5];
+    normal[2] = (c2 == 0) ? U[6] : (c2 == 1) ? U[7] : U[8];
 }
 
-constexpr int K4_THREADS = 256;
 constexpr uint32_t K4_PAD = 0xFFFFFFFFu;
 
 // "a sorts after b" for the (z, source position) order -- std::stable_sort by z of the bin's points
@@ -568,22 +641,40 @@ __device__ __forceinline__ bool k4_after(const float* Z, uint32_t a, uint32_t b)
     return (za > zb) || (za == zb && a > b);
 }
 
+// in-place bitonic sort of ORD[0..np2) with comparator `after(a, b)`; np2 a power of two; all threads of the CTA.
+template <int THREADS, class After>
+__device__ __forceinline__ void block_bitonic(uint32_t* ORD, uint32_t np2, After after) {
+    const int tid = threadIdx.x;
+    for (uint32_t k = 2; k <= np2; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = tid; t < (np2 >> 1); t += THREADS) {
+                const uint32_t i = ((t & ~(j - 1u)) << 1) | (t & (j - 1u));   // j is a power of two
+                const uint32_t l = i + j;
+                const uint32_t a = ORD[i], b = ORD[l];
+                const bool asc = ((i & k) == 0);
+                const bool sw  = asc ? after(a, b) : after(b, a);
+                if (sw) { ORD[i] = b; ORD[l] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 // ordered compaction of indices i in [0,n) with pred(i) into out[]; returns count (all threads).
-template <class Pred>
-__device__ uint32_t k4_compact(uint32_t n, uint32_t* out, uint32_t* s_warp /*[K4_THREADS/32 + 1]*/, Pred pred) {
+template <int THREADS, class Pred>
+__device__ __forceinline__ uint32_t k4_compact(uint32_t n, uint32_t* out, uint32_t* s_warp /*[THREADS/32 + 1]*/, Pred pred) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = K4_THREADS / 32;
+    constexpr int NW = THREADS / 32;
     uint32_t total = 0;
-    for (uint32_t base = 0; base < n; base += K4_THREADS) {
+    for (uint32_t base = 0; base < n; base += THREADS) {
         const uint32_t i = base + tid;
         const bool g = (i < n) && pred(i);
         const unsigned bal = __ballot_sync(FULL_MASK, g);
         if (lane == 0) s_warp[warp] = __popc(bal);
         __syncthreads();
-        uint32_t off = total;
-        for (int w = 0; w < warp; ++w) off += s_warp[w];
-        uint32_t round = 0;
-        for (int w = 0; w < NW; ++w) round += s_warp[w];
+        uint32_t off = total, round = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { const uint32_t c = s_warp[w]; off += (w < warp) ? c : 0u; round += c; }
         if (g) out[off + __popc(bal & ((1u << lane) - 1u))] = i;
         total += round;
         __syncthreads();
@@ -591,200 +682,251 @@ __device__ uint32_t k4_compact(uint32_t n, uint32_t* out, uint32_t* s_warp /*[K4
     return total;
 }
 
-__global__ void __launch_bounds__(K4_THREADS)
-k4_rgpf(GpfParams P, FlagRec* __restrict__ recs, const uint32_t* __restrict__ n_recs, uint32_t rec_capacity,
-        const float4* __restrict__ sorted_pts, const uint32_t* __restrict__ sorted_src,
-        const uint32_t* __restrict__ frame_off /*map cloud [F+1]*/, float4* __restrict__ part_pts /*nullable*/,
-        uint8_t* __restrict__ keep_mask /*nullable*/, uint8_t* __restrict__ ground_mask /*nullable*/,
-        uint32_t* __restrict__ frame_rejected /*[F] nullable*/,
-        unsigned char* __restrict__ gscratch, uint32_t smem_cap_points, unsigned long long* __restrict__ fence) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ float    s_normal[3];
-    __shared__ double   s_thd;
-    __shared__ double   s_seed_thr;
-    __shared__ uint32_t s_warp[K4_THREADS / 32 + 1];
+struct K4Shared {
+    float    normal[3];
+    double   thd;
+    double   seed_thr;
+    uint32_t warp[33];
+};
+
+// One flagged bin.  X/Y/Z/ORD/FLG live in shared memory (kShared) or in the bin's slice of the global scratch.
+template <int THREADS, bool kShared>
+__device__ __forceinline__ void k4_process_bin(const GpfParams& P, FlagRec& rc, unsigned char* base, K4Shared& sh,
+                                               const float4* __restrict__ sorted_pts, uint32_t* __restrict__ sorted_src,
+                                               const float4* __restrict__ in_pts, const uint32_t* __restrict__ frame_off,
+                                               float4* __restrict__ part_pts, uint8_t* __restrict__ keep_mask,
+                                               uint8_t* __restrict__ ground_mask, uint32_t* __restrict__ frame_rejected,
+                                               unsigned long long* __restrict__ fence) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t nrec = min(*n_recs, rec_capacity);
+    const uint32_t n = rc.n_points, src_begin = rc.src_begin;
+    const uint32_t fbase = frame_off[rc.frame];
+    uint32_t np2 = 1; while (np2 < n) np2 <<= 1;
+    float*    X   = reinterpret_cast<float*>(base);
+    float*    Y   = X + n;
+    float*    Z   = Y + n;
+    uint32_t* ORD = reinterpret_cast<uint32_t*>(Z + n);
+    uint8_t*  FLG = reinterpret_cast<uint8_t*>(ORD + np2);
 
-    for (uint32_t w = blockIdx.x; w < nrec; w += gridDim.x) {
-        FlagRec& rc = recs[w];
-        const uint32_t n = rc.n_points, src_begin = rc.src_begin;
-        uint32_t np2 = 1; while (np2 < n) np2 <<= 1;
-        // working arrays: shared memory if the bin fits, else this bin's private slice of the global scratch
-        unsigned char* base = (n <= smem_cap_points) ? smem_raw : (gscratch + (size_t)src_begin * 24u);
-        float*    X   = reinterpret_cast<float*>(base);
-        float*    Y   = X + n;
-        float*    Z   = Y + n;
-        uint32_t* ORD = reinterpret_cast<uint32_t*>(Z + n);
-        uint8_t*  FLG = reinterpret_cast<uint8_t*>(ORD + np2);
-
-        for (uint32_t i = tid; i < n; i += K4_THREADS) {
+    if (sorted_pts) {
+        // cloud mode: K2 already placed the bin's points contiguously in source order
+        for (uint32_t i = tid; i < n; i += THREADS) {
             const float4 p = sorted_pts[src_begin + i];
             X[i] = p.x; Y[i] = p.y; Z[i] = p.z; ORD[i] = i;
         }
-        for (uint32_t i = n + tid; i < np2; i += K4_THREADS) ORD[i] = K4_PAD;
+    } else {
+        // mask mode: K2g appended the bin's source indices in arbitrary order; restore source order first
+        for (uint32_t i = tid; i < np2; i += THREADS) ORD[i] = (i < n) ? sorted_src[src_begin + i] : K4_PAD;
         __syncthreads();
-
-        // bitonic sort of ORD by (z, position)
-        for (uint32_t k = 2; k <= np2; k <<= 1) {
-            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-                for (uint32_t t = tid; t < (np2 >> 1); t += K4_THREADS) {
-                    const uint32_t i = ((t / j) * (j << 1)) + (t % j);
-                    const uint32_t l = i + j;
-                    const uint32_t a = ORD[i], b = ORD[l];
-                    const bool asc = ((i & k) == 0);
-                    const bool sw  = asc ? k4_after(Z, a, b) : k4_after(Z, b, a);
-                    if (sw) { ORD[i] = b; ORD[l] = a; }
-                }
-                __syncthreads();
-            }
-        }
-
-        // extract_initial_seeds_ (erasor.cpp:204-231)
-        if (tid == 0) {
-            double sum = 0.0;
-            int    cnt = 0;
-            if (P.num_lowest_pts >= 0) {
-                for (uint32_t i = (uint32_t)P.num_lowest_pts; i < n && cnt < P.num_lpr; ++i) { sum += (double)Z[ORD[i]]; ++cnt; }
-            }
-            const double lpr = cnt != 0 ? sum / cnt : 0.0;
-            rc.lpr_height = lpr;
-            s_seed_thr    = lpr + P.th_seeds;
+        block_bitonic<THREADS>(ORD, np2, [](uint32_t a, uint32_t b) { return a > b; });
+        for (uint32_t i = tid; i < n; i += THREADS) {
+            const uint32_t s = ORD[i];
+            sorted_src[src_begin + i] = s;
+            const float4 p = in_pts[fbase + s];
+            X[i] = p.x; Y[i] = p.y; Z[i] = p.z;
         }
         __syncthreads();
-        const double seed_thr = s_seed_thr;
-        // seeds = sorted prefix with z < lpr + th_seeds; count it
-        uint32_t m;
-        {
-            uint32_t c = 0;
-            for (uint32_t i = tid; i < n; i += K4_THREADS) c += ((double)Z[ORD[i]] < seed_thr) ? 1u : 0u;
-            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL_MASK, c, o);
-            if (lane == 0) s_warp[warp] = c;
-            __syncthreads();
-            m = 0;
-            for (int ww = 0; ww < K4_THREADS / 32; ++ww) m += s_warp[ww];
-            __syncthreads();
-        }
-        if (tid == 0) rc.n_seeds = m;
+        for (uint32_t i = tid; i < n; i += THREADS) ORD[i] = i;
+    }
+    for (uint32_t i = n + tid; i < np2; i += THREADS) ORD[i] = K4_PAD;
+    __syncthreads();
 
-        uint32_t n_empty = 0;
-        for (int it = 0; it < P.iters; ++it) {
-            // ---- estimate_plane_ over ORD[0..m) (erasor.cpp:183-198) ----
-            if (warp == 0) {
-                // pcl::computeMeanAndCovarianceMatrix: nine float accumulators walked in list order; lane L owns accu[L]
-                const float* pa = (lane == 0 || lane == 1 || lane == 2 || lane == 6) ? X : (lane == 3 || lane == 4 || lane == 7) ? Y : Z;
-                const float* pb = (lane == 0) ? X : (lane == 1 || lane == 3) ? Y : Z;
-                const bool   unit_b = lane >= 6;
-                float Ka = 0.0f, Kb = 0.0f, K0 = 0.0f, K1 = 0.0f, K2 = 0.0f;
-                if (P.cov_mode == 1 && m > 0) {
-                    const uint32_t f0 = ORD[0];
-                    K0 = X[f0]; K1 = Y[f0]; K2 = Z[f0];
-                    Ka = pa[f0]; Kb = unit_b ? 0.0f : pb[f0];
-                }
-                float acc = 0.0f;
-                if (lane < 9) {
-                    uint32_t i = 0;
-                    for (; i + 4 <= m; i += 4) {
-                        const uint32_t i0 = ORD[i], i1 = ORD[i + 1], i2 = ORD[i + 2], i3 = ORD[i + 3];
-                        const float a0 = FS(pa[i0], Ka), a1 = FS(pa[i1], Ka), a2 = FS(pa[i2], Ka), a3 = FS(pa[i3], Ka);
-                        const float b0 = unit_b ? 1.0f : FS(pb[i0], Kb), b1 = unit_b ? 1.0f : FS(pb[i1], Kb);
-                        const float b2 = unit_b ? 1.0f : FS(pb[i2], Kb), b3 = unit_b ? 1.0f : FS(pb[i3], Kb);
-                        const float q0 = FM(a0, b0), q1 = FM(a1, b1), q2 = FM(a2, b2), q3 = FM(a3, b3);
-                        acc = FA(acc, q0); acc = FA(acc, q1); acc = FA(acc, q2); acc = FA(acc, q3);
-                    }
-                    for (; i < m; ++i) {
-                        const uint32_t i0 = ORD[i];
-                        const float a0 = FS(pa[i0], Ka);
-                        const float b0 = unit_b ? 1.0f : FS(pb[i0], Kb);
-                        acc = FA(acc, FM(a0, b0));
-                    }
-                    if (m != 0) acc = FD(acc, (float)m);
-                }
-                float a[9];
+    // std::sort by z (erasor.cpp:240), ties in source order
+    block_bitonic<THREADS>(ORD, np2, [&](uint32_t a, uint32_t b) { return k4_after(Z, a, b); });
+
+    // extract_initial_seeds_ (erasor.cpp:204-231)
+    if (tid == 0) {
+        double sum = 0.0;
+        int    cnt = 0;
+        if (P.num_lowest_pts >= 0) {
+            for (uint32_t i = (uint32_t)P.num_lowest_pts; i < n && cnt < P.num_lpr; ++i) { sum += (double)Z[ORD[i]]; ++cnt; }
+        }
+        const double lpr = cnt != 0 ? sum / cnt : 0.0;
+        rc.lpr_height = lpr;
+        sh.seed_thr   = lpr + P.th_seeds;
+    }
+    __syncthreads();
+    const double seed_thr = sh.seed_thr;
+    uint32_t m;   // seeds = sorted prefix with z < lpr + th_seeds
+    {
+        uint32_t c = 0;
+        for (uint32_t i = tid; i < n; i += THREADS) c += ((double)Z[ORD[i]] < seed_thr) ? 1u : 0u;
 #pragma unroll
-                for (int k = 0; k < 9; ++k) a[k] = __shfl_sync(FULL_MASK, acc, k);
-                if (lane == 0) {
-                    float cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, mean[3] = {0, 0, 0};
-                    if (m != 0) {
-                        mean[0] = (P.cov_mode == 1) ? FA(a[6], K0) : a[6];
-                        mean[1] = (P.cov_mode == 1) ? FA(a[7], K1) : a[7];
-                        mean[2] = (P.cov_mode == 1) ? FA(a[8], K2) : a[8];
-                        cov[0] = FS(a[0], FM(a[6], a[6]));
-                        cov[1] = FS(a[1], FM(a[6], a[7]));
-                        cov[2] = FS(a[2], FM(a[6], a[8]));
-                        cov[4] = FS(a[3], FM(a[7], a[7]));
-                        cov[5] = FS(a[4], FM(a[7], a[8]));
-                        cov[8] = FS(a[5], FM(a[8], a[8]));
-                        cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL_MASK, c, o);
+        if (lane == 0) sh.warp[warp] = c;
+        __syncthreads();
+        m = 0;
+#pragma unroll
+        for (int ww = 0; ww < THREADS / 32; ++ww) m += sh.warp[ww];
+        __syncthreads();
+    }
+    if (tid == 0) rc.n_seeds = m;
+
+    uint32_t n_empty = 0;
+    for (int it = 0; it < P.iters; ++it) {
+        // ---- estimate_plane_ over ORD[0..m) (erasor.cpp:183-198) ----
+        if (warp == 0) {
+            // pcl::computeMeanAndCovarianceMatrix: nine float accumulators walked in list order; lane L owns accu[L].
+            // The FADD chain (4 cycles per element) is the only true dependency; loads and products run one group ahead.
+            const float* pa = (lane == 0 || lane == 1 || lane == 2 || lane == 6) ? X : (lane == 3 || lane == 4 || lane == 7) ? Y : Z;
+            const float* pb = (lane == 0) ? X : (lane == 1 || lane == 3) ? Y : Z;
+            const bool   unit_b = lane >= 6;
+            float Ka = 0.0f, Kb = 0.0f, K0 = 0.0f, K1 = 0.0f, K2 = 0.0f;
+            if (P.cov_mode == 1 && m > 0) {
+                const uint32_t f0 = ORD[0];
+                K0 = X[f0]; K1 = Y[f0]; K2 = Z[f0];
+                Ka = pa[f0]; Kb = unit_b ? 0.0f : pb[f0];
+            }
+            float acc = 0.0f;
+            if (lane < 9) {
+                auto prod = [&](uint32_t idx) -> float {
+                    const float a = FS(pa[idx], Ka);
+                    const float b = unit_b ? 1.0f : FS(pb[idx], Kb);
+                    return FM(a, b);
+                };
+                uint32_t i = 0;
+                if (m >= 8) {
+                    float q0 = prod(ORD[0]), q1 = prod(ORD[1]), q2 = prod(ORD[2]), q3 = prod(ORD[3]);
+                    for (i = 4; i + 4 <= m; i += 4) {
+                        const float r0 = prod(ORD[i]), r1 = prod(ORD[i + 1]), r2 = prod(ORD[i + 2]), r3 = prod(ORD[i + 3]);
+                        acc = FA(acc, q0); acc = FA(acc, q1); acc = FA(acc, q2); acc = FA(acc, q3);
+                        q0 = r0; q1 = r1; q2 = r2; q3 = r3;
                     }
-                    float nrm[3];
-                    jacobi_svd_normal(cov, nrm);
-                    const float dot = FA(FA(FM(nrm[0], mean[0]), FM(nrm[1], mean[1])), FM(nrm[2], mean[2]));
-                    const double d  = (double)(-dot);
-                    s_normal[0] = nrm[0]; s_normal[1] = nrm[1]; s_normal[2] = nrm[2];
-                    s_thd = P.th_dist - d;
-                    if (it < kMaxIter) {
-                        rc.normal_d[it][0] = nrm[0]; rc.normal_d[it][1] = nrm[1]; rc.normal_d[it][2] = nrm[2]; rc.normal_d[it][3] = d;
-                    }
+                    acc = FA(acc, q0); acc = FA(acc, q1); acc = FA(acc, q2); acc = FA(acc, q3);
+                }
+                for (; i < m; ++i) acc = FA(acc, prod(ORD[i]));
+                if (m != 0) acc = FD(acc, (float)m);
+            }
+            float a[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) a[k] = __shfl_sync(FULL_MASK, acc, k);
+            if (lane == 0) {
+                float cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, mean[3] = {0, 0, 0};
+                if (m != 0) {
+                    mean[0] = (P.cov_mode == 1) ? FA(a[6], K0) : a[6];
+                    mean[1] = (P.cov_mode == 1) ? FA(a[7], K1) : a[7];
+                    mean[2] = (P.cov_mode == 1) ? FA(a[8], K2) : a[8];
+                    cov[0] = FS(a[0], FM(a[6], a[6]));
+                    cov[1] = FS(a[1], FM(a[6], a[7]));
+                    cov[2] = FS(a[2], FM(a[6], a[8]));
+                    cov[4] = FS(a[3], FM(a[7], a[7]));
+                    cov[5] = FS(a[4], FM(a[7], a[8]));
+                    cov[8] = FS(a[5], FM(a[8], a[8]));
+                    cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
+                }
+                float nrm[3];
+                jacobi_svd_normal(cov, nrm);
+                const float dot = FA(FA(FM(nrm[0], mean[0]), FM(nrm[1], mean[1])), FM(nrm[2], mean[2]));
+                const double d  = (double)(-dot);
+                sh.normal[0] = nrm[0]; sh.normal[1] = nrm[1]; sh.normal[2] = nrm[2];
+                sh.thd = P.th_dist - d;
+                if (it < kMaxIter) {
+                    rc.normal_d[it][0] = nrm[0]; rc.normal_d[it][1] = nrm[1]; rc.normal_d[it][2] = nrm[2]; rc.normal_d[it][3] = d;
                 }
             }
-            if (m == 0) ++n_empty;
-            __syncthreads();
-            const float n0 = s_normal[0], n1 = s_normal[1], n2 = s_normal[2];
-            const double thd = s_thd;
-            // ---- classify every point of the bin in source order (erasor.cpp:265-281) ----
-            for (uint32_t i = tid; i < n; i += K4_THREADS) {
-                const float r = FA(FA(FM(X[i], n0), FM(Y[i], n1)), FM(Z[i], n2));
-                FLG[i] = ((double)r < thd) ? 1 : 0;
-            }
-            __syncthreads();
-            m = k4_compact(n, ORD, s_warp, [&](uint32_t i) { return FLG[i] != 0; });
-            if (tid == 0 && it < kMaxIter) rc.n_ground[it] = m;
         }
-        // with gf_iter == 0 the reference returns the seeds as ground and nothing as outliers... but then
-        // non_ground_pc_ is never filled; FLG must mirror "ground = seeds" in that case.
-        if (P.iters <= 0) {
-            for (uint32_t i = tid; i < n; i += K4_THREADS) FLG[i] = 0;
-            __syncthreads();
-            for (uint32_t i = tid; i < m; i += K4_THREADS) FLG[ORD[i]] = 1;
-            __syncthreads();
-        }
-        if (tid == 0) { rc.n_ground_final = m; rc.n_empty_fits = n_empty; }
-        if (tid == 0 && n_empty) atomicAdd(&fence[1], (unsigned long long)n_empty);
-
-        // ---- outputs ----
-        const uint32_t fbase = frame_off[rc.frame];
-        if (keep_mask || ground_mask) {
-            for (uint32_t i = tid; i < n; i += K4_THREADS) {
-                const uint32_t s = sorted_src[src_begin + i];
-                if (keep_mask && !FLG[i] && P.iters > 0) keep_mask[fbase + s] = 0;
-                if (ground_mask && FLG[i]) ground_mask[fbase + s] = 1;
-            }
-        }
-        if (frame_rejected && tid == 0 && P.iters > 0) atomicAdd(&frame_rejected[rc.frame], n - m);
-        if (part_pts) {
-            // partitioned copy of the bin: [ground, source order][non-ground, source order]
-            for (uint32_t i = tid; i < m; i += K4_THREADS) part_pts[src_begin + i] = sorted_pts[src_begin + ORD[i]];
-            __syncthreads();
-            const uint32_t m2 = k4_compact(n, ORD, s_warp, [&](uint32_t i) { return FLG[i] == 0; });
-            for (uint32_t i = tid; i < m2; i += K4_THREADS) part_pts[src_begin + m + i] = sorted_pts[src_begin + ORD[i]];
+        if (m == 0) ++n_empty;
+        __syncthreads();
+        const float n0 = sh.normal[0], n1 = sh.normal[1], n2 = sh.normal[2];
+        const double thd = sh.thd;
+        // ---- classify every point of the bin in source order (erasor.cpp:265-281) ----
+        for (uint32_t i = tid; i < n; i += THREADS) {
+            const float r = FA(FA(FM(X[i], n0), FM(Y[i], n1)), FM(Z[i], n2));
+            FLG[i] = ((double)r < thd) ? 1 : 0;
         }
         __syncthreads();
+        m = k4_compact<THREADS>(n, ORD, sh.warp, [&](uint32_t i) { return FLG[i] != 0; });
+        if (tid == 0 && it < kMaxIter) rc.n_ground[it] = m;
+    }
+    // gf_iter == 0: the reference returns the seeds as ground and fills no outliers (erasor.cpp:260-285)
+    if (P.iters <= 0) {
+        for (uint32_t i = tid; i < n; i += THREADS) FLG[i] = 0;
+        __syncthreads();
+        for (uint32_t i = tid; i < m; i += THREADS) FLG[ORD[i]] = 1;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        rc.n_ground_final = m; rc.n_empty_fits = n_empty;
+        if (n_empty) atomicAdd(&fence[1], (unsigned long long)n_empty);
+        if (frame_rejected && P.iters > 0) atomicAdd(&frame_rejected[rc.frame], n - m);
+    }
+
+    // ---- outputs ----
+    if (keep_mask || ground_mask) {
+        for (uint32_t i = tid; i < n; i += THREADS) {
+            const uint32_t s = sorted_src[src_begin + i];
+            if (keep_mask && !FLG[i] && P.iters > 0) keep_mask[fbase + s] = 0;
+            if (ground_mask && FLG[i]) ground_mask[fbase + s] = 1;
+        }
+    }
+    if (part_pts) {
+        // partitioned copy of the bin: [ground, source order][non-ground, source order]
+        for (uint32_t i = tid; i < m; i += THREADS) part_pts[src_begin + i] = sorted_pts[src_begin + ORD[i]];
+        __syncthreads();
+        const uint32_t m2 = k4_compact<THREADS>(n, ORD, sh.warp, [&](uint32_t i) { return FLG[i] == 0; });
+        for (uint32_t i = tid; i < m2; i += THREADS) part_pts[src_begin + m + i] = sorted_pts[src_begin + ORD[i]];
+    }
+    __syncthreads();
+}
+
+// Records are served to size classes: this launch handles bins with lo < n_points <= hi; bins above smem_cap_points
+// (only in the last class) work in their slice of the global scratch.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k4_rgpf(GpfParams P, FlagRec* __restrict__ recs, const uint32_t* __restrict__ n_recs, uint32_t rec_capacity,
+        uint32_t n_lo, uint32_t n_hi, const float4* __restrict__ sorted_pts, uint32_t* __restrict__ sorted_src,
+        const float4* __restrict__ in_pts, const uint32_t* __restrict__ frame_off /*map cloud [F+1]*/,
+        float4* __restrict__ part_pts /*nullable*/, uint8_t* __restrict__ keep_mask /*nullable*/,
+        uint8_t* __restrict__ ground_mask /*nullable*/, uint32_t* __restrict__ frame_rejected /*[F] nullable*/,
+        unsigned char* __restrict__ gscratch, uint32_t smem_cap_points, unsigned long long* __restrict__ fence) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ K4Shared sh;
+    const uint32_t nrec = min(*n_recs, rec_capacity);
+    for (uint32_t w = blockIdx.x; w < nrec; w += gridDim.x) {
+        FlagRec& rc = recs[w];
+        const uint32_t n = rc.n_points;
+        if (n <= n_lo || n > n_hi) continue;
+        if (n <= smem_cap_points)
+            k4_process_bin<THREADS, true>(P, rc, smem_raw, sh, sorted_pts, sorted_src, in_pts, frame_off, part_pts, keep_mask,
+                                          ground_mask, frame_rejected, fence);
+        else
+            k4_process_bin<THREADS, false>(P, rc, gscratch + (size_t)rc.src_begin * 24u, sh, sorted_pts, sorted_src, in_pts, frame_off,
+                                           part_pts, keep_mask, ground_mask, frame_rejected, fence);
     }
 }
 
-cudaError_t launch_k4(cudaStream_t st, const GpfParams& P, FlagRec* recs, const uint32_t* n_recs, uint32_t rec_capacity,
-                      const float4* sorted_pts, const uint32_t* sorted_src, const uint32_t* frame_off, float4* part_pts,
-                      uint8_t* keep_mask, uint8_t* ground_mask, uint32_t* frame_rejected, unsigned char* gscratch,
-                      int grid, unsigned long long* fence) {
-    constexpr uint32_t SMEM_BYTES = 72 * 1024;
+template <int THREADS>
+static cudaError_t launch_k4_class(cudaStream_t st, const GpfParams& P, FlagRec* recs, const uint32_t* n_recs, uint32_t rec_capacity,
+                                   uint32_t n_lo, uint32_t n_hi, uint32_t smem_bytes, const float4* sorted_pts, uint32_t* sorted_src,
+                                   const float4* in_pts, const uint32_t* frame_off, float4* part_pts, uint8_t* keep_mask,
+                                   uint8_t* ground_mask, uint32_t* frame_rejected, unsigned char* gscratch, int grid,
+                                   unsigned long long* fence) {
     // 12 n (xyz) + 4 np2 (<= 8n, order) + n (flags) <= 21 n + 16
-    const uint32_t cap = (SMEM_BYTES - 64) / 21u;
-    cudaError_t e = cudaFuncSetAttribute(k4_rgpf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    const uint32_t cap = (smem_bytes - 64) / 21u;
+    auto kern = k4_rgpf<THREADS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
-    k4_rgpf<<<grid, K4_THREADS, SMEM_BYTES, st>>>(P, recs, n_recs, rec_capacity, sorted_pts, sorted_src, frame_off, part_pts,
-                                                  keep_mask, ground_mask, frame_rejected, gscratch, cap, fence);
+    kern<<<grid, THREADS, smem_bytes, st>>>(P, recs, n_recs, rec_capacity, n_lo, n_hi, sorted_pts, sorted_src, in_pts, frame_off,
+                                            part_pts, keep_mask, ground_mask, frame_rejected, gscratch, cap, fence);
     return cudaGetLastError();
+}
+
+int k4_num_launches() { return 3; }
+
+cudaError_t launch_k4(cudaStream_t st, const GpfParams& P, FlagRec* recs, const uint32_t* n_recs, uint32_t rec_capacity,
+                      const float4* sorted_pts, uint32_t* sorted_src, const float4* in_pts, const uint32_t* frame_off, float4* part_pts,
+                      uint8_t* keep_mask, uint8_t* ground_mask, uint32_t* frame_rejected, unsigned char* gscratch,
+                      int sm_count, unsigned long long* fence) {
+    // size classes: small bins get small CTAs (the plane fit is serial in one warp, so many small CTAs per SM
+    // keep the SM busy), large bins get the whole shared memory of an SM, anything beyond works in global scratch.
+    cudaError_t e;
+    e = launch_k4_class<64>(st, P, recs, n_recs, rec_capacity, 0u, 512u, 12 * 1024, sorted_pts, sorted_src, in_pts, frame_off, part_pts,
+                            keep_mask, ground_mask, frame_rejected, gscratch, sm_count * 16, fence);
+    if (e != cudaSuccess) return e;
+    e = launch_k4_class<256>(st, P, recs, n_recs, rec_capacity, 512u, 2560u, 54 * 1024, sorted_pts, sorted_src, in_pts, frame_off, part_pts,
+                             keep_mask, ground_mask, frame_rejected, gscratch, sm_count * 4, fence);
+    if (e != cudaSuccess) return e;
+    return launch_k4_class<1024>(st, P, recs, n_recs, rec_capacity, 2560u, 0xFFFFFFFFu, 200 * 1024, sorted_pts, sorted_src, in_pts, frame_off,
+                                 part_pts, keep_mask, ground_mask, frame_rejected, gscratch, sm_count, fence);
 }
 
 // ============================================================================================
@@ -795,6 +937,8 @@ cudaError_t launch_k4(cudaStream_t st, const GpfParams& P, FlagRec* recs, const 
 //      Unpinned third-party choices, fixed the same way in the oracle: members of one voxel are summed in input
 //      order; 1-NN ties go to the lowest input index.
 // ============================================================================================
+constexpr int K4B_THREADS = 256;
+
 __device__ __forceinline__ bool k4b_after(const uint32_t* KEY, uint32_t a, uint32_t b) {
     if (a == K4_PAD) return b != K4_PAD;
     if (b == K4_PAD) return false;
@@ -802,15 +946,15 @@ __device__ __forceinline__ bool k4b_after(const uint32_t* KEY, uint32_t a, uint3
     return (ka > kb) || (ka == kb && a > b);
 }
 
-__global__ void __launch_bounds__(K4_THREADS)
+__global__ void __launch_bounds__(K4B_THREADS)
 k4b_voxelize(float leaf_f, int B, const FlagRec* __restrict__ recs, const uint32_t* __restrict__ n_recs, uint32_t rec_capacity,
              const uint32_t* __restrict__ cnt /*[2][1][B+1]*/, const uint32_t* __restrict__ dst_start /*[2][1][B+2]*/,
              const float4* __restrict__ qry_sorted, const float4* __restrict__ part_pts,
              float4* __restrict__ vox_pts, uint32_t* __restrict__ vox_cnt, uint32_t* __restrict__ vox_start,
              unsigned char* __restrict__ gscratch, uint32_t smem_cap_points) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ uint32_t s_warp[K4_THREADS / 32 + 1];
-    __shared__ float    s_red[6][K4_THREADS / 32];
+    __shared__ uint32_t s_warp[K4B_THREADS / 32 + 1];
+    __shared__ float    s_red[6][K4B_THREADS / 32];
     __shared__ float    s_minmax[6];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t nrec = min(*n_recs, rec_capacity);
@@ -836,16 +980,16 @@ k4b_voxelize(float leaf_f, int B, const FlagRec* __restrict__ recs, const uint32
             if (tid == 0) { vox_cnt[rc.slot] = 0u; vox_start[rc.slot] = region; }
             continue;
         }
-        for (uint32_t i = tid; i < n; i += K4_THREADS) {
+        for (uint32_t i = tid; i < n; i += K4B_THREADS) {
             const float4 p = (i < qc) ? qry_sorted[dsq[b] + i] : part_pts[rc.src_begin + (i - qc)];
             X[i] = p.x; Y[i] = p.y; Z[i] = p.z; I[i] = p.w; ORD[i] = i;
         }
-        for (uint32_t i = n + tid; i < np2; i += K4_THREADS) ORD[i] = K4_PAD;
+        for (uint32_t i = n + tid; i < np2; i += K4B_THREADS) ORD[i] = K4_PAD;
         __syncthreads();
         // getMinMax3D
         {
             float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-            for (uint32_t i = tid; i < n; i += K4_THREADS) {
+            for (uint32_t i = tid; i < n; i += K4B_THREADS) {
                 mn[0] = fminf(mn[0], X[i]); mx[0] = fmaxf(mx[0], X[i]);
                 mn[1] = fminf(mn[1], Y[i]); mx[1] = fmaxf(mx[1], Y[i]);
                 mn[2] = fminf(mn[2], Z[i]); mx[2] = fmaxf(mx[2], Z[i]);
@@ -861,7 +1005,7 @@ k4b_voxelize(float leaf_f, int B, const FlagRec* __restrict__ recs, const uint32
             __syncthreads();
             if (tid < 6) {
                 float v = s_red[tid][0];
-                for (int ww = 1; ww < K4_THREADS / 32; ++ww) v = (tid < 3) ? fminf(v, s_red[tid][ww]) : fmaxf(v, s_red[tid][ww]);
+                for (int ww = 1; ww < K4B_THREADS / 32; ++ww) v = (tid < 3) ? fminf(v, s_red[tid][ww]) : fmaxf(v, s_red[tid][ww]);
                 s_minmax[tid] = v;
             }
             __syncthreads();
@@ -877,39 +1021,27 @@ k4b_voxelize(float leaf_f, int B, const FlagRec* __restrict__ recs, const uint32
         if (overflow) {
             // "Leaf size is too small for the input dataset": output = input
             nv = n;
-            for (uint32_t i = tid; i < n; i += K4_THREADS) out[i] = make_float4(X[i], Y[i], Z[i], I[i]);
+            for (uint32_t i = tid; i < n; i += K4B_THREADS) out[i] = make_float4(X[i], Y[i], Z[i], I[i]);
             __syncthreads();
         } else {
             const int mb0 = (int)floorf(FM(mnx, inv)), mb1 = (int)floorf(FM(mny, inv)), mb2 = (int)floorf(FM(mnz, inv));
             const int Mb0 = (int)floorf(FM(mxx, inv)), Mb1 = (int)floorf(FM(mxy, inv));
             const int div0 = Mb0 - mb0 + 1, div1 = Mb1 - mb1 + 1;
             const int mul1 = div0, mul2 = div0 * div1;
-            for (uint32_t i = tid; i < n; i += K4_THREADS) {
+            for (uint32_t i = tid; i < n; i += K4B_THREADS) {
                 const int ijk0 = (int)FS(floorf(FM(X[i], inv)), (float)mb0);
                 const int ijk1 = (int)FS(floorf(FM(Y[i], inv)), (float)mb1);
                 const int ijk2 = (int)FS(floorf(FM(Z[i], inv)), (float)mb2);
                 KEY[i] = (uint32_t)(ijk0 + ijk1 * mul1 + ijk2 * mul2);
             }
             __syncthreads();
-            for (uint32_t k = 2; k <= np2; k <<= 1) {
-                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-                    for (uint32_t t = tid; t < (np2 >> 1); t += K4_THREADS) {
-                        const uint32_t i = ((t / j) * (j << 1)) + (t % j);
-                        const uint32_t l = i + j;
-                        const uint32_t a = ORD[i], c = ORD[l];
-                        const bool asc = ((i & k) == 0);
-                        const bool sw  = asc ? k4b_after(KEY, a, c) : k4b_after(KEY, c, a);
-                        if (sw) { ORD[i] = c; ORD[l] = a; }
-                    }
-                    __syncthreads();
-                }
-            }
+            block_bitonic<K4B_THREADS>(ORD, np2, [&](uint32_t a, uint32_t c) { return k4b_after(KEY, a, c); });
             // voxel heads in sorted order
-            nv = k4_compact(n, VST, s_warp, [&](uint32_t i) { return i == 0 || KEY[ORD[i]] != KEY[ORD[i - 1]]; });
+            nv = k4_compact<K4B_THREADS>(n, VST, s_warp, [&](uint32_t i) { return i == 0 || KEY[ORD[i]] != KEY[ORD[i - 1]]; });
             if (tid == 0) VST[nv] = n;
             __syncthreads();
             // centroids: float sums in member order, divided by float(count)  (pcl::CentroidPoint)
-            for (uint32_t v = tid; v < nv; v += K4_THREADS) {
+            for (uint32_t v = tid; v < nv; v += K4B_THREADS) {
                 const uint32_t a = VST[v], e = VST[v + 1];
                 float sx = 0.0f, sy = 0.0f, sz = 0.0f, si = 0.0f;
                 for (uint32_t li = a; li < e; ++li) {
@@ -922,7 +1054,7 @@ k4b_voxelize(float leaf_f, int B, const FlagRec* __restrict__ recs, const uint32
             __syncthreads();
         }
         // exact 1-NN of every centroid into the bin's points; copy that point's intensity
-        for (uint32_t v = tid; v < nv; v += K4_THREADS) {
+        for (uint32_t v = tid; v < nv; v += K4B_THREADS) {
             const float4 c = out[v];
             float best = __int_as_float(0x7f800000);
             uint32_t bi = 0;
@@ -946,7 +1078,7 @@ cudaError_t launch_k4b(cudaStream_t st, float leaf, int B, const FlagRec* recs, 
     const uint32_t cap = (SMEM_BYTES - 64) / 32u;
     cudaError_t e = cudaFuncSetAttribute(k4b_voxelize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    k4b_voxelize<<<grid, K4_THREADS, SMEM_BYTES, st>>>(leaf, B, recs, n_recs, rec_capacity, cnt, dst_start, qry_sorted, part_pts,
+    k4b_voxelize<<<grid, K4B_THREADS, SMEM_BYTES, st>>>(leaf, B, recs, n_recs, rec_capacity, cnt, dst_start, qry_sorted, part_pts,
                                                        vox_pts, vox_cnt, vox_start, gscratch, cap);
     return cudaGetLastError();
 }
@@ -1069,16 +1201,20 @@ cudaError_t launch_k5(cudaStream_t st, int B, int version, int skip_voxelize, co
 // ============================================================================================
 // small utilities
 // ============================================================================================
-__global__ void k_init_tables(uint32_t* zmin, uint32_t* zmax, size_t n, uint32_t* n_recs, uint32_t* frame_rejected, int F) {
+__global__ void k_init_tables(uint32_t* zmin, uint32_t* zmax, size_t n, uint32_t* cnt, size_t n_cnt, uint32_t* n_recs,
+                              uint32_t* frame_rejected, int F) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { zmin[i] = 0xFFFFFFFFu; zmax[i] = 0u; }
+    if (i < n_cnt) cnt[i] = 0u;
     if (i == 0) *n_recs = 0u;
     if (frame_rejected && i < (size_t)F) frame_rejected[i] = 0u;
 }
-cudaError_t launch_init_tables(cudaStream_t st, uint32_t* zmin, uint32_t* zmax, size_t n, uint32_t* n_recs, uint32_t* frame_rejected, int F) {
-    const size_t m = n > (size_t)F ? n : (size_t)F;
+cudaError_t launch_init_tables(cudaStream_t st, uint32_t* zmin, uint32_t* zmax, size_t n, uint32_t* cnt, size_t n_cnt, uint32_t* n_recs,
+                               uint32_t* frame_rejected, int F) {
+    size_t m = n > (size_t)F ? n : (size_t)F;
+    m = m > n_cnt ? m : n_cnt;
     const int blocks = (int)((m + 255) / 256);
-    k_init_tables<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(zmin, zmax, n, n_recs, frame_rejected, F);
+    k_init_tables<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(zmin, zmax, n, cnt, n_cnt, n_recs, frame_rejected, F);
     return cudaGetLastError();
 }
 

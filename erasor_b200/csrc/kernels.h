@@ -19,26 +19,33 @@ struct CopyJob {
 size_t k1_smem_bytes(int R, int B);
 size_t k3_smem_bytes(int B);
 
-cudaError_t launch_init_tables(cudaStream_t st, uint32_t* zmin, uint32_t* zmax, size_t n, uint32_t* n_recs,
+cudaError_t launch_init_tables(cudaStream_t st, uint32_t* zmin, uint32_t* zmax, size_t n, uint32_t* cnt, size_t n_cnt, uint32_t* n_recs,
                                uint32_t* frame_rejected, int F);
 
 cudaError_t launch_k1(cudaStream_t st, const BinTablesView& T, const float4* map_pts, const float4* qry_pts,
                       const ChunkDesc* chunks, int n_chunks, uint16_t* bin_map, uint16_t* bin_qry, uint32_t* ch_cnt,
-                      uint32_t* zmin, uint32_t* zmax, int B, int F, unsigned long long* fence);
+                      uint32_t* zmin, uint32_t* zmax, uint32_t* cnt_tab, int B, int F, bool rows, unsigned long long* fence);
 
 cudaError_t launch_k3(cudaStream_t st, const SrtParams& P, int F, const uint32_t* chunk_range, uint32_t* ch_cnt,
-                      const uint32_t* zmin, const uint32_t* zmax, const uint32_t* frame_off, uint32_t* cnt, uint32_t* dst_start,
-                      uint8_t* status, uint8_t* action, uint32_t* flag_slot, uint32_t* n_flagged, FlagRec* recs,
-                      uint32_t* n_recs, uint32_t rec_capacity);
+                      const uint32_t* zmin, const uint32_t* zmax, const uint32_t* frame_off, const uint32_t* cnt, uint32_t* dst_start,
+                      uint8_t* status, uint8_t* action, uint32_t* flag_slot, uint32_t* n_flagged, uint32_t* frame_rec_base,
+                      FlagRec* recs, uint32_t* n_recs, uint32_t rec_capacity);
+
+cudaError_t launch_k2_gather(cudaStream_t st, const ChunkDesc* chunks, uint32_t n_chunks_map, int B, const uint16_t* bin_ids,
+                             const uint32_t* flag_slot, const uint32_t* frame_rec_base, FlagRec* recs, uint32_t rec_capacity,
+                             uint32_t* out_src);
 
 cudaError_t launch_k2(cudaStream_t st, const ChunkDesc* chunks, uint32_t chunk_base, uint32_t n_chunks, int F,
                       const uint16_t* bin_ids, const float4* pts, const uint32_t* ch_cnt, const uint32_t* dst_start,
                       float4* out_pts, uint32_t* out_src, int B);
 
+int k4_num_launches();
+// sorted_pts != nullptr: cloud mode (bins contiguous in source order, from K2).  sorted_pts == nullptr: mask mode
+// (sorted_src holds K2g's unordered source indices; points are gathered from in_pts).
 cudaError_t launch_k4(cudaStream_t st, const GpfParams& P, FlagRec* recs, const uint32_t* n_recs, uint32_t rec_capacity,
-                      const float4* sorted_pts, const uint32_t* sorted_src, const uint32_t* frame_off, float4* part_pts,
+                      const float4* sorted_pts, uint32_t* sorted_src, const float4* in_pts, const uint32_t* frame_off, float4* part_pts,
                       uint8_t* keep_mask, uint8_t* ground_mask, uint32_t* frame_rejected, unsigned char* gscratch,
-                      int grid, unsigned long long* fence);
+                      int sm_count, unsigned long long* fence);
 
 cudaError_t launch_k4b(cudaStream_t st, float leaf, int B, const FlagRec* recs, const uint32_t* n_recs, uint32_t rec_capacity,
                        const uint32_t* cnt, const uint32_t* dst_start, const float4* qry_sorted, const float4* part_pts,

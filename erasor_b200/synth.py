@@ -133,21 +133,44 @@ class Scene:
             tg = np.where(dz < -1e-6, -o_w[2] / dz, np.inf)
         t_best = tg.copy()
         lab[:] = LABEL_ROAD
-        # boxes: slab test, only those within range of the sensor
+        # boxes: slab test, restricted to the azimuth columns each box can subtend
         inv = 1.0 / np.where(np.abs(d_w) < 1e-12, 1e-12, d_w)
+        inv = inv.reshape(n_beams, n_az, 3)
+        t_best = t_best.reshape(n_beams, n_az)
+        lab = lab.reshape(n_beams, n_az)
+        az_w = az + yaw                                   # world azimuth of column k (increasing)
+        daz = 2 * np.pi / n_az
         for b in self.boxes:
             shift = b.vel * k
             lo, hi = b.lo + shift, b.hi + shift
             ctr = 0.5 * (lo + hi)
             if np.hypot(ctr[0] - o_w[0], ctr[1] - o_w[1]) > max_range + 30.0:
                 continue
-            t0 = (lo - o_w) * inv
-            t1 = (hi - o_w) * inv
-            tn = np.minimum(t0, t1).max(axis=1)
-            tf = np.maximum(t0, t1).min(axis=1)
-            hit = (tf >= np.maximum(tn, 0.0)) & (tn > 0.5) & (tn < t_best)
-            t_best = np.where(hit, tn, t_best)
-            lab = np.where(hit, np.float32(b.label), lab)
+            if lo[0] <= o_w[0] <= hi[0] and lo[1] <= o_w[1] <= hi[1]:
+                cols = np.arange(n_az)
+            else:
+                cx = np.array([lo[0], lo[0], hi[0], hi[0]]) - o_w[0]
+                cy = np.array([lo[1], hi[1], lo[1], hi[1]]) - o_w[1]
+                ac = np.arctan2(ctr[1] - o_w[1], ctr[0] - o_w[0])
+                rel = np.arctan2(cy, cx) - ac
+                rel = (rel + np.pi) % (2 * np.pi) - np.pi
+                a0, a1 = ac + rel.min() - daz, ac + rel.max() + daz
+                k0 = int(np.floor((a0 - az_w[0]) / daz))
+                k1 = int(np.ceil((a1 - az_w[0]) / daz))
+                cols = np.arange(k0, k1 + 1) % n_az
+                if len(cols) >= n_az:
+                    cols = np.arange(n_az)
+            iv = inv[:, cols, :]
+            t0 = (lo - o_w) * iv
+            t1 = (hi - o_w) * iv
+            tn = np.minimum(t0, t1).max(axis=2)
+            tf = np.maximum(t0, t1).min(axis=2)
+            tb = t_best[:, cols]
+            hit = (tf >= np.maximum(tn, 0.0)) & (tn > 0.5) & (tn < tb)
+            t_best[:, cols] = np.where(hit, tn, tb)
+            lab[:, cols] = np.where(hit, np.float32(b.label), lab[:, cols])
+        t_best = t_best.reshape(-1)
+        lab = lab.reshape(-1)
         ok = np.isfinite(t_best) & (t_best < max_range) & (t_best > 2.7)
         t = t_best[ok] + rng.normal(0.0, noise, size=int(ok.sum()))
         p_w = o_w[None, :] + d_w[ok] * t[:, None]

@@ -1,0 +1,44 @@
+// examples/erasor_cpp_demo.cpp -- the reference's call sequence (OfflineMapUpdater.cpp:266-284) against the
+// ROS-free C++ class.  Reads two clouds as raw float32 [n][4] files, prints the output sizes.
+//   usage: erasor_cpp_demo map_voi.f32 query_voi.f32 [version]
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+
+#include "../include/erasor/erasor.hpp"
+
+static erasor_b200::PointCloud load(const char* path) {
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
+    if (!f) throw std::invalid_argument(std::string("cannot open ") + path);
+    const size_t bytes = static_cast<size_t>(f.tellg());
+    erasor_b200::PointCloud c(bytes / sizeof(erasor_b200::PointXYZI));
+    f.seekg(0);
+    f.read(reinterpret_cast<char*>(c.data()), c.size() * sizeof(erasor_b200::PointXYZI));
+    return c;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 3) { std::fprintf(stderr, "usage: %s map_voi.f32 query_voi.f32 [version]\n", argv[0]); return 2; }
+    try {
+        erasor_params_t p = erasor_b200::default_params();   // config/seq_05.yaml
+        p.max_range = 60.0; p.num_rings = 15; p.num_sectors = 60; p.min_h = -1.3; p.max_h = 3.2; p.th_bin_max_h = 0.05;
+        p.scan_ratio_threshold = 0.3; p.minimum_num_pts = 10; p.rejection_ratio = 0; p.gf_dist_thr = 0.15; p.gf_iter = 3;
+        p.gf_num_lpr = 10; p.gf_th_seeds_height = 0.5;
+        p.version = argc > 3 ? std::atoi(argv[3]) : 3;
+        erasor_b200::ERASOR erasor(p);
+        const auto map_voi = load(argv[1]), query_voi = load(argv[2]);
+        erasor_b200::PointCloud map_static_estimate, map_egocentric_complement, map_rejected, query_rejected;
+        erasor.set_inputs(map_voi, query_voi);
+        if (p.version == 2) erasor.compare_vois_and_revert_ground(0);
+        else                erasor.compare_vois_and_revert_ground_w_block(0);
+        erasor.get_static_estimate(map_static_estimate, map_egocentric_complement);
+        erasor.get_outliers(map_rejected, query_rejected);
+        std::cout << "ERASOR Input: " << map_voi.size() << " = " << map_static_estimate.size() << " + "
+                  << map_egocentric_complement.size() << " - " << map_rejected.size() << std::endl;
+    } catch (const std::exception& e) {
+        std::cerr << e.what() << std::endl;
+        return 1;
+    }
+    return 0;
+}

@@ -153,3 +153,21 @@ def test_negzero_fence(capi, oracle_mod):
     assert np.array_equal(bop, o.bin_of_point(0))
     assert h.fence_counts()["negzero_points"] == 3 and o.negzero_fenced() == 3   # two map points + one query point
     h.close()
+
+
+@pytest.mark.parametrize("name", ["seq_05", "seq_00", "large_scale_05"])
+def test_v3_with_in_bin_voxelization(capi, oracle_mod, small_workload, name):
+    """Version 3 as shipped: flagged bins = voxelize_preserving_labels(bin_curr + ground) (erasor.cpp:526-528)."""
+    p = P.preset(name).replace(skip_voxelize=0, version=3)
+    for fi in (1, 4):
+        m, q = _frame(small_workload, fi, p)
+        o, h = _run_both(capi, oracle_mod, p, m, q)
+        h.compare(3)
+        assert len(o.planes()) > 0, "the frame must exercise flagged bins"
+        arr, cmp_ = h.get_static_estimate()
+        oarr, _ = o.cloud(o.ARRANGED)
+        assert arr.shape == oarr.shape, f"{arr.shape} vs {oarr.shape}"
+        assert np.array_equal(arr.view(np.uint32), oarr.view(np.uint32)), f"{name}: arranged cloud differs"
+        ocmp, _ = o.cloud(o.COMPLEMENT)
+        assert np.array_equal(cmp_.view(np.uint32), ocmp.view(np.uint32))
+        h.close()
