@@ -26,7 +26,7 @@ EXPORTS = [
     "erasor_set_inputs", "erasor_compare", "erasor_get_output_sizes", "erasor_get_static_estimate", "erasor_get_outliers",
     "erasor_get_max_range", "erasor_get_bins", "erasor_get_status", "erasor_get_planes", "erasor_get_static_mask",
     "erasor_get_fence_counts", "erasor_process_frames", "erasor_get_frame_stats", "erasor_kernel_launch_count",
-    "erasor_get_kernel_time_ms", "erasor_reset_kernel_times",
+    "erasor_get_kernel_time_ms", "erasor_reset_kernel_times", "erasor_get_rgpf_profile",
 ]
 
 
@@ -72,6 +72,7 @@ def _load():
     L.erasor_kernel_launch_count.argtypes = [c_void_p]
     L.erasor_get_kernel_time_ms.argtypes = [c_void_p, c_int, POINTER(c_double), POINTER(c_uint64)]
     L.erasor_reset_kernel_times.argtypes = [c_void_p, c_int]
+    L.erasor_get_rgpf_profile.argtypes = [c_void_p, POINTER(c_uint32), POINTER(c_uint32), POINTER(c_size_t)]
     return L
 
 
@@ -254,6 +255,17 @@ class Handle:
 
     def reset_kernel_times(self, enable: bool):
         self._ck(self.L.erasor_reset_kernel_times(self.h, 1 if enable else 0))
+
+    def rgpf_profile(self):
+        n = c_size_t(0)
+        self._ck(self.L.erasor_get_rgpf_profile(self.h, None, None, ctypes.byref(n)))
+        k = n.value
+        npts = np.zeros(k, dtype=np.uint32)
+        prof = np.zeros((k, 8), dtype=np.uint32)
+        cap = c_size_t(k)
+        if k:
+            self._ck(self.L.erasor_get_rgpf_profile(self.h, npts.ctypes.data_as(POINTER(c_uint32)), prof.ctypes.data_as(POINTER(c_uint32)), ctypes.byref(cap)))
+        return npts, prof
 
     def kernel_time_ms(self, kernel_id: int):
         t, n = c_double(), c_uint64()

@@ -58,6 +58,7 @@ struct FlagRec {
     double   lpr_height;
     double   normal_d[kMaxIter][4];
     uint32_t n_ground[kMaxIter];
+    uint32_t prof[8];          // SM cycles per phase (thread 0): load+idx sort, z sort, seeds, accumulate, svd, classify+compact, outputs, sweeps
 };
 
 }  // namespace erasor

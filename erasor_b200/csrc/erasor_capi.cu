@@ -67,7 +67,8 @@ struct Timer {
 struct erasor_ctx {
     erasor_params_t p{};
     int             device = 0;
-    cudaStream_t    stream = nullptr;
+    cudaStream_t    stream = nullptr, stream_b = nullptr, stream_c = nullptr;   // b/c: concurrent R-GPF size classes
+    cudaEvent_t     ev_fork = nullptr, ev_join_b = nullptr, ev_join_c = nullptr;
     int             sm_count = 148;
     std::string     err;
     HostBinTables   tables;
@@ -143,11 +144,11 @@ void drain_timers(erasor_ctx* h) {
     }
 }
 
-uint32_t choose_chunk(const erasor_ctx* h, size_t total_points) {
-    // Chunk = one CTA of K1 / one warp of K2.  Dense per-chunk count rows cost 4*(B+1) bytes, so keep the chunk
-    // at >= 5*B points (<= 5 % extra traffic); otherwise aim at ~8 chunks per SM.
-    const size_t target = total_points / ((size_t)h->sm_count * 8) + 1;
-    size_t ch = std::max<size_t>(target, std::max<size_t>(2048, (size_t)5 * h->B));
+uint32_t choose_chunk(const erasor_ctx* h, size_t total_points, int mode) {
+    // Chunk = one CTA of K1 (and one warp of K2 in cloud mode).  Aim at ~12 chunks per SM.  In cloud mode the dense
+    // per-chunk count rows cost 4*(B+1) bytes each, so keep the chunk at >= 5*B points (<= 5 % extra traffic).
+    const size_t target = total_points / ((size_t)h->sm_count * 12) + 1;
+    size_t ch = std::max<size_t>(target, mode == 0 ? std::max<size_t>(2048, (size_t)5 * h->B) : (size_t)2048);
     ch = std::min<size_t>(ch, 65536);
     ch = (ch + 127) & ~(size_t)127;
     return (uint32_t)ch;
@@ -164,7 +165,7 @@ int prepare_batch(erasor_ctx* h, const uint64_t* map_off, const uint64_t* qry_of
     h->F = F; h->NM = NM; h->NQ = NQ;
     h->map_off.assign(map_off, map_off + F + 1);
     h->qry_off.assign(qry_off, qry_off + F + 1);
-    const uint32_t CH = choose_chunk(h, NM + NQ);
+    const uint32_t CH = choose_chunk(h, NM + NQ, mode);
 
     std::vector<ChunkDesc> chunks;
     std::vector<uint32_t>  range(2 * (size_t)(F + 1)), foff(2 * (size_t)(F + 1));
@@ -305,10 +306,17 @@ int run_compare(erasor_ctx* h, int version, int mode, uint8_t* keep_mask, uint8_
         gp.th_dist = h->p.gf_dist_thr; gp.th_seeds = h->p.gf_th_seeds_height; gp.num_lowest_pts = h->p.num_lowest_pts;
         gp.num_lpr = h->p.gf_num_lpr; gp.iters = std::min(h->p.gf_iter, kMaxIter); gp.cov_mode = h->p.cov_mode;
         h->launches += k4_num_launches();
-        CK(launch_k4(h->stream, gp, h->d_recs.as<FlagRec>(), h->d_nrecs.as<uint32_t>(), h->rec_capacity,
+        CK(cudaEventRecord(h->ev_fork, h->stream));
+        CK(cudaStreamWaitEvent(h->stream_b, h->ev_fork, 0));
+        CK(cudaStreamWaitEvent(h->stream_c, h->ev_fork, 0));
+        CK(launch_k4(h->stream, h->stream_b, h->stream_c, gp, h->d_recs.as<FlagRec>(), h->d_nrecs.as<uint32_t>(), h->rec_capacity,
                      mode == 0 ? h->d_map_sorted.as<float4>() : nullptr, h->d_map_src.as<uint32_t>(), h->cur_map,
                      h->d_frame_off.as<uint32_t>(), mode == 0 ? h->d_part.as<float4>() : nullptr, keep_mask, ground_mask,
                      h->d_frame_rej.as<uint32_t>(), h->d_scratch.as<unsigned char>(), h->sm_count, h->d_fence.as<unsigned long long>()));
+        CK(cudaEventRecord(h->ev_join_b, h->stream_b));
+        CK(cudaEventRecord(h->ev_join_c, h->stream_c));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_join_b, 0));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_join_c, 0));
     }
     return ERASOR_OK;
 }
@@ -374,6 +382,11 @@ int erasor_create(const erasor_params_t* params, int device, erasor_handle_t* ou
         return ERASOR_E_UNSUPPORTED;
     }
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&h->stream_b, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&h->stream_c, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    if ((e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&h->ev_join_b, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&h->ev_join_c, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     const size_t rb = sizeof(double) * h->tables.ring_thr.size(), sb = sizeof(SectorBoundary) * h->tables.sec_pos.size();
     if ((e = h->d_ring.ensure(rb)) != cudaSuccess || (e = h->d_pos.ensure(sb)) != cudaSuccess || (e = h->d_neg.ensure(sb)) != cudaSuccess ||
         (e = h->d_fence.ensure(sizeof(unsigned long long) * 4)) != cudaSuccess)
@@ -400,6 +413,11 @@ void erasor_destroy(erasor_handle_t h) {
                       &h->d_vox_scratch, &h->d_frame_rec_base};
     for (DevBuf* b : bufs) b->release();
     h->h_stage.release();
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join_b) cudaEventDestroy(h->ev_join_b);
+    if (h->ev_join_c) cudaEventDestroy(h->ev_join_c);
+    if (h->stream_b) cudaStreamDestroy(h->stream_b);
+    if (h->stream_c) cudaStreamDestroy(h->stream_c);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -648,6 +666,28 @@ int erasor_get_frame_stats(erasor_handle_t h, uint32_t* n_flagged_bins, uint32_t
     CK(cudaStreamSynchronize(h->stream));
     if (n_flagged_bins) CK(cudaMemcpy(n_flagged_bins, h->d_nflag.p, sizeof(uint32_t) * h->F, cudaMemcpyDeviceToHost));
     if (n_rejected_points) CK(cudaMemcpy(n_rejected_points, h->d_frame_rej.p, sizeof(uint32_t) * h->F, cudaMemcpyDeviceToHost));
+    return ERASOR_OK;
+}
+
+// instrumentation: per flagged bin of the last run, n_points and the SM cycles thread 0 spent per phase
+// (load + index sort, z sort, seeds, accumulate, SVD + plane, classify + compact, outputs) and the Jacobi sweep count
+int erasor_get_rgpf_profile(erasor_handle_t h, uint32_t* n_points, uint32_t* prof8, size_t* n) {
+    if (!h || !n) return ERASOR_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    uint32_t nr = 0;
+    CK(cudaMemcpy(&nr, h->d_nrecs.p, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    nr = std::min(nr, h->rec_capacity);
+    const size_t cap = *n;
+    *n = nr;
+    if (!n_points && !prof8) return ERASOR_OK;
+    if (cap < nr) { h->err = "profile buffer too small"; return ERASOR_E_CAPACITY; }
+    std::vector<FlagRec> recs(nr);
+    if (nr) CK(cudaMemcpy(recs.data(), h->d_recs.p, sizeof(FlagRec) * nr, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < nr; ++i) {
+        if (n_points) n_points[i] = recs[i].n_points;
+        if (prof8) for (int k = 0; k < 8; ++k) prof8[i * 8 + k] = recs[i].prof[k];
+    }
     return ERASOR_OK;
 }
 

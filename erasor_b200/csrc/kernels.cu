@@ -57,12 +57,36 @@ __device__ __forceinline__ void k1_aggregate(int key, uint32_t zenc, int lane, u
         }
         return;
     }
-    // runs of equal keys in lane order; segmented min/max towards each run's first lane with shuffles
-    // (partial-mask __reduce_*_sync compiles to a per-lane software loop on sm_100a -- measured 60 % of this
-    //  kernel's instructions -- so it is not used here)
+    // runs of equal keys in lane order.  (Partial-mask __reduce_*_sync compiles to a per-lane software loop on sm_100a
+    // -- measured at 60 % of this kernel's instructions -- so runs are reduced either one at a time with full-mask REDUX
+    // (few runs: the common case for spatially coherent clouds) or with a segmented shuffle scan.)
     const int      prev  = __shfl_up_sync(FULL_MASK, key, 1);
     const bool     head  = (lane == 0) || (key != prev);
     const unsigned heads = __ballot_sync(FULL_MASK, head);
+    const int      nruns = __popc(heads);
+    if (nruns <= 4) {
+        unsigned rest = heads;
+#pragma unroll 1
+        for (int r = 0; r < nruns; ++r) {
+            const int h = __ffs(rest) - 1;
+            rest &= rest - 1u;
+            const int e = rest ? (__ffs(rest) - 1) : 32;
+            const bool in = (lane >= h) && (lane < e);
+            const int  k  = __shfl_sync(FULL_MASK, key, h);
+            if (k >= 0 && k < B) {                                  // uniform across the warp
+                const uint32_t mn = __reduce_min_sync(FULL_MASK, in ? zenc : 0xFFFFFFFFu);
+                const uint32_t mx = __reduce_max_sync(FULL_MASK, in ? zenc : 0u);
+                if (lane == h) {
+                    atomicMin(&s_mn[k], mn);
+                    atomicMax(&s_mx[k], mx);
+                    atomicAdd(&s_cnt[k], (uint32_t)(e - h));
+                }
+            } else if (k == B && lane == h) {
+                atomicAdd(&s_cnt[B], (uint32_t)(e - h));
+            }
+        }
+        return;
+    }
     const unsigned above = heads & ~((2u << lane) - 1u);      // run heads at lanes > lane (lane 31: mask 0)
     const int      e     = above ? (__ffs(above) - 1) : 32;   // my run is [.., e)
     uint32_t mn = zenc, mx = zenc;
@@ -73,15 +97,41 @@ __device__ __forceinline__ void k1_aggregate(int key, uint32_t zenc, int lane, u
         if (lane + d < e) { mn = min(mn, omn); mx = max(mx, omx); }
     }
     if (head && key >= 0) {
-        const int h = lane;
         if (key < B) {
             atomicMin(&s_mn[key], mn);
             atomicMax(&s_mx[key], mx);
-            atomicAdd(&s_cnt[key], (uint32_t)(e - h));
+            atomicAdd(&s_cnt[key], (uint32_t)(e - lane));
         } else {
-            atomicAdd(&s_cnt[B], (uint32_t)(e - h));
+            atomicAdd(&s_cnt[B], (uint32_t)(e - lane));
         }
     }
+}
+
+// Branch-free fast path of binning.h's bin_of_point for the device: returns the bin, -1 (not binned) or -3 when the
+// point needs the exact path (ring guess off, sector coordinate inside the guard band, y == 0).  The decisions are the
+// same threshold comparisons as in binning.h; only the guesses use approximate float ops (MUFU rcp / rsqrt).
+__device__ __forceinline__ int bin_fast(float x, float y, float z, float z_lo, float z_hi, double s_max, float inv_ring, float inv_ss,
+                                        float eps_q, int R, int S, const double* __restrict__ s_ring) {
+    const double xd = (double)x, yd = (double)y;
+    const double s  = fma(yd, yd, xd * xd);
+    const bool inr  = (z < z_hi) && (z > z_lo) && (s <= s_max);
+    const float sf  = fmaxf((float)s, 1e-30f);
+    int g = (int)(sf * rsqrtf(sf) * inv_ring);
+    g = min(g, R - 1);
+    const bool ring_ok = (s_ring[g] <= s) && (s < s_ring[g + 1]);
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    float a = atan_unit(__fdividef(mn, mx));
+    if (ay > ax)  a = 1.57079637f - a;
+    if (x < 0.0f) a = 3.14159274f - a;
+    if (y < 0.0f) a = 6.28318548f - a;
+    const float q  = a * inv_ss;
+    const int   k  = (int)q;
+    const float fr = q - (float)k;
+    const bool sec_ok = (fr >= eps_q) && (fr <= 1.0f - eps_q) && (ay != 0.0f);
+    if (!inr) return -1;
+    if (!(ring_ok && sec_ok)) return -3;
+    return min(k, S - 1) * R + g;
 }
 
 template <int THREADS, int UNROLL, bool ROWS>
@@ -108,22 +158,28 @@ k1_rpod_bin(BinTablesView T, const float4* __restrict__ map_pts, const float4* _
     const float4* __restrict__ src = (cd.cloud == 0 ? map_pts : qry_pts) + cd.begin;
     uint16_t* __restrict__     dst = (cd.cloud == 0 ? bin_map : bin_qry) + cd.begin;
     BinFenceCounters fc{0u, 0u, 0u};
+    const float  z_lo = T.z_lo, z_hi = T.z_hi, inv_ring = T.inv_ring, inv_ss = T.inv_ss, eps_q = T.eps_q;
+    const double s_max = T.s_max;
+    const int    R = T.R, S = T.S;
 
     for (uint32_t base = warp * (32u * UNROLL); base < cd.len; base += NW * (32u * UNROLL)) {
         float4 p[UNROLL];
-        bool   ok[UNROLL];
+        const bool full = base + 32u * UNROLL <= cd.len;          // warp-uniform
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const uint32_t i = base + u * 32u + lane;
-            ok[u] = i < cd.len;
-            p[u]  = ok[u] ? ld_stream_f4(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            p[u] = (full || i < cd.len) ? ld_stream_f4(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const uint32_t i = base + u * 32u + lane;
+            const bool ok = full || i < cd.len;
+            int b = bin_fast(p[u].x, p[u].y, p[u].z, z_lo, z_hi, s_max, inv_ring, inv_ss, eps_q, R, S, s_ring);
+            if (__any_sync(FULL_MASK, ok && b == -3)) {
+                if (ok && b == -3) b = bin_of_point(T, s_ring, p[u].x, p[u].y, p[u].z, &fc);   // exact path (rare)
+            }
             int key = -2;
-            if (ok[u]) {
-                const int b = bin_of_point(T, s_ring, p[u].x, p[u].y, p[u].z, &fc);
+            if (ok) {
                 dst[i] = (b < 0) ? kNoBin16 : (uint16_t)b;
                 key    = (b < 0) ? B : b;
             }
@@ -520,7 +576,7 @@ struct Rot { float c, s; };
 
 // Eigen 3.3 JacobiSVD<MatrixXf>(A, ComputeFullU) on a 3x3 (two-sided Jacobi, no preconditioner); returns U.col(2).
 // Everything stays in registers: the (p,q) sweep is unrolled so that all matrix indices are compile-time.
-__device__ __forceinline__ void jacobi_svd_normal(const float (&A)[9], float (&normal)[3]) {
+__device__ __forceinline__ uint32_t jacobi_svd_normal(const float (&A)[9], float (&normal)[3]) {
     const float precision = 2.0f * FLT_EPSILON, considerAsZero = FLT_MIN;
     float W[9], U[9];
     float scale = 0.0f;
@@ -629,109 +685,243 @@ __device__ __forceinline__ void jacobi_svd_normal(const float (&A)[9], float (&n
     normal[0] = (c2 == 0) ? U[0] : (c2 == 1) ? U[1] : U[2];
     normal[1] = (c2 == 0) ? U[3] : (c2 == 1) ? U[4] : U[5];
     normal[2] = (c2 == 0) ? U[6] : (c2 == 1) ? U[7] : U[8];
+    return (uint32_t)sweeps;
 }
 
 constexpr uint32_t K4_PAD = 0xFFFFFFFFu;
 
-// "a sorts after b" for the (z, source position) order -- std::stable_sort by z of the bin's points
-__device__ __forceinline__ bool k4_after(const float* Z, uint32_t a, uint32_t b) {
-    if (a == K4_PAD) return b != K4_PAD;
-    if (b == K4_PAD) return false;
-    const float za = Z[a], zb = Z[b];
-    return (za > zb) || (za == zb && a > b);
-}
+// A "group" is the set of threads that cooperates on one flagged bin: a whole CTA (G == blockDim.x) for large
+// bins, one warp (G == 32) for small ones -- the plane fit is serial in one warp, so small bins are better served
+// by many independent warps than by CTAs whose other warps wait at a barrier.
+template <int G> __device__ __forceinline__ void group_sync() { if (G == 32) __syncwarp(); else __syncthreads(); }
+template <int G> __device__ __forceinline__ int  group_tid() { return (G == 32) ? (threadIdx.x & 31) : threadIdx.x; }
 
-// in-place bitonic sort of ORD[0..np2) with comparator `after(a, b)`; np2 a power of two; all threads of the CTA.
-template <int THREADS, class After>
-__device__ __forceinline__ void block_bitonic(uint32_t* ORD, uint32_t np2, After after) {
-    const int tid = threadIdx.x;
+// in-place bitonic sort of ORD[0..np2) (np2 a power of two) by key(ORD[.]) ascending, ties by the value itself;
+// K4_PAD sorts last.  Each thread stages up to 8 pairs per pass: all loads first, then all keys, then the swaps, so
+// the shared-memory latencies of different pairs overlap.  Stages with j <= 32 only touch 64-element blocks owned
+// by one warp, so they synchronise with __syncwarp instead of the group barrier.
+template <int G, class KeyF>
+__device__ __forceinline__ void block_bitonic(uint32_t* __restrict__ ORD, uint32_t np2, KeyF key) {
+    const int tid = group_tid<G>();
+    const uint32_t half = np2 >> 1;
     for (uint32_t k = 2; k <= np2; k <<= 1) {
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t t = tid; t < (np2 >> 1); t += THREADS) {
-                const uint32_t i = ((t & ~(j - 1u)) << 1) | (t & (j - 1u));   // j is a power of two
-                const uint32_t l = i + j;
-                const uint32_t a = ORD[i], b = ORD[l];
-                const bool asc = ((i & k) == 0);
-                const bool sw  = asc ? after(a, b) : after(b, a);
-                if (sw) { ORD[i] = b; ORD[l] = a; }
+            for (uint32_t t0 = tid; t0 < half; t0 += 8u * G) {
+                uint32_t a[8], b[8], pi[8];
+                bool ok[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t t = t0 + (uint32_t)u * G;
+                    ok[u] = t < half;
+                    pi[u] = ((t & ~(j - 1u)) << 1) | (t & (j - 1u));   // j is a power of two
+                    a[u] = ok[u] ? ORD[pi[u]] : 0u;
+                    b[u] = ok[u] ? ORD[pi[u] + j] : 0u;
+                }
+                decltype(key(0u)) ka[8], kb[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { ka[u] = key(ok[u] ? a[u] : K4_PAD); kb[u] = key(ok[u] ? b[u] : K4_PAD); }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (ok[u]) {
+                        const bool a_after_b = (ka[u] > kb[u]) || (ka[u] == kb[u] && a[u] > b[u]);
+                        const bool b_after_a = (kb[u] > ka[u]) || (kb[u] == ka[u] && b[u] > a[u]);
+                        const bool sw = ((pi[u] & k) == 0) ? a_after_b : b_after_a;
+                        if (sw) { ORD[pi[u]] = b[u]; ORD[pi[u] + j] = a[u]; }
+                    }
+                }
             }
-            __syncthreads();
+            if (G == 32 || j <= 32) __syncwarp(); else __syncthreads();
         }
+        if (G != 32 && k >= 64) __syncthreads();   // next k starts with j = k: partners leave the warp's 64-element block
     }
+    if (G != 32) __syncthreads();
 }
 
-// ordered compaction of indices i in [0,n) with pred(i) into out[]; returns count (all threads).
-template <int THREADS, class Pred>
-__device__ __forceinline__ uint32_t k4_compact(uint32_t n, uint32_t* out, uint32_t* s_warp /*[THREADS/32 + 1]*/, Pred pred) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = THREADS / 32;
+// ordered compaction of indices i in [0,n) with pred(i) into out[]; returns count (all threads of the group).
+template <int G, class Pred>
+__device__ __forceinline__ uint32_t k4_compact(uint32_t n, uint32_t* out, uint32_t* s_warp /*[G/32 + 1], unused for G == 32*/, Pred pred) {
+    const int tid = group_tid<G>(), lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = G / 32;
     uint32_t total = 0;
-    for (uint32_t base = 0; base < n; base += THREADS) {
+    for (uint32_t base = 0; base < n; base += G) {
         const uint32_t i = base + tid;
         const bool g = (i < n) && pred(i);
         const unsigned bal = __ballot_sync(FULL_MASK, g);
-        if (lane == 0) s_warp[warp] = __popc(bal);
-        __syncthreads();
-        uint32_t off = total, round = 0;
+        if (G == 32) {
+            if (g) out[total + __popc(bal & ((1u << lane) - 1u))] = i;
+            total += __popc(bal);
+            __syncwarp();
+        } else {
+            if (lane == 0) s_warp[warp] = __popc(bal);
+            __syncthreads();
+            uint32_t off = total, round = 0;
 #pragma unroll
-        for (int w = 0; w < NW; ++w) { const uint32_t c = s_warp[w]; off += (w < warp) ? c : 0u; round += c; }
-        if (g) out[off + __popc(bal & ((1u << lane) - 1u))] = i;
-        total += round;
-        __syncthreads();
+            for (int w = 0; w < NW; ++w) { const uint32_t c = s_warp[w]; off += (w < warp) ? c : 0u; round += c; }
+            if (g) out[off + __popc(bal & ((1u << lane) - 1u))] = i;
+            total += round;
+            __syncthreads();
+        }
     }
     return total;
 }
 
+// exclusive scan of 8*G counters by the group (8 per thread); s_part: G/32 + 2 words of scratch
+template <int G>
+__device__ __forceinline__ void group_excl_scan8(uint32_t* CNT, uint32_t* s_part) {
+    const int tid = group_tid<G>(), lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = G / 32;
+    uint32_t v[8], sum = 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { v[u] = CNT[tid * 8 + u]; sum += v[u]; }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL_MASK, incl, o);
+        if (lane >= o) incl += t;
+    }
+    uint32_t excl = incl - sum;
+    if (G != 32) {
+        if (lane == 31) s_part[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = lane < NW ? s_part[lane] : 0u;
+            uint32_t wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL_MASK, wi, o);
+                if (lane >= o) wi += t;
+            }
+            if (lane < NW) s_part[lane] = wi - w;
+        }
+        __syncthreads();
+        excl += s_part[warp];
+    }
+    uint32_t run = excl;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { CNT[tid * 8 + u] = run; run += v[u]; }
+    group_sync<G>();
+}
+
+// Stable LSD radix sort (8-bit digits) of the n values in A by key(value); Bf is an n-word ping-pong buffer,
+// CNT 8*G counters laid out [digit][warp].  Each warp owns a contiguous segment of the input: it histograms the
+// segment (match_any dedups equal digits inside a 32-element step, so no atomics), and after the group-wide scan
+// re-walks the segment in order handing out destinations -- which is what makes the sort stable.  Returns the
+// buffer (A or Bf) that holds the result.  ~35 warp instructions per 32 elements per pass: about 8x fewer than
+// the shared-memory bitonic network this replaced (profiles/README.md, R-GPF section).
+template <int G, class KeyF>
+__device__ __forceinline__ uint32_t* group_radix_sort(uint32_t* A, uint32_t* Bf, uint32_t n, uint32_t* CNT, uint32_t* s_part,
+                                                      int key_bits, KeyF key) {
+    constexpr int NW = G / 32;
+    const int tid = group_tid<G>(), lane = tid & 31, warp = tid >> 5;
+    const uint32_t seg = (((n + NW - 1) / NW) + 31u) & ~31u;
+    const uint32_t s0 = min(n, (uint32_t)warp * seg), s1 = min(n, s0 + seg);
+    uint32_t* src = A;
+    uint32_t* dst = Bf;
+    for (int shift = 0; shift < key_bits; shift += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) CNT[tid + u * G] = 0u;
+        group_sync<G>();
+        for (uint32_t e0 = s0; e0 < s1; e0 += 32) {
+            const uint32_t e = e0 + lane;
+            const bool valid = e < s1;
+            const unsigned vmask = __ballot_sync(FULL_MASK, valid);
+            if (valid) {
+                const uint32_t d = (key(src[e]) >> shift) & 255u;
+                const unsigned peers = __match_any_sync(vmask, d);
+                if (lane == __ffs(peers) - 1) CNT[d * NW + warp] += __popc(peers);
+            }
+            __syncwarp();
+        }
+        group_sync<G>();
+        group_excl_scan8<G>(CNT, s_part);
+        for (uint32_t e0 = s0; e0 < s1; e0 += 32) {
+            const uint32_t e = e0 + lane;
+            const bool valid = e < s1;
+            const unsigned vmask = __ballot_sync(FULL_MASK, valid);
+            if (valid) {
+                const uint32_t id = src[e];
+                const uint32_t d  = (key(id) >> shift) & 255u;
+                const unsigned peers = __match_any_sync(vmask, d);
+                const uint32_t base  = CNT[d * NW + warp];
+                __syncwarp(vmask);
+                if (lane == __ffs(peers) - 1) CNT[d * NW + warp] = base + __popc(peers);
+                dst[base + __popc(peers & ((1u << lane) - 1u))] = id;
+            }
+            __syncwarp();
+        }
+        group_sync<G>();
+        uint32_t* t = src; src = dst; dst = t;
+    }
+    return src;
+}
+
 struct K4Shared {
     float    normal[3];
+    uint32_t pad_;
     double   thd;
     double   seed_thr;
-    uint32_t warp[33];
+    uint32_t warp[34];
 };
 
-// One flagged bin.  X/Y/Z/ORD/FLG live in shared memory (kShared) or in the bin's slice of the global scratch.
-template <int THREADS, bool kShared>
-__device__ __forceinline__ void k4_process_bin(const GpfParams& P, FlagRec& rc, unsigned char* base, K4Shared& sh,
+// One flagged bin, handled by one group.  X/Y/Z/ORD/FLG live in shared memory or in the bin's slice of the global scratch.
+template <int G, bool kShared>
+__device__ __forceinline__ void k4_process_bin(const GpfParams& P, FlagRec& rc, unsigned char* base, float* prd, uint32_t* cnt_scratch, K4Shared& sh,
                                                const float4* __restrict__ sorted_pts, uint32_t* __restrict__ sorted_src,
                                                const float4* __restrict__ in_pts, const uint32_t* __restrict__ frame_off,
                                                float4* __restrict__ part_pts, uint8_t* __restrict__ keep_mask,
                                                uint8_t* __restrict__ ground_mask, uint32_t* __restrict__ frame_rejected,
                                                unsigned long long* __restrict__ fence) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = group_tid<G>(), lane = tid & 31, warp = tid >> 5;
     const uint32_t n = rc.n_points, src_begin = rc.src_begin;
     const uint32_t fbase = frame_off[rc.frame];
-    uint32_t np2 = 1; while (np2 < n) np2 <<= 1;
     float*    X   = reinterpret_cast<float*>(base);
     float*    Y   = X + n;
     float*    Z   = Y + n;
     uint32_t* ORD = reinterpret_cast<uint32_t*>(Z + n);
-    uint8_t*  FLG = reinterpret_cast<uint8_t*>(ORD + np2);
+    uint32_t* TMP = ORD + n;
+    uint8_t*  FLG = reinterpret_cast<uint8_t*>(TMP + n);
+    constexpr int TILE = (G == 32) ? 64 : 256;
+    float*    PRD = prd;                          // 9 x (TILE + 1) floats, always shared memory
+    long long t_prev = clock64();
+    uint32_t prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define K4_TICK(slot) do { const long long t_now__ = clock64(); prof[slot] += (uint32_t)(t_now__ - t_prev); t_prev = t_now__; } while (0)
 
     if (sorted_pts) {
         // cloud mode: K2 already placed the bin's points contiguously in source order
-        for (uint32_t i = tid; i < n; i += THREADS) {
+        for (uint32_t i = tid; i < n; i += G) {
             const float4 p = sorted_pts[src_begin + i];
             X[i] = p.x; Y[i] = p.y; Z[i] = p.z; ORD[i] = i;
         }
     } else {
         // mask mode: K2g appended the bin's source indices in arbitrary order; restore source order first
-        for (uint32_t i = tid; i < np2; i += THREADS) ORD[i] = (i < n) ? sorted_src[src_begin + i] : K4_PAD;
-        __syncthreads();
-        block_bitonic<THREADS>(ORD, np2, [](uint32_t a, uint32_t b) { return a > b; });
-        for (uint32_t i = tid; i < n; i += THREADS) {
-            const uint32_t s = ORD[i];
+        for (uint32_t i = tid; i < n; i += G) ORD[i] = sorted_src[src_begin + i];
+        group_sync<G>();
+        const uint32_t flen = frame_off[rc.frame + 1] - fbase;
+        const int idx_bits = 32 - __clz(max(flen, 2u) - 1u);
+        const uint32_t* srt = group_radix_sort<G>(ORD, TMP, n, cnt_scratch, sh.warp, idx_bits, [](uint32_t v) { return v; });
+        for (uint32_t i = tid; i < n; i += G) {
+            const uint32_t s = srt[i];
             sorted_src[src_begin + i] = s;
             const float4 p = in_pts[fbase + s];
             X[i] = p.x; Y[i] = p.y; Z[i] = p.z;
         }
-        __syncthreads();
-        for (uint32_t i = tid; i < n; i += THREADS) ORD[i] = i;
+        group_sync<G>();
+        for (uint32_t i = tid; i < n; i += G) ORD[i] = i;
     }
-    for (uint32_t i = n + tid; i < np2; i += THREADS) ORD[i] = K4_PAD;
-    __syncthreads();
+    group_sync<G>();
+    K4_TICK(0);
 
-    // std::sort by z (erasor.cpp:240), ties in source order
-    block_bitonic<THREADS>(ORD, np2, [&](uint32_t a, uint32_t b) { return k4_after(Z, a, b); });
+    // std::sort by z (erasor.cpp:240), ties in source order: stable radix sort on the order-preserving encoding of z
+    // (-0.0 is folded onto +0.0 first: the comparator a.z < b.z treats them as equal)
+    {
+        uint32_t* zs = group_radix_sort<G>(ORD, TMP, n, cnt_scratch, sh.warp, 32, [&](uint32_t id) {
+            uint32_t u = __float_as_uint(Z[id]);
+            if (u == 0x80000000u) u = 0u;
+            return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+        });
+        if (zs != ORD) { TMP = ORD; ORD = zs; }
+    }
+    K4_TICK(1);
 
     // extract_initial_seeds_ (erasor.cpp:204-231)
     if (tid == 0) {
@@ -744,58 +934,71 @@ __device__ __forceinline__ void k4_process_bin(const GpfParams& P, FlagRec& rc, 
         rc.lpr_height = lpr;
         sh.seed_thr   = lpr + P.th_seeds;
     }
-    __syncthreads();
+    group_sync<G>();
     const double seed_thr = sh.seed_thr;
     uint32_t m;   // seeds = sorted prefix with z < lpr + th_seeds
     {
         uint32_t c = 0;
-        for (uint32_t i = tid; i < n; i += THREADS) c += ((double)Z[ORD[i]] < seed_thr) ? 1u : 0u;
+        for (uint32_t i = tid; i < n; i += G) c += ((double)Z[ORD[i]] < seed_thr) ? 1u : 0u;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL_MASK, c, o);
-        if (lane == 0) sh.warp[warp] = c;
-        __syncthreads();
-        m = 0;
+        if (G == 32) {
+            m = c;
+        } else {
+            if (lane == 0) sh.warp[warp] = c;
+            __syncthreads();
+            m = 0;
 #pragma unroll
-        for (int ww = 0; ww < THREADS / 32; ++ww) m += sh.warp[ww];
-        __syncthreads();
+            for (int ww = 0; ww < G / 32; ++ww) m += sh.warp[ww];
+            __syncthreads();
+        }
     }
     if (tid == 0) rc.n_seeds = m;
+    K4_TICK(2);
 
     uint32_t n_empty = 0;
     for (int it = 0; it < P.iters; ++it) {
         // ---- estimate_plane_ over ORD[0..m) (erasor.cpp:183-198) ----
-        if (warp == 0) {
-            // pcl::computeMeanAndCovarianceMatrix: nine float accumulators walked in list order; lane L owns accu[L].
-            // The FADD chain (4 cycles per element) is the only true dependency; loads and products run one group ahead.
-            const float* pa = (lane == 0 || lane == 1 || lane == 2 || lane == 6) ? X : (lane == 3 || lane == 4 || lane == 7) ? Y : Z;
-            const float* pb = (lane == 0) ? X : (lane == 1 || lane == 3) ? Y : Z;
-            const bool   unit_b = lane >= 6;
-            float Ka = 0.0f, Kb = 0.0f, K0 = 0.0f, K1 = 0.0f, K2 = 0.0f;
-            if (P.cov_mode == 1 && m > 0) {
-                const uint32_t f0 = ORD[0];
-                K0 = X[f0]; K1 = Y[f0]; K2 = Z[f0];
-                Ka = pa[f0]; Kb = unit_b ? 0.0f : pb[f0];
+        // pcl::computeMeanAndCovarianceMatrix: nine float accumulators walked in list order.  The nine products of a
+        // tile of list elements are computed by the whole group into shared memory (row stride TILE+1: conflict-free
+        // for the nine summing lanes), then lane L of warp 0 adds row L in order: the serial FADD chain is fed by
+        // independent, prefetchable shared-memory loads (4-5 cycles per element instead of a dependent gather).
+        float K0 = 0.0f, K1 = 0.0f, K2 = 0.0f;
+        if (P.cov_mode == 1 && m > 0) { const uint32_t f0 = ORD[0]; K0 = X[f0]; K1 = Y[f0]; K2 = Z[f0]; }
+        float acc = 0.0f;
+        for (uint32_t base_i = 0; base_i < m; base_i += TILE) {
+            const uint32_t cntk = min((uint32_t)TILE, m - base_i);
+            for (uint32_t k = tid; k < cntk; k += G) {
+                const uint32_t idx = ORD[base_i + k];
+                const float x = FS(X[idx], K0), y = FS(Y[idx], K1), z = FS(Z[idx], K2);
+                PRD[0 * (TILE + 1) + k] = FM(x, x);
+                PRD[1 * (TILE + 1) + k] = FM(x, y);
+                PRD[2 * (TILE + 1) + k] = FM(x, z);
+                PRD[3 * (TILE + 1) + k] = FM(y, y);
+                PRD[4 * (TILE + 1) + k] = FM(y, z);
+                PRD[5 * (TILE + 1) + k] = FM(z, z);
+                PRD[6 * (TILE + 1) + k] = x;
+                PRD[7 * (TILE + 1) + k] = y;
+                PRD[8 * (TILE + 1) + k] = z;
             }
-            float acc = 0.0f;
-            if (lane < 9) {
-                auto prod = [&](uint32_t idx) -> float {
-                    const float a = FS(pa[idx], Ka);
-                    const float b = unit_b ? 1.0f : FS(pb[idx], Kb);
-                    return FM(a, b);
-                };
-                uint32_t i = 0;
-                if (m >= 8) {
-                    float q0 = prod(ORD[0]), q1 = prod(ORD[1]), q2 = prod(ORD[2]), q3 = prod(ORD[3]);
-                    for (i = 4; i + 4 <= m; i += 4) {
-                        const float r0 = prod(ORD[i]), r1 = prod(ORD[i + 1]), r2 = prod(ORD[i + 2]), r3 = prod(ORD[i + 3]);
-                        acc = FA(acc, q0); acc = FA(acc, q1); acc = FA(acc, q2); acc = FA(acc, q3);
-                        q0 = r0; q1 = r1; q2 = r2; q3 = r3;
-                    }
-                    acc = FA(acc, q0); acc = FA(acc, q1); acc = FA(acc, q2); acc = FA(acc, q3);
+            group_sync<G>();
+            if (warp == 0 && lane < 9) {
+                const float* row = PRD + lane * (TILE + 1);
+                uint32_t k = 0;
+                for (; k + 16 <= cntk; k += 16) {
+                    float q[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) q[u] = row[k + u];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) acc = FA(acc, q[u]);
                 }
-                for (; i < m; ++i) acc = FA(acc, prod(ORD[i]));
-                if (m != 0) acc = FD(acc, (float)m);
+                for (; k < cntk; ++k) acc = FA(acc, row[k]);
             }
+            group_sync<G>();
+        }
+        if (warp == 0) {
+            if (lane < 9 && m != 0) acc = FD(acc, (float)m);
+            K4_TICK(3);
             float a[9];
 #pragma unroll
             for (int k = 0; k < 9; ++k) a[k] = __shfl_sync(FULL_MASK, acc, k);
@@ -814,7 +1017,7 @@ __device__ __forceinline__ void k4_process_bin(const GpfParams& P, FlagRec& rc, 
                     cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
                 }
                 float nrm[3];
-                jacobi_svd_normal(cov, nrm);
+                prof[7] += jacobi_svd_normal(cov, nrm);
                 const float dot = FA(FA(FM(nrm[0], mean[0]), FM(nrm[1], mean[1])), FM(nrm[2], mean[2]));
                 const double d  = (double)(-dot);
                 sh.normal[0] = nrm[0]; sh.normal[1] = nrm[1]; sh.normal[2] = nrm[2];
@@ -825,24 +1028,26 @@ __device__ __forceinline__ void k4_process_bin(const GpfParams& P, FlagRec& rc, 
             }
         }
         if (m == 0) ++n_empty;
-        __syncthreads();
+        group_sync<G>();
+        K4_TICK(4);
         const float n0 = sh.normal[0], n1 = sh.normal[1], n2 = sh.normal[2];
         const double thd = sh.thd;
         // ---- classify every point of the bin in source order (erasor.cpp:265-281) ----
-        for (uint32_t i = tid; i < n; i += THREADS) {
+        for (uint32_t i = tid; i < n; i += G) {
             const float r = FA(FA(FM(X[i], n0), FM(Y[i], n1)), FM(Z[i], n2));
             FLG[i] = ((double)r < thd) ? 1 : 0;
         }
-        __syncthreads();
-        m = k4_compact<THREADS>(n, ORD, sh.warp, [&](uint32_t i) { return FLG[i] != 0; });
+        group_sync<G>();
+        m = k4_compact<G>(n, ORD, sh.warp, [&](uint32_t i) { return FLG[i] != 0; });
         if (tid == 0 && it < kMaxIter) rc.n_ground[it] = m;
+        K4_TICK(5);
     }
     // gf_iter == 0: the reference returns the seeds as ground and fills no outliers (erasor.cpp:260-285)
     if (P.iters <= 0) {
-        for (uint32_t i = tid; i < n; i += THREADS) FLG[i] = 0;
-        __syncthreads();
-        for (uint32_t i = tid; i < m; i += THREADS) FLG[ORD[i]] = 1;
-        __syncthreads();
+        for (uint32_t i = tid; i < n; i += G) FLG[i] = 0;
+        group_sync<G>();
+        for (uint32_t i = tid; i < m; i += G) FLG[ORD[i]] = 1;
+        group_sync<G>();
     }
     if (tid == 0) {
         rc.n_ground_final = m; rc.n_empty_fits = n_empty;
@@ -852,7 +1057,7 @@ __device__ __forceinline__ void k4_process_bin(const GpfParams& P, FlagRec& rc, 
 
     // ---- outputs ----
     if (keep_mask || ground_mask) {
-        for (uint32_t i = tid; i < n; i += THREADS) {
+        for (uint32_t i = tid; i < n; i += G) {
             const uint32_t s = sorted_src[src_begin + i];
             if (keep_mask && !FLG[i] && P.iters > 0) keep_mask[fbase + s] = 0;
             if (ground_mask && FLG[i]) ground_mask[fbase + s] = 1;
@@ -860,73 +1065,92 @@ __device__ __forceinline__ void k4_process_bin(const GpfParams& P, FlagRec& rc, 
     }
     if (part_pts) {
         // partitioned copy of the bin: [ground, source order][non-ground, source order]
-        for (uint32_t i = tid; i < m; i += THREADS) part_pts[src_begin + i] = sorted_pts[src_begin + ORD[i]];
-        __syncthreads();
-        const uint32_t m2 = k4_compact<THREADS>(n, ORD, sh.warp, [&](uint32_t i) { return FLG[i] == 0; });
-        for (uint32_t i = tid; i < m2; i += THREADS) part_pts[src_begin + m + i] = sorted_pts[src_begin + ORD[i]];
+        for (uint32_t i = tid; i < m; i += G) part_pts[src_begin + i] = sorted_pts[src_begin + ORD[i]];
+        group_sync<G>();
+        const uint32_t m2 = k4_compact<G>(n, ORD, sh.warp, [&](uint32_t i) { return FLG[i] == 0; });
+        for (uint32_t i = tid; i < m2; i += G) part_pts[src_begin + m + i] = sorted_pts[src_begin + ORD[i]];
     }
-    __syncthreads();
+    group_sync<G>();
+    K4_TICK(6);
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) rc.prof[k] = prof[k];
+    }
+#undef K4_TICK
 }
 
-// Records are served to size classes: this launch handles bins with lo < n_points <= hi; bins above smem_cap_points
-// (only in the last class) work in their slice of the global scratch.
-template <int THREADS>
+// Records are served to size classes: a launch handles bins with n_lo < n_points <= n_hi.
+// G == 32: every warp of the CTA is a group with its own shared-memory slice (slice_bytes); bins are dealt to warps.
+// G == THREADS: the CTA is the group; bins above smem_cap_points work in their slice of the global scratch.
+template <int THREADS, int G>
 __global__ void __launch_bounds__(THREADS)
 k4_rgpf(GpfParams P, FlagRec* __restrict__ recs, const uint32_t* __restrict__ n_recs, uint32_t rec_capacity,
         uint32_t n_lo, uint32_t n_hi, const float4* __restrict__ sorted_pts, uint32_t* __restrict__ sorted_src,
         const float4* __restrict__ in_pts, const uint32_t* __restrict__ frame_off /*map cloud [F+1]*/,
         float4* __restrict__ part_pts /*nullable*/, uint8_t* __restrict__ keep_mask /*nullable*/,
         uint8_t* __restrict__ ground_mask /*nullable*/, uint32_t* __restrict__ frame_rejected /*[F] nullable*/,
-        unsigned char* __restrict__ gscratch, uint32_t smem_cap_points, unsigned long long* __restrict__ fence) {
+        unsigned char* __restrict__ gscratch, uint32_t smem_cap_points, uint32_t slice_bytes,
+        unsigned long long* __restrict__ fence) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ K4Shared sh;
+    constexpr int NG = THREADS / G;
+    constexpr int TILE = (G == 32) ? 64 : 256;
+    __shared__ K4Shared sh[NG];
+    __shared__ float    s_prd[NG][9 * (TILE + 1)];
+    __shared__ uint32_t s_cnt[NG][8 * G];
     const uint32_t nrec = min(*n_recs, rec_capacity);
-    for (uint32_t w = blockIdx.x; w < nrec; w += gridDim.x) {
+    const int grp = (G == 32) ? (threadIdx.x >> 5) : 0;
+    const uint32_t first = blockIdx.x * NG + grp, stride = gridDim.x * NG;
+    for (uint32_t w = first; w < nrec; w += stride) {
         FlagRec& rc = recs[w];
         const uint32_t n = rc.n_points;
         if (n <= n_lo || n > n_hi) continue;
         if (n <= smem_cap_points)
-            k4_process_bin<THREADS, true>(P, rc, smem_raw, sh, sorted_pts, sorted_src, in_pts, frame_off, part_pts, keep_mask,
-                                          ground_mask, frame_rejected, fence);
+            k4_process_bin<G, true>(P, rc, smem_raw + (size_t)grp * slice_bytes, s_prd[grp], s_cnt[grp], sh[grp], sorted_pts, sorted_src, in_pts,
+                                    frame_off, part_pts, keep_mask, ground_mask, frame_rejected, fence);
         else
-            k4_process_bin<THREADS, false>(P, rc, gscratch + (size_t)rc.src_begin * 24u, sh, sorted_pts, sorted_src, in_pts, frame_off,
-                                           part_pts, keep_mask, ground_mask, frame_rejected, fence);
+            k4_process_bin<G, false>(P, rc, gscratch + (size_t)rc.src_begin * 24u, s_prd[grp], s_cnt[grp], sh[grp], sorted_pts, sorted_src, in_pts,
+                                     frame_off, part_pts, keep_mask, ground_mask, frame_rejected, fence);
     }
 }
 
-template <int THREADS>
+template <int THREADS, int G>
 static cudaError_t launch_k4_class(cudaStream_t st, const GpfParams& P, FlagRec* recs, const uint32_t* n_recs, uint32_t rec_capacity,
                                    uint32_t n_lo, uint32_t n_hi, uint32_t smem_bytes, const float4* sorted_pts, uint32_t* sorted_src,
                                    const float4* in_pts, const uint32_t* frame_off, float4* part_pts, uint8_t* keep_mask,
                                    uint8_t* ground_mask, uint32_t* frame_rejected, unsigned char* gscratch, int grid,
                                    unsigned long long* fence) {
-    // 12 n (xyz) + 4 np2 (<= 8n, order) + n (flags) <= 21 n + 16
-    const uint32_t cap = (smem_bytes - 64) / 21u;
-    auto kern = k4_rgpf<THREADS>;
+    // per bin: 12 n (xyz) + 4 n (order) + 4 n (ping-pong) + n (flags) = 21 n
+    constexpr int NG = THREADS / G;
+    const uint32_t slice = (smem_bytes / NG) & ~15u;
+    const uint32_t cap = (slice - 32) / 21u;
+    auto kern = k4_rgpf<THREADS, G>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
     kern<<<grid, THREADS, smem_bytes, st>>>(P, recs, n_recs, rec_capacity, n_lo, n_hi, sorted_pts, sorted_src, in_pts, frame_off,
-                                            part_pts, keep_mask, ground_mask, frame_rejected, gscratch, cap, fence);
+                                            part_pts, keep_mask, ground_mask, frame_rejected, gscratch, cap, slice, fence);
     return cudaGetLastError();
 }
 
 int k4_num_launches() { return 3; }
 
-cudaError_t launch_k4(cudaStream_t st, const GpfParams& P, FlagRec* recs, const uint32_t* n_recs, uint32_t rec_capacity,
-                      const float4* sorted_pts, uint32_t* sorted_src, const float4* in_pts, const uint32_t* frame_off, float4* part_pts,
-                      uint8_t* keep_mask, uint8_t* ground_mask, uint32_t* frame_rejected, unsigned char* gscratch,
+cudaError_t launch_k4(cudaStream_t st, cudaStream_t st_b, cudaStream_t st_c, const GpfParams& P, FlagRec* recs, const uint32_t* n_recs,
+                      uint32_t rec_capacity, const float4* sorted_pts, uint32_t* sorted_src, const float4* in_pts, const uint32_t* frame_off,
+                      float4* part_pts, uint8_t* keep_mask, uint8_t* ground_mask, uint32_t* frame_rejected, unsigned char* gscratch,
                       int sm_count, unsigned long long* fence) {
-    // size classes: small bins get small CTAs (the plane fit is serial in one warp, so many small CTAs per SM
-    // keep the SM busy), large bins get the whole shared memory of an SM, anything beyond works in global scratch.
+    // The three size classes touch disjoint bins, so they run concurrently on three streams (the caller forks / joins).
     cudaError_t e;
-    e = launch_k4_class<64>(st, P, recs, n_recs, rec_capacity, 0u, 512u, 12 * 1024, sorted_pts, sorted_src, in_pts, frame_off, part_pts,
-                            keep_mask, ground_mask, frame_rejected, gscratch, sm_count * 16, fence);
+    // class A: n <= 512, one warp per bin, 8 warps per CTA with 9 KB slices (512 pts: 12*512 + 8*512 + 512 = 10.5 KB -> cap 438;
+    //          bins between the slice cap and 512 points use the global scratch)
+    e = launch_k4_class<256, 32>(st, P, recs, n_recs, rec_capacity, 0u, 512u, 8 * 11 * 1024, sorted_pts, sorted_src, in_pts, frame_off,
+                                 part_pts, keep_mask, ground_mask, frame_rejected, gscratch, sm_count * 2, fence);
     if (e != cudaSuccess) return e;
-    e = launch_k4_class<256>(st, P, recs, n_recs, rec_capacity, 512u, 2560u, 54 * 1024, sorted_pts, sorted_src, in_pts, frame_off, part_pts,
-                             keep_mask, ground_mask, frame_rejected, gscratch, sm_count * 4, fence);
+    // class B: 512 < n <= 2560, one 256-thread CTA per bin
+    e = launch_k4_class<256, 256>(st_b, P, recs, n_recs, rec_capacity, 512u, 2560u, 54 * 1024, sorted_pts, sorted_src, in_pts, frame_off,
+                                  part_pts, keep_mask, ground_mask, frame_rejected, gscratch, sm_count * 3, fence);
     if (e != cudaSuccess) return e;
-    return launch_k4_class<1024>(st, P, recs, n_recs, rec_capacity, 2560u, 0xFFFFFFFFu, 200 * 1024, sorted_pts, sorted_src, in_pts, frame_off,
-                                 part_pts, keep_mask, ground_mask, frame_rejected, gscratch, sm_count, fence);
+    // class C: anything larger, one 1024-thread CTA with most of an SM's shared memory; beyond ~8.7 k points global scratch
+    return launch_k4_class<1024, 1024>(st_c, P, recs, n_recs, rec_capacity, 2560u, 0xFFFFFFFFu, 180 * 1024, sorted_pts, sorted_src, in_pts,
+                                       frame_off, part_pts, keep_mask, ground_mask, frame_rejected, gscratch, sm_count, fence);
 }
 
 // ============================================================================================
@@ -938,13 +1162,6 @@ cudaError_t launch_k4(cudaStream_t st, const GpfParams& P, FlagRec* recs, const 
 //      order; 1-NN ties go to the lowest input index.
 // ============================================================================================
 constexpr int K4B_THREADS = 256;
-
-__device__ __forceinline__ bool k4b_after(const uint32_t* KEY, uint32_t a, uint32_t b) {
-    if (a == K4_PAD) return b != K4_PAD;
-    if (b == K4_PAD) return false;
-    const uint32_t ka = KEY[a], kb = KEY[b];
-    return (ka > kb) || (ka == kb && a > b);
-}
 
 __global__ void __launch_bounds__(K4B_THREADS)
 k4b_voxelize(float leaf_f, int B, const FlagRec* __restrict__ recs, const uint32_t* __restrict__ n_recs, uint32_t rec_capacity,
@@ -1035,7 +1252,7 @@ k4b_voxelize(float leaf_f, int B, const FlagRec* __restrict__ recs, const uint32
                 KEY[i] = (uint32_t)(ijk0 + ijk1 * mul1 + ijk2 * mul2);
             }
             __syncthreads();
-            block_bitonic<K4B_THREADS>(ORD, np2, [&](uint32_t a, uint32_t c) { return k4b_after(KEY, a, c); });
+            block_bitonic<K4B_THREADS>(ORD, np2, [&](uint32_t a) { return (a == K4_PAD) ? 0xFFFFFFFFu : KEY[a]; });
             // voxel heads in sorted order
             nv = k4_compact<K4B_THREADS>(n, VST, s_warp, [&](uint32_t i) { return i == 0 || KEY[ORD[i]] != KEY[ORD[i - 1]]; });
             if (tid == 0) VST[nv] = n;

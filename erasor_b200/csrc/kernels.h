@@ -42,9 +42,9 @@ cudaError_t launch_k2(cudaStream_t st, const ChunkDesc* chunks, uint32_t chunk_b
 int k4_num_launches();
 // sorted_pts != nullptr: cloud mode (bins contiguous in source order, from K2).  sorted_pts == nullptr: mask mode
 // (sorted_src holds K2g's unordered source indices; points are gathered from in_pts).
-cudaError_t launch_k4(cudaStream_t st, const GpfParams& P, FlagRec* recs, const uint32_t* n_recs, uint32_t rec_capacity,
-                      const float4* sorted_pts, uint32_t* sorted_src, const float4* in_pts, const uint32_t* frame_off, float4* part_pts,
-                      uint8_t* keep_mask, uint8_t* ground_mask, uint32_t* frame_rejected, unsigned char* gscratch,
+cudaError_t launch_k4(cudaStream_t st, cudaStream_t st_b, cudaStream_t st_c, const GpfParams& P, FlagRec* recs, const uint32_t* n_recs,
+                      uint32_t rec_capacity, const float4* sorted_pts, uint32_t* sorted_src, const float4* in_pts, const uint32_t* frame_off,
+                      float4* part_pts, uint8_t* keep_mask, uint8_t* ground_mask, uint32_t* frame_rejected, unsigned char* gscratch,
                       int sm_count, unsigned long long* fence);
 
 cudaError_t launch_k4b(cudaStream_t st, float leaf, int B, const FlagRec* recs, const uint32_t* n_recs, uint32_t rec_capacity,

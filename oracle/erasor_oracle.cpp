@@ -259,6 +259,7 @@ inline void real_2x2_jacobi_svd(const float* W, int p, int q, Rot* j_left, Rot* 
 }
 }  // namespace
 
+int g_last_sweeps = 0;
 void jacobi_svd_3x3_full_u(const float A[9], float U[9], float sv[3]) {
     const float precision      = 2.0f * FLT_EPSILON;
     const float considerAsZero = FLT_MIN;
@@ -291,6 +292,7 @@ void jacobi_svd_3x3_full_u(const float A[9], float U[9], float sv[3]) {
             }
         }
     }
+    g_last_sweeps = sweeps;
     for (int i = 0; i < 3; ++i) {
         const float a = W[i * 4];
         sv[i] = std::fabs(a);
