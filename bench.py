@@ -144,14 +144,17 @@ def run_reference(args):
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     ctx = mp.get_context("fork")
     with ctx.Pool(cores, initializer=_ref_init, initargs=(dataclasses.asdict(p), maps, qs)) as pool:
-        idx = list(range(len(maps)))
+        # a step = enough frames to give every host core one (the 20-frame pass repeated): the reference is
+        # single-threaded, so "all the host threads it can use" means independent frames in parallel processes
+        reps = max(1, -(-cores // len(maps)))
+        idx = list(range(len(maps))) * reps
         for _ in range(args.warmup):
             pool.map(_ref_frame, idx, chunksize=1)
         t0 = time.perf_counter()
         for _ in range(args.steps):
             pool.map(_ref_frame, idx, chunksize=1)
         dt = time.perf_counter() - t0
-    sps = len(maps) * args.steps / dt
+    sps = len(idx) * args.steps / dt
     line = {
         "impl": "reference", "metric": "LiDAR scans/sec through R-POD+SRT+R-GPF on KITTI-05 (synthetic twin)",
         "value": sps, "unit": "scans/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -159,7 +162,7 @@ def run_reference(args):
         "dtype": "f32 points, f64 index/SRT arithmetic", "data": "synthetic",
         "config": workload_config(p, maps, qs, 1),
         "cpu_baseline": {"value": sps, "unit": "scans/s", "cores": cores, "kind": "port",
-                         "sample": f"{len(maps)} frames per step x {args.steps} steps, one oracle process per core "
+                         "sample": f"{len(idx)} frames per step x {args.steps} steps, one oracle process per core "
                                    "(the reference itself is single-threaded and cannot be compiled here: needs ROS/PCL/Eigen)"},
         "e2e": {"value": sps, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -221,19 +224,16 @@ def run_ours(args):
     # (a point survives if no frame rejected it) and the per-rank masks are all-gathered over NVLink.
     NG = len(map_world)
     gidx = torch.from_numpy(np.concatenate(idxs).astype(np.int64)).to(dev)
-    gather_buf = torch.empty((world, NG), dtype=torch.uint8, device=dev) if world > 1 else None
     keep_g = torch.ones(NG, dtype=torch.uint8, device=dev)
     final_keep = [None]
+
+    from erasor_b200 import dist as edist
 
     def exchange(keep_dev):
         with torch.cuda.stream(xs):
             keep_g.fill_(1)
-            keep_g.scatter_reduce_(0, gidx, keep_dev, reduce="amin")
-            if world > 1:
-                dist.all_gather_into_tensor(gather_buf.view(-1), keep_g)
-                final_keep[0] = gather_buf.amin(dim=0)
-            else:
-                final_keep[0] = keep_g
+            keep_g.scatter_reduce_(0, gidx, keep_dev, reduce="amin")     # == edist.fold_masks, buffers reused
+            final_keep[0] = edist.allgather_and(keep_g)                   # the single NCCL collective (no-op at N=1)
 
     def step_resident(i):
         c = i % N_INPUT_COPIES

@@ -145,9 +145,9 @@ void drain_timers(erasor_ctx* h) {
 }
 
 uint32_t choose_chunk(const erasor_ctx* h, size_t total_points, int mode) {
-    // Chunk = one CTA of K1 (and one warp of K2 in cloud mode).  Aim at ~12 chunks per SM.  In cloud mode the dense
+    // Chunk = one CTA of K1 (and one warp of K2 in cloud mode).  Aim at one wave of K1 CTAs (table init / flush amortised).  In cloud mode the dense
     // per-chunk count rows cost 4*(B+1) bytes each, so keep the chunk at >= 5*B points (<= 5 % extra traffic).
-    const size_t target = total_points / ((size_t)h->sm_count * 12) + 1;
+    const size_t target = total_points / ((size_t)h->sm_count * 4) + 1;      // one wave of 4 resident CTAs per SM
     size_t ch = std::max<size_t>(target, mode == 0 ? std::max<size_t>(2048, (size_t)5 * h->B) : (size_t)2048);
     ch = std::min<size_t>(ch, 65536);
     ch = (ch + 127) & ~(size_t)127;

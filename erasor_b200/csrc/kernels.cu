@@ -58,35 +58,11 @@ __device__ __forceinline__ void k1_aggregate(int key, uint32_t zenc, int lane, u
         return;
     }
     // runs of equal keys in lane order.  (Partial-mask __reduce_*_sync compiles to a per-lane software loop on sm_100a
-    // -- measured at 60 % of this kernel's instructions -- so runs are reduced either one at a time with full-mask REDUX
-    // (few runs: the common case for spatially coherent clouds) or with a segmented shuffle scan.)
+    // -- measured at 60 % of this kernel's instructions, also when the mask is full but the call sits in control flow the
+    // compiler cannot prove uniform -- so runs are reduced with a segmented shuffle scan.)
     const int      prev  = __shfl_up_sync(FULL_MASK, key, 1);
     const bool     head  = (lane == 0) || (key != prev);
     const unsigned heads = __ballot_sync(FULL_MASK, head);
-    const int      nruns = __popc(heads);
-    if (nruns <= 4) {
-        unsigned rest = heads;
-#pragma unroll 1
-        for (int r = 0; r < nruns; ++r) {
-            const int h = __ffs(rest) - 1;
-            rest &= rest - 1u;
-            const int e = rest ? (__ffs(rest) - 1) : 32;
-            const bool in = (lane >= h) && (lane < e);
-            const int  k  = __shfl_sync(FULL_MASK, key, h);
-            if (k >= 0 && k < B) {                                  // uniform across the warp
-                const uint32_t mn = __reduce_min_sync(FULL_MASK, in ? zenc : 0xFFFFFFFFu);
-                const uint32_t mx = __reduce_max_sync(FULL_MASK, in ? zenc : 0u);
-                if (lane == h) {
-                    atomicMin(&s_mn[k], mn);
-                    atomicMax(&s_mx[k], mx);
-                    atomicAdd(&s_cnt[k], (uint32_t)(e - h));
-                }
-            } else if (k == B && lane == h) {
-                atomicAdd(&s_cnt[B], (uint32_t)(e - h));
-            }
-        }
-        return;
-    }
     const unsigned above = heads & ~((2u << lane) - 1u);      // run heads at lanes > lane (lane 31: mask 0)
     const int      e     = above ? (__ffs(above) - 1) : 32;   // my run is [.., e)
     uint32_t mn = zenc, mx = zenc;
