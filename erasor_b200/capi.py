@@ -27,7 +27,18 @@ EXPORTS = [
     "erasor_get_max_range", "erasor_get_bins", "erasor_get_status", "erasor_get_planes", "erasor_get_static_mask",
     "erasor_get_fence_counts", "erasor_process_frames", "erasor_get_frame_stats", "erasor_kernel_launch_count",
     "erasor_get_kernel_time_ms", "erasor_reset_kernel_times", "erasor_get_rgpf_profile",
+    "erasor_updater_create", "erasor_updater_destroy", "erasor_updater_last_error", "erasor_updater_process_node",
+    "erasor_updater_map_size", "erasor_updater_get_cloud", "erasor_updater_save_static_map", "erasor_updater_voxelize",
+    "erasor_updater_erasor", "erasor_updater_kernel_launch_count",
 ]
+
+
+class UpdaterParamsC(ctypes.Structure):
+    """erasor_updater_params_t"""
+    _fields_ = [
+        ("query_voxel_size", c_double), ("map_voxel_size", c_double), ("removal_interval", c_int), ("is_large_scale", c_int),
+        ("submap_size", c_double), ("max_range", c_double), ("version", c_int), ("pad_", c_int), ("lidar2body", c_double * 7),
+    ]
 
 
 class ErasorError(RuntimeError):
@@ -73,6 +84,20 @@ def _load():
     L.erasor_get_kernel_time_ms.argtypes = [c_void_p, c_int, POINTER(c_double), POINTER(c_uint64)]
     L.erasor_reset_kernel_times.argtypes = [c_void_p, c_int]
     L.erasor_get_rgpf_profile.argtypes = [c_void_p, POINTER(c_uint32), POINTER(c_uint32), POINTER(c_size_t)]
+    L.erasor_updater_create.argtypes = [POINTER(UpdaterParamsC), POINTER(ErasorParamsC), c_void_p, c_size_t, c_int, POINTER(c_void_p)]
+    L.erasor_updater_destroy.restype = None
+    L.erasor_updater_destroy.argtypes = [c_void_p]
+    L.erasor_updater_last_error.restype = c_char_p
+    L.erasor_updater_last_error.argtypes = [c_void_p]
+    L.erasor_updater_process_node.argtypes = [c_void_p, c_int, POINTER(c_double), c_void_p, c_size_t, c_int, POINTER(c_int)]
+    L.erasor_updater_map_size.argtypes = [c_void_p, POINTER(c_size_t)]
+    L.erasor_updater_get_cloud.argtypes = [c_void_p, c_int, c_void_p, c_size_t, POINTER(c_size_t), c_int]
+    L.erasor_updater_save_static_map.argtypes = [c_void_p, c_float, c_void_p, c_size_t, POINTER(c_size_t)]
+    L.erasor_updater_voxelize.argtypes = [c_void_p, c_void_p, c_size_t, c_float, c_void_p, c_size_t, POINTER(c_size_t)]
+    L.erasor_updater_erasor.restype = c_void_p
+    L.erasor_updater_erasor.argtypes = [c_void_p]
+    L.erasor_updater_kernel_launch_count.restype = c_uint64
+    L.erasor_updater_kernel_launch_count.argtypes = [c_void_p]
     return L
 
 
@@ -271,3 +296,84 @@ class Handle:
         t, n = c_double(), c_uint64()
         self._ck(self.L.erasor_get_kernel_time_ms(self.h, kernel_id, ctypes.byref(t), ctypes.byref(n)))
         return t.value, n.value
+
+
+class Updater:
+    """Device-resident mirror of ``erasor::OfflineMapUpdater`` (one ``erasor_updater_t``)."""
+    MAP_ARRANGED, MAP_VOI, QUERY_VOI, MAP_REJECTED, OUTSKIRTS, SUBMAP_COMPLEMENT = 0, 1, 2, 5, 7, 8
+
+    def __init__(self, up, ep: ErasorParams, initial_map, device: int = 0):
+        self.L = lib()
+        self.ep, self.up = ep, up
+        upc = UpdaterParamsC()
+        upc.query_voxel_size, upc.map_voxel_size = up.query_voxel_size, up.map_voxel_size
+        upc.removal_interval, upc.is_large_scale = up.removal_interval, 1 if up.is_large_scale else 0
+        upc.submap_size, upc.max_range, upc.version = up.submap_size, up.max_range, up.version
+        for i in range(7):
+            upc.lidar2body[i] = up.lidar2body[i]
+        self._upc, self._epc = upc, ep.to_c()
+        m = _cloud(initial_map)
+        h = c_void_p()
+        rc = self.L.erasor_updater_create(ctypes.byref(upc), ctypes.byref(self._epc), m.ctypes.data, len(m), device, ctypes.byref(h))
+        if rc != OK:
+            raise ErasorError(rc, (self.L.erasor_updater_last_error(None) or b"").decode())
+        self.h = h
+
+    def _ck(self, rc: int):
+        if rc != OK:
+            raise ErasorError(rc, (self.L.erasor_updater_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.erasor_updater_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def process_node(self, seq: int, odom7, lidar) -> bool:
+        o = np.ascontiguousarray(odom7, dtype=np.float64)
+        l = _cloud(lidar)
+        done = c_int(0)
+        self._ck(self.L.erasor_updater_process_node(self.h, seq, o.ctypes.data_as(POINTER(c_double)), l.ctypes.data, len(l), PTR_HOST, ctypes.byref(done)))
+        return bool(done.value)
+
+    def process_node_ptr(self, seq: int, odom7, lidar_ptr: int, n: int, ptr_kind: int) -> bool:
+        o = np.ascontiguousarray(odom7, dtype=np.float64)
+        done = c_int(0)
+        self._ck(self.L.erasor_updater_process_node(self.h, seq, o.ctypes.data_as(POINTER(c_double)), c_void_p(lidar_ptr), n, ptr_kind, ctypes.byref(done)))
+        return bool(done.value)
+
+    def cloud(self, which: int) -> np.ndarray:
+        n = c_size_t(0)
+        self._ck(self.L.erasor_updater_get_cloud(self.h, which, None, 0, ctypes.byref(n), PTR_HOST))
+        out = np.empty((n.value, 4), dtype=np.float32)
+        if n.value:
+            self._ck(self.L.erasor_updater_get_cloud(self.h, which, out.ctypes.data, n.value, ctypes.byref(n), PTR_HOST))
+        return out
+
+    def map_size(self) -> int:
+        n = c_size_t(0)
+        self._ck(self.L.erasor_updater_map_size(self.h, ctypes.byref(n)))
+        return n.value
+
+    def save_static_map(self, voxel_size: float) -> np.ndarray:
+        n = c_size_t(0)
+        self._ck(self.L.erasor_updater_save_static_map(self.h, voxel_size, None, 0, ctypes.byref(n)))
+        out = np.empty((n.value, 4), dtype=np.float32)
+        if n.value:
+            self._ck(self.L.erasor_updater_save_static_map(self.h, voxel_size, out.ctypes.data, n.value, ctypes.byref(n)))
+        return out
+
+    def voxelize(self, cloud, leaf: float) -> np.ndarray:
+        c = _cloud(cloud)
+        out = np.empty((max(len(c), 1), 4), dtype=np.float32)
+        n = c_size_t(0)
+        self._ck(self.L.erasor_updater_voxelize(self.h, c.ctypes.data, len(c), leaf, out.ctypes.data, len(out), ctypes.byref(n)))
+        return out[:n.value].copy()
+
+    def kernel_launch_count(self) -> int:
+        return int(self.L.erasor_updater_kernel_launch_count(self.h))

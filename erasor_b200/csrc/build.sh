@@ -8,10 +8,12 @@ mkdir -p ../_lib ../_build
 NVCC=${NVCC:-nvcc}
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 CXXF="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC"
-$NVCC $ARCH $CXXF -Xptxas -v -c kernels.cu -o ../_build/kernels.o 2> ../_build/kernels.ptxas.log
+$NVCC $ARCH $CXXF -Xptxas -v -c kernels.cu -o ../_build/kernels.o 2> ../_build/kernels.ptxas.log || { cat ../_build/kernels.ptxas.log; exit 1; }
 $NVCC $ARCH $CXXF -c erasor_capi.cu -o ../_build/erasor_capi.o
+$NVCC $ARCH $CXXF -Xptxas -v -c updater_kernels.cu -o ../_build/updater_kernels.o 2> ../_build/updater_kernels.ptxas.log || { cat ../_build/updater_kernels.ptxas.log; exit 1; }
+$NVCC $ARCH $CXXF -c updater_capi.cu -o ../_build/updater_capi.o
 g++ -O2 -std=c++17 -fPIC -ffp-contract=off -c binning_tables.cpp -o ../_build/binning_tables.o
-$NVCC $ARCH -shared -o ../_lib/liberasor_b200.so ../_build/kernels.o ../_build/erasor_capi.o ../_build/binning_tables.o -lquadmath -lcudart
+$NVCC $ARCH -shared -o ../_lib/liberasor_b200.so ../_build/kernels.o ../_build/erasor_capi.o ../_build/updater_kernels.o ../_build/updater_capi.o ../_build/binning_tables.o -lquadmath -lcudart
 g++ -O2 -std=c++17 -fPIC -shared -ffp-contract=off -o ../_lib/liberasor_b200_hostcheck.so host_selftest.cpp binning_tables.cpp -lquadmath
 echo "built: $(ls ../_lib)"
 # C++ host-class demo (include/erasor/erasor.hpp over the C ABI)

@@ -83,6 +83,14 @@ __device__ __forceinline__ void k1_aggregate(int key, uint32_t zenc, int lane, u
     }
 }
 
+__device__ __forceinline__ float rsqrt_ftz(float v) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float div_ftz(float a, float b) { float r; asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+
+// the exact path of binning.h, kept out of line: it is taken by ~1e-4 of the points
+__device__ __noinline__ int bin_exact(const BinTablesView& T, const double* ring_thr, float x, float y, float z, BinFenceCounters* fc) {
+    return bin_of_point(T, ring_thr, x, y, z, fc);
+}
+
 // Branch-free fast path of binning.h's bin_of_point for the device: returns the bin, -1 (not binned) or -3 when the
 // point needs the exact path (ring guess off, sector coordinate inside the guard band, y == 0).  The decisions are the
 // same threshold comparisons as in binning.h; only the guesses use approximate float ops (MUFU rcp / rsqrt).
@@ -92,12 +100,12 @@ __device__ __forceinline__ int bin_fast(float x, float y, float z, float z_lo, f
     const double s  = fma(yd, yd, xd * xd);
     const bool inr  = (z < z_hi) && (z > z_lo) && (s <= s_max);
     const float sf  = fmaxf((float)s, 1e-30f);
-    int g = (int)(sf * rsqrtf(sf) * inv_ring);
+    int g = (int)(sf * rsqrt_ftz(sf) * inv_ring);
     g = min(g, R - 1);
     const bool ring_ok = (s_ring[g] <= s) && (s < s_ring[g + 1]);
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    float a = atan_unit(__fdividef(mn, mx));
+    float a = atan_unit(div_ftz(mn, mx));
     if (ay > ax)  a = 1.57079637f - a;
     if (x < 0.0f) a = 3.14159274f - a;
     if (y < 0.0f) a = 6.28318548f - a;
@@ -152,7 +160,7 @@ k1_rpod_bin(BinTablesView T, const float4* __restrict__ map_pts, const float4* _
             const bool ok = full || i < cd.len;
             int b = bin_fast(p[u].x, p[u].y, p[u].z, z_lo, z_hi, s_max, inv_ring, inv_ss, eps_q, R, S, s_ring);
             if (__any_sync(FULL_MASK, ok && b == -3)) {
-                if (ok && b == -3) b = bin_of_point(T, s_ring, p[u].x, p[u].y, p[u].z, &fc);   // exact path (rare)
+                if (ok && b == -3) b = bin_exact(T, s_ring, p[u].x, p[u].y, p[u].z, &fc);   // exact path (rare)
             }
             int key = -2;
             if (ok) {

@@ -1,0 +1,341 @@
+// updater_capi.cu -- device-resident mirror of erasor::OfflineMapUpdater (reference
+// src/offline_map_updater/src/OfflineMapUpdater.cpp:203-449, 174-196), ROS stripped: SURVEY.md section 8f rows 1-3.
+// The global map stays in HBM between nodes; per node only the raw scan and a pose cross PCIe.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/erasor_b200.h"
+#include "updater_kernels.h"
+
+using namespace erasor;
+
+namespace {
+struct Buf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes, bool keep = false, cudaStream_t st = nullptr, size_t keep_bytes = 0) {
+        if (bytes <= cap) return cudaSuccess;
+        void* q = nullptr;
+        const size_t want = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaMalloc(&q, want);
+        if (e != cudaSuccess) return e;
+        if (keep && p && keep_bytes) { e = cudaMemcpyAsync(q, p, keep_bytes, cudaMemcpyDeviceToDevice, st); if (e == cudaSuccess) e = cudaStreamSynchronize(st); }
+        if (p) cudaFree(p);
+        p = q; cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// erasor_utils::geoPose2eigen via tf::Matrix3x3(q) (erasor_utils.cpp:35-55): double quaternion math, cast to float
+void pose_to_mat(const double pose[7], Mat4& T) {
+    const double qx = pose[3], qy = pose[4], qz = pose[5], qw = pose[6];
+    const double d = qx * qx + qy * qy + qz * qz + qw * qw, s = 2.0 / d;
+    const double xs = qx * s, ys = qy * s, zs = qz * s;
+    const double wx = qw * xs, wy = qw * ys, wz = qw * zs, xx = qx * xs, xy = qx * ys, xz = qx * zs, yy = qy * ys, yz = qy * zs, zz = qz * zs;
+    const double m[9] = {1.0 - (yy + zz), xy - wz, xz + wy, xy + wz, 1.0 - (xx + zz), yz - wx, xz - wy, yz + wx, 1.0 - (xx + yy)};
+    for (int i = 0; i < 16; ++i) T.m[i] = 0.0f;
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) T.m[r * 4 + c] = (float)m[r * 3 + c];
+    T.m[3] = (float)pose[0]; T.m[7] = (float)pose[1]; T.m[11] = (float)pose[2]; T.m[15] = 1.0f;
+}
+void mat_mul(const Mat4& A, const Mat4& B, Mat4& C) {
+    Mat4 t;
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) { float acc = 0.0f; for (int k = 0; k < 4; ++k) acc += A.m[r * 4 + k] * B.m[k * 4 + c]; t.m[r * 4 + c] = acc; }
+    C = t;
+}
+// Eigen::Matrix4f::inverse() stand-in: general cofactor inverse in float (bits of Eigen's SSE kernel are unpinned)
+void mat_inv(const Mat4& M, Mat4& O) {
+    const float* m = M.m; float inv[16];
+    inv[0]  =  m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+    inv[4]  = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+    inv[8]  =  m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+    inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+    inv[1]  = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+    inv[5]  =  m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+    inv[9]  = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+    inv[13] =  m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+    inv[2]  =  m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+    inv[6]  = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+    inv[10] =  m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+    inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+    inv[3]  = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+    inv[7]  =  m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+    inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+    inv[15] =  m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+    float det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
+    det = 1.0f / det;
+    for (int i = 0; i < 16; ++i) O.m[i] = inv[i] * det;
+}
+}  // namespace
+
+struct erasor_updater_ctx {
+    erasor_updater_params_t up{};
+    erasor_params_t ep{};
+    erasor_handle_t er = nullptr;
+    int device = 0;
+    cudaStream_t st = nullptr;
+    std::string err;
+    Mat4 tf_lidar2body{}, tf_body2origin{};
+    // maps (origin frame), double-buffered
+    Buf map_a, map_b;        size_t n_map = 0;
+    Buf global_a;            size_t n_global = 0;      // large-scale: map_arranged_global_
+    Buf complement;          size_t n_complement = 0;  // large-scale: map_arranged_complement_
+    Buf scan, qvox, voi, outskirts, tmp_arr, tmp_cmp, tmp_rej, part_tmp, vox_tmp, grid, counters, save_out;
+    size_t n_query = 0, n_voi = 0, n_out = 0, n_rej = 0;
+    bool submap_uninit = true;
+    double submap_cx = 0, submap_cy = 0;
+    size_t num_pcs_init = 0;
+    int stack_count = 0;
+    uint64_t launches = 0;
+};
+
+namespace {
+thread_local std::string g_uerr;
+#define UCK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { u->err = std::string(#call) + ": " + cudaGetErrorString(e__); return ERASOR_E_CUDA; } } while (0)
+#define ECK(call) do { int rc__ = (call); if (rc__ != ERASOR_OK) { u->err = std::string(#call) + ": " + erasor_last_error(u->er); return rc__; } } while (0)
+
+int d2h_u32(erasor_updater_ctx* u, const uint32_t* d, uint32_t* h) {
+    UCK(cudaMemcpyAsync(h, d, sizeof(uint32_t), cudaMemcpyDeviceToHost, u->st));
+    UCK(cudaStreamSynchronize(u->st));
+    return ERASOR_OK;
+}
+
+// stable partition of src[0..n) into sel / rest (both in order); returns the number selected
+int partition(erasor_updater_ctx* u, const PartPred& P, const Mat4& T, bool xform, const float4* src, size_t n, Buf& sel, Buf& rest, size_t* n_sel) {
+    UCK(sel.ensure(sizeof(float4) * std::max<size_t>(n, 1)));
+    UCK(rest.ensure(sizeof(float4) * std::max<size_t>(n, 1)));
+    UCK(u->part_tmp.ensure(sizeof(uint32_t) * partition_tmp_words((uint32_t)n)));
+    u->launches += 3;
+    UCK(launch_partition(u->st, P, T, xform, src, (uint32_t)n, u->part_tmp.as<uint32_t>(), u->counters.as<uint32_t>(), sel.as<float4>(), rest.as<float4>()));
+    uint32_t k = 0;
+    int rc = d2h_u32(u, u->counters.as<uint32_t>(), &k);
+    if (rc) return rc;
+    *n_sel = k;
+    return ERASOR_OK;
+}
+
+int voxelize(erasor_updater_ctx* u, const float4* src, size_t n, float leaf, Buf& out, size_t* n_out) {
+    UCK(out.ensure(sizeof(float4) * std::max<size_t>(n, 1)));
+    UCK(u->vox_tmp.ensure(voxelize_tmp_bytes((uint32_t)n)));
+    u->launches += voxelize_num_launches();
+    UCK(launch_voxelize(u->st, src, (uint32_t)n, leaf, u->grid.as<VoxGrid>(), u->vox_tmp.p, out.as<float4>(), u->counters.as<uint32_t>() + 1));
+    uint32_t k = 0;
+    int rc = d2h_u32(u, u->counters.as<uint32_t>() + 1, &k);
+    if (rc) return rc;
+    *n_out = k;
+    return ERASOR_OK;
+}
+
+// set_submap + bookkeeping of reassign_submap (OfflineMapUpdater.cpp:332-379)
+int reassign_submap(erasor_updater_ctx* u, double px, double py) {
+    auto split = [&]() -> int {
+        PartPred P{PART_SUBMAP, 0, px, py, u->up.submap_size};
+        Mat4 I{};
+        size_t nsel = 0;
+        int rc = partition(u, P, I, false, u->global_a.as<float4>(), u->n_global, u->map_a, u->complement, &nsel);
+        if (rc) return rc;
+        u->n_map = nsel; u->n_complement = u->n_global - nsel;
+        u->submap_cx = px; u->submap_cy = py;
+        return ERASOR_OK;
+    };
+    if (u->submap_uninit) {
+        int rc = split();
+        if (rc) return rc;
+        u->submap_uninit = false;
+        return ERASOR_OK;
+    }
+    const double dx = std::abs(u->submap_cx - px), dy = std::abs(u->submap_cy - py), half = u->up.submap_size / 2.0;
+    if (dx > half || dy > half) {
+        // map_arranged_global_ = map_arranged_ + map_arranged_complement_
+        const size_t n = u->n_map + u->n_complement;
+        UCK(u->global_a.ensure(sizeof(float4) * std::max<size_t>(n, 1)));
+        if (u->n_map) UCK(cudaMemcpyAsync(u->global_a.p, u->map_a.p, sizeof(float4) * u->n_map, cudaMemcpyDeviceToDevice, u->st));
+        if (u->n_complement) UCK(cudaMemcpyAsync(u->global_a.as<float4>() + u->n_map, u->complement.p, sizeof(float4) * u->n_complement, cudaMemcpyDeviceToDevice, u->st));
+        u->n_global = n;
+        return split();
+    }
+    return ERASOR_OK;
+}
+}  // namespace
+
+extern "C" {
+
+const char* erasor_updater_last_error(erasor_updater_t u) { return u ? u->err.c_str() : g_uerr.c_str(); }
+
+int erasor_updater_create(const erasor_updater_params_t* up, const erasor_params_t* ep, const float* initial_map_xyzi, size_t n_map,
+                          int device, erasor_updater_t* out) {
+    if (!up || !ep || !out || (n_map && !initial_map_xyzi)) { g_uerr = "null argument"; return ERASOR_E_INVALID; }
+    *out = nullptr;
+    if (up->removal_interval < 1) { g_uerr = "removal_interval must be >= 1"; return ERASOR_E_INVALID; }
+    erasor_updater_ctx* u = new erasor_updater_ctx();
+    u->up = *up; u->ep = *ep; u->device = device;
+    erasor_params_t e2 = *ep;
+    e2.version = up->version;                              // /erasor/version is read by the updater (OfflineMapUpdater.cpp:81)
+    int rc = erasor_create(&e2, device, &u->er);
+    if (rc != ERASOR_OK) { g_uerr = erasor_last_error(nullptr); delete u; return rc; }
+    u->st = (cudaStream_t)erasor_stream(u->er);
+    auto fail = [&](const char* what, cudaError_t ce) { g_uerr = std::string(what) + ": " + cudaGetErrorString(ce); erasor_updater_destroy(u); return ERASOR_E_CUDA; };
+    cudaError_t e;
+    if ((e = u->counters.ensure(64)) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = u->grid.ensure(sizeof(VoxGrid))) != cudaSuccess) return fail("cudaMalloc", e);
+    // set_params (OfflineMapUpdater.cpp:89-104): tf_lidar2body_ = geoPose2eigen(pose) * Identity
+    Mat4 G, I{};
+    for (int i = 0; i < 4; ++i) I.m[i * 5] = 1.0f;
+    pose_to_mat(up->lidar2body, G);
+    mat_mul(G, I, u->tf_lidar2body);
+    u->tf_body2origin = I;
+    // load_global_map (OfflineMapUpdater.cpp:107-167), outdoor
+    u->num_pcs_init = n_map;
+    Buf& dst = up->is_large_scale ? u->global_a : u->map_a;
+    if ((e = dst.ensure(sizeof(float4) * std::max<size_t>(n_map, 1))) != cudaSuccess) return fail("cudaMalloc", e);
+    if (n_map && (e = cudaMemcpy(dst.p, initial_map_xyzi, sizeof(float4) * n_map, cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy", e);
+    if (up->is_large_scale) { u->n_global = n_map; u->n_map = 0; } else { u->n_map = n_map; }
+    *out = u;
+    return ERASOR_OK;
+}
+
+void erasor_updater_destroy(erasor_updater_t u) {
+    if (!u) return;
+    cudaSetDevice(u->device);
+    if (u->st) cudaStreamSynchronize(u->st);
+    Buf* bufs[] = {&u->map_a, &u->map_b, &u->global_a, &u->complement, &u->scan, &u->qvox, &u->voi, &u->outskirts, &u->tmp_arr, &u->tmp_cmp,
+                   &u->tmp_rej, &u->part_tmp, &u->vox_tmp, &u->grid, &u->counters, &u->save_out};
+    for (Buf* b : bufs) b->release();
+    if (u->er) erasor_destroy(u->er);
+    delete u;
+}
+
+erasor_handle_t erasor_updater_erasor(erasor_updater_t u) { return u ? u->er : nullptr; }
+
+// OfflineMapUpdater::callback_node (OfflineMapUpdater.cpp:203-330)
+int erasor_updater_process_node(erasor_updater_t u, int seq, const double* odom7, const float* lidar_xyzi, size_t n_lidar, int ptr_kind, int* processed) {
+    if (!u || !odom7 || (n_lidar && !lidar_xyzi)) { if (u) u->err = "null argument"; return ERASOR_E_INVALID; }
+    if (processed) *processed = 0;
+    u->stack_count++;
+    if (u->stack_count % u->up.removal_interval != 0) return ERASOR_OK;                      // "PASS!" (:328)
+    UCK(cudaSetDevice(u->device));
+    pose_to_mat(odom7, u->tf_body2origin);                                                    // :219
+    // 1. query: voxelize_preserving_labels, lidar -> body (:237-241)
+    const float4* d_scan = reinterpret_cast<const float4*>(lidar_xyzi);
+    if (ptr_kind != ERASOR_PTR_DEVICE) {
+        UCK(u->scan.ensure(sizeof(float4) * std::max<size_t>(n_lidar, 1)));
+        if (n_lidar) UCK(cudaMemcpyAsync(u->scan.p, lidar_xyzi, sizeof(float4) * n_lidar, cudaMemcpyHostToDevice, u->st));
+        d_scan = u->scan.as<float4>();
+    }
+    int rc = voxelize(u, d_scan, n_lidar, (float)u->up.query_voxel_size, u->qvox, &u->n_query);
+    if (rc) return rc;
+    u->launches++;
+    UCK(launch_affine_copy(u->st, u->tf_lidar2body, true, u->qvox.as<float4>(), u->qvox.as<float4>(), (uint32_t)u->n_query));
+    // 2. map VoI (:246-254)
+    const double x_curr = u->tf_body2origin.m[3], y_curr = u->tf_body2origin.m[7];
+    if (u->up.is_large_scale && (rc = reassign_submap(u, x_curr, y_curr))) return rc;
+    Mat4 Tinv;
+    mat_inv(u->tf_body2origin, Tinv);
+    PartPred P{PART_RADIUS, 0, x_curr, y_curr, std::pow(u->up.max_range + 0.0, 2)};
+    if ((rc = partition(u, P, Tinv, true, u->map_a.as<float4>(), u->n_map, u->voi, u->outskirts, &u->n_voi))) return rc;
+    u->n_out = u->n_map - u->n_voi;
+    // 3. the path (:266-275)
+    ECK(erasor_set_inputs(u->er, u->voi.as<float>(), u->n_voi, u->qvox.as<float>(), u->n_query, ERASOR_PTR_DEVICE));
+    if (u->up.version != 2 && u->up.version != 3) { u->err = "Other version is not implemented!"; return ERASOR_E_INVALID; }
+    ECK(erasor_compare(u->er, u->up.version, seq));
+    size_t n_arr = 0, n_cmp = 0, n_rej = 0, n_crej = 0;
+    ECK(erasor_get_output_sizes(u->er, &n_arr, &n_cmp, &n_rej, &n_crej));
+    UCK(u->tmp_arr.ensure(sizeof(float4) * std::max<size_t>(n_arr, 1)));
+    UCK(u->tmp_cmp.ensure(sizeof(float4) * std::max<size_t>(n_cmp, 1)));
+    UCK(u->tmp_rej.ensure(sizeof(float4) * std::max<size_t>(n_rej, 1)));
+    ECK(erasor_get_static_estimate(u->er, u->tmp_arr.as<float>(), n_arr, &n_arr, u->tmp_cmp.as<float>(), n_cmp, &n_cmp, ERASOR_PTR_DEVICE));
+    ECK(erasor_get_outliers(u->er, u->tmp_rej.as<float>(), n_rej, &n_rej, nullptr, 0, &n_crej, ERASOR_PTR_DEVICE));
+    // 4. map_filtered = static + complement, body -> origin, + outskirts (:281-290)
+    const size_t n_new = n_arr + n_cmp + u->n_out;
+    UCK(u->map_b.ensure(sizeof(float4) * std::max<size_t>(n_new, 1)));
+    u->launches += 3;
+    UCK(launch_affine_copy(u->st, u->tf_body2origin, true, u->tmp_arr.as<float4>(), u->map_b.as<float4>(), (uint32_t)n_arr));
+    UCK(launch_affine_copy(u->st, u->tf_body2origin, true, u->tmp_cmp.as<float4>(), u->map_b.as<float4>() + n_arr, (uint32_t)n_cmp));
+    if (u->n_out) UCK(cudaMemcpyAsync(u->map_b.as<float4>() + n_arr + n_cmp, u->outskirts.p, sizeof(float4) * u->n_out, cudaMemcpyDeviceToDevice, u->st));
+    UCK(launch_affine_copy(u->st, u->tf_body2origin, true, u->tmp_rej.as<float4>(), u->tmp_rej.as<float4>(), (uint32_t)n_rej));   // :287
+    u->n_rej = n_rej;
+    UCK(cudaStreamSynchronize(u->st));
+    std::swap(u->map_a, u->map_b);
+    u->n_map = n_new;
+    if (processed) *processed = 1;
+    return ERASOR_OK;
+}
+
+int erasor_updater_map_size(erasor_updater_t u, size_t* n) {
+    if (!u || !n) return ERASOR_E_INVALID;
+    *n = u->n_map;
+    return ERASOR_OK;
+}
+
+// which: 0 map_arranged_, 1 map_voi_ (body frame), 2 query_voi_ (body frame), 5 map_rejected_ (origin frame), 7 map_outskirts_,
+//        8 map_arranged_complement_ (large-scale)
+int erasor_updater_get_cloud(erasor_updater_t u, int which, float* xyzi, size_t cap, size_t* n, int ptr_kind) {
+    if (!u || !n) return ERASOR_E_INVALID;
+    const void* src = nullptr; size_t k = 0;
+    switch (which) {
+        case 0: src = u->map_a.p; k = u->n_map; break;
+        case 1: src = u->voi.p; k = u->n_voi; break;
+        case 2: src = u->qvox.p; k = u->n_query; break;
+        case 5: src = u->tmp_rej.p; k = u->n_rej; break;
+        case 7: src = u->outskirts.p; k = u->n_out; break;
+        case 8: src = u->complement.p; k = u->n_complement; break;
+        default: u->err = "unknown cloud id"; return ERASOR_E_INVALID;
+    }
+    *n = k;
+    if (!xyzi) return ERASOR_OK;
+    if (cap < k) { u->err = "output buffer too small"; return ERASOR_E_CAPACITY; }
+    UCK(cudaSetDevice(u->device));
+    if (k) UCK(cudaMemcpyAsync(xyzi, src, sizeof(float4) * k, ptr_kind == ERASOR_PTR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, u->st));
+    UCK(cudaStreamSynchronize(u->st));
+    return ERASOR_OK;
+}
+
+// OfflineMapUpdater::save_static_map minus the file write (OfflineMapUpdater.cpp:174-196)
+int erasor_updater_save_static_map(erasor_updater_t u, float voxel_size, float* out_xyzi, size_t cap, size_t* n) {
+    if (!u || !n) return ERASOR_E_INVALID;
+    UCK(cudaSetDevice(u->device));
+    const float4* src = u->map_a.as<float4>();
+    size_t ns = u->n_map;
+    if (u->up.is_large_scale) {
+        // *ptr_src = *map_arranged_ + *map_arranged_complement_
+        UCK(u->map_b.ensure(sizeof(float4) * std::max<size_t>(u->n_map + u->n_complement, 1)));
+        if (u->n_map) UCK(cudaMemcpyAsync(u->map_b.p, u->map_a.p, sizeof(float4) * u->n_map, cudaMemcpyDeviceToDevice, u->st));
+        if (u->n_complement) UCK(cudaMemcpyAsync(u->map_b.as<float4>() + u->n_map, u->complement.p, sizeof(float4) * u->n_complement, cudaMemcpyDeviceToDevice, u->st));
+        src = u->map_b.as<float4>(); ns = u->n_map + u->n_complement;
+    }
+    size_t k = 0;
+    int rc = voxelize(u, src, ns, voxel_size, u->save_out, &k);
+    if (rc) return rc;
+    *n = k;
+    if (!out_xyzi) return ERASOR_OK;
+    if (cap < k) { u->err = "output buffer too small"; return ERASOR_E_CAPACITY; }
+    if (k) UCK(cudaMemcpyAsync(out_xyzi, u->save_out.p, sizeof(float4) * k, cudaMemcpyDeviceToHost, u->st));
+    UCK(cudaStreamSynchronize(u->st));
+    return ERASOR_OK;
+}
+
+// voxelize_preserving_labels on a free-standing host cloud (unit-test entry for U3)
+int erasor_updater_voxelize(erasor_updater_t u, const float* xyzi, size_t n_in, float leaf, float* out_xyzi, size_t cap, size_t* n) {
+    if (!u || !n || (n_in && !xyzi)) return ERASOR_E_INVALID;
+    UCK(cudaSetDevice(u->device));
+    UCK(u->scan.ensure(sizeof(float4) * std::max<size_t>(n_in, 1)));
+    if (n_in) UCK(cudaMemcpyAsync(u->scan.p, xyzi, sizeof(float4) * n_in, cudaMemcpyHostToDevice, u->st));
+    size_t k = 0;
+    int rc = voxelize(u, u->scan.as<float4>(), n_in, leaf, u->save_out, &k);
+    if (rc) return rc;
+    *n = k;
+    if (!out_xyzi) return ERASOR_OK;
+    if (cap < k) { u->err = "output buffer too small"; return ERASOR_E_CAPACITY; }
+    if (k) UCK(cudaMemcpyAsync(out_xyzi, u->save_out.p, sizeof(float4) * k, cudaMemcpyDeviceToHost, u->st));
+    UCK(cudaStreamSynchronize(u->st));
+    return ERASOR_OK;
+}
+
+uint64_t erasor_updater_kernel_launch_count(erasor_updater_t u) { return u ? u->launches + erasor_kernel_launch_count(u->er) : 0; }
+
+}  // extern "C"

@@ -148,6 +148,48 @@ uint64_t erasor_kernel_launch_count(erasor_handle_t h);
 int erasor_get_kernel_time_ms(erasor_handle_t h, int kernel_id, double* total_ms, uint64_t* launches);
 int erasor_reset_kernel_times(erasor_handle_t h, int enable_timing);
 
+/* ============================================================================================
+ * The caller, device-resident: erasor::OfflineMapUpdater (reference include/erasor/OfflineMapUpdater.h,
+ * src/offline_map_updater/src/OfflineMapUpdater.cpp) with ROS stripped -- SURVEY.md section 8f rows 1-3.
+ * The global map lives in HBM; per node only the raw scan and the pose cross PCIe.
+ * ========================================================================================== */
+typedef struct erasor_updater_ctx* erasor_updater_t;
+
+typedef struct {
+    double query_voxel_size;   /* /MapUpdater/query_voxel_size   OfflineMapUpdater.cpp:66 */
+    double map_voxel_size;     /* /MapUpdater/map_voxel_size     :67 (unused by the path) */
+    int    removal_interval;   /* /MapUpdater/removal_interval   :69 */
+    int    is_large_scale;     /* /large_scale/is_large_scale    :75 */
+    double submap_size;        /* /large_scale/submap_size       :76 */
+    double max_range;          /* /erasor/max_range as read by the updater, default 60.0  :78 */
+    int    version;            /* /erasor/version                :81 */
+    int    pad_;
+    double lidar2body[7];      /* /tf/lidar2body  x y z qx qy qz qw   :89-104 */
+} erasor_updater_params_t;
+
+/* replaces OfflineMapUpdater::OfflineMapUpdater() = set_params + load_global_map + new ERASOR (:5-32, 63-167);
+ * the initial map is handed over as a host cloud instead of a PCD path. */
+int  erasor_updater_create(const erasor_updater_params_t* up, const erasor_params_t* ep, const float* initial_map_xyzi, size_t n_map,
+                           int device, erasor_updater_t* out);
+void erasor_updater_destroy(erasor_updater_t u);
+const char* erasor_updater_last_error(erasor_updater_t u);
+/* replaces OfflineMapUpdater::callback_node(msg) (:203-330): seq = msg->header.seq, odom7 = msg->odom as x y z qx qy qz qw
+ * (body -> origin), lidar = msg->lidar in the LIDAR frame.  *processed = 1 when the node was processed (every
+ * removal_interval-th call), 0 for the reference's "PASS!". */
+int  erasor_updater_process_node(erasor_updater_t u, int seq, const double* odom7, const float* lidar_xyzi, size_t n_lidar, int ptr_kind,
+                                 int* processed);
+int  erasor_updater_map_size(erasor_updater_t u, size_t* n);
+/* clouds of the last processed node (parity taps): 0 map_arranged_, 1 map_voi_ (body), 2 query_voi_ (body),
+ * 5 map_rejected_ (origin), 7 map_outskirts_, 8 map_arranged_complement_ (large-scale).  xyzi may be NULL to query *n. */
+int  erasor_updater_get_cloud(erasor_updater_t u, int which, float* xyzi, size_t cap, size_t* n, int ptr_kind);
+/* replaces OfflineMapUpdater::save_static_map(voxel_size) minus the PCD write (:174-196) */
+int  erasor_updater_save_static_map(erasor_updater_t u, float voxel_size, float* out_xyzi, size_t cap, size_t* n);
+/* erasor_utils::voxelize_preserving_labels on a free-standing host cloud (erasor_utils.cpp:80-114) */
+int  erasor_updater_voxelize(erasor_updater_t u, const float* xyzi, size_t n_in, float leaf, float* out_xyzi, size_t cap, size_t* n);
+/* the ERASOR handle inside the updater (for the parity taps above) */
+erasor_handle_t erasor_updater_erasor(erasor_updater_t u);
+uint64_t erasor_updater_kernel_launch_count(erasor_updater_t u);
+
 #ifdef __cplusplus
 }
 #endif

@@ -171,7 +171,7 @@ int oracle_updater_callback_node(void* h, int seq, const double* odom7, const fl
 double oracle_updater_last_erasor_seconds(void* h) { return static_cast<USession*>(h)->u->last_erasor_seconds; }
 double oracle_updater_last_voi_seconds(void* h) { return static_cast<USession*>(h)->u->last_voi_seconds; }
 // which: 0 map_arranged_, 1 map_voi_, 2 query_voi_, 3 map_static_estimate_, 4 map_egocentric_complement_,
-//        5 map_rejected_ (origin frame), 6 total_map_rejected_, 7 map_outskirts_
+//        5 map_rejected_ (origin frame), 6 total_map_rejected_, 7 map_outskirts_, 8 map_arranged_complement_
 static const Cloud* upick(USession* s, int which) {
     switch (which) {
         case 0: return &s->u->map_arranged_;
@@ -182,6 +182,7 @@ static const Cloud* upick(USession* s, int which) {
         case 5: return &s->u->map_rejected_;
         case 6: return &s->u->total_map_rejected_;
         case 7: return &s->u->map_outskirts_;
+        case 8: return &s->u->map_arranged_complement_;
         default: return nullptr;
     }
 }

@@ -252,7 +252,7 @@ def invert4(T) -> np.ndarray:
 
 class OracleUpdater:
     """The restated caller loop (OfflineMapUpdater::callback_node)."""
-    MAP_ARRANGED, MAP_VOI, QUERY_VOI, STATIC_EST, EGO_COMPLEMENT, MAP_REJECTED, TOTAL_MAP_REJECTED, OUTSKIRTS = range(8)
+    MAP_ARRANGED, MAP_VOI, QUERY_VOI, STATIC_EST, EGO_COMPLEMENT, MAP_REJECTED, TOTAL_MAP_REJECTED, OUTSKIRTS, SUBMAP_COMPLEMENT = range(9)
 
     def __init__(self, up, ep, initial_map):
         self.L = lib()
@@ -302,7 +302,7 @@ class OracleUpdater:
         return xyzi, src
 
     def save_static_map(self, voxel_size: float) -> np.ndarray:
-        n = self.L.oracle_updater_cloud_size(self.h, 0) + 16
+        n = self.L.oracle_updater_cloud_size(self.h, 0) + self.L.oracle_updater_cloud_size(self.h, 8) + 16
         out = np.empty((n, 4), dtype=np.float32)
         k = self.L.oracle_updater_save_static_map(self.h, voxel_size, _fptr(out), n)
         return out[:k].copy()
