@@ -1,0 +1,92 @@
+"""GPU: the C++ host side end to end.  examples/offline_map_updater_main (the ROS-free counterpart of the reference's
+main_in_your_env.cpp) reads the reference's file layout -- dense_global_map.pcd, poses_lidar2body.csv, pcds/%06d.pcd and a
+reference-style config yaml -- drives the device-resident OfflineMapUpdater class and writes <data_name>_result.pcd.
+The result must equal the oracle's pass point for point, hence give the same PR / RR."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from erasor_b200 import evaluate as E
+from erasor_b200 import params as P
+from erasor_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "erasor_b200", "_lib", "offline_map_updater_main")
+
+YAML = """
+erasor:
+    max_range: 60.0
+    num_rings: 15
+    num_sectors: 60
+    min_h: -1.3   # [m]
+    max_h: 3.2
+    th_bin_max_h: 0.05
+    scan_ratio_threshold: 0.3
+    minimum_num_pts: 10
+    rejection_ratio: 0
+    gf_dist_thr: 0.15
+    gf_iter: 3
+    gf_num_lpr: 10
+    gf_th_seeds_height: 0.5
+    version: 3
+
+MapUpdater:
+    data_name: "05"
+    initial_map_path: "unused"
+    env: "outdoor"
+    save_path: "{save}"
+    query_voxel_size: 0.2
+    map_voxel_size: 0.05
+    voxelization_interval: 5
+    removal_interval: 2
+
+tf:
+     lidar2body: [0.0, 0.0, 1.73, 0, 0.0, 0.0, 1.0] # xyz q_x, q_y, q_z, q_w in order
+
+verbose: false
+"""
+
+
+def test_cpp_driver_matches_oracle_pass(tmp_path, oracle_mod):
+    assert os.path.exists(BIN), "build with erasor_b200/csrc/build.sh"
+    sc = synth.Scene(seed=43, length=40.0, n_nodes=15, n_dynamic=6)
+    kw = dict(n_beams=24, n_az=480)
+    nodes = list(range(15))
+    gt_map = sc.build_map(nodes, voxel=0.2, **kw)
+    data = tmp_path / "data"
+    (data / "pcds").mkdir(parents=True)
+    save = tmp_path / "out"
+    save.mkdir()
+    E.write_pcd_ascii(str(data / "dense_global_map.pcd"), gt_map)
+    scans, poses = [], []
+    with open(data / "poses_lidar2body.csv", "w") as f:
+        f.write("index,time,x,y,z,qx,qy,qz,qw\n")
+        for k in nodes:
+            s = sc.scan(k, seed_offset=9, **kw)
+            E.write_pcd_ascii(str(data / "pcds" / f"{k:06d}.pcd"), s)
+            p = sc.pose7(k)
+            f.write(f"{k},{k * 0.1}," + ",".join(f"{v:.9g}" for v in p) + "\n")
+            scans.append(E.read_pcd_ascii(str(data / "pcds" / f"{k:06d}.pcd")))      # what the driver will actually read
+            poses.append(np.array([np.float32(v) for v in (f"{v:.9g}" for v in p)], dtype=np.float64))  # stof() in the driver
+    cfg = tmp_path / "seq_05.yaml"
+    cfg.write_text(YAML.format(save=str(save)))
+    r = subprocess.run([BIN, str(cfg), str(data)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:] + r.stdout[-2000:]
+    result = E.read_pcd_ascii(str(save / "05_result.pcd"))
+
+    ep, up = P.preset("seq_05"), P.updater_preset("seq_05")
+    up.removal_interval = 2
+    m0 = E.read_pcd_ascii(str(data / "dense_global_map.pcd"))
+    o = oracle_mod.OracleUpdater(up, ep, m0)
+    for k in nodes:
+        o.callback_node(k, poses[k], scans[k])
+    ref = o.save_static_map(0.2)
+    assert result.shape == ref.shape
+    # the ASCII writer prints 8 significant digits: compare at that precision
+    assert np.allclose(result, ref, rtol=2e-7, atol=1e-7)
+    a, b = E.evaluate(m0, result), E.evaluate(m0, ref)
+    assert abs(a["PR"] - b["PR"]) < 1e-9 and abs(a["RR"] - b["RR"]) < 1e-9
+    assert b["RR"] > 20.0
