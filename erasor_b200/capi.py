@@ -27,7 +27,7 @@ EXPORTS = [
     "erasor_get_max_range", "erasor_get_bins", "erasor_get_status", "erasor_get_planes", "erasor_get_static_mask",
     "erasor_get_fence_counts", "erasor_process_frames", "erasor_get_frame_stats", "erasor_kernel_launch_count",
     "erasor_get_kernel_time_ms", "erasor_reset_kernel_times", "erasor_get_rgpf_profile",
-    "erasor_updater_create", "erasor_updater_destroy", "erasor_updater_last_error", "erasor_updater_process_node",
+    "erasor_updater_create", "erasor_updater_destroy", "erasor_updater_reset", "erasor_updater_last_error", "erasor_updater_process_node",
     "erasor_updater_map_size", "erasor_updater_get_cloud", "erasor_updater_save_static_map", "erasor_updater_voxelize",
     "erasor_updater_erasor", "erasor_updater_kernel_launch_count",
 ]
@@ -87,6 +87,7 @@ def _load():
     L.erasor_updater_create.argtypes = [POINTER(UpdaterParamsC), POINTER(ErasorParamsC), c_void_p, c_size_t, c_int, POINTER(c_void_p)]
     L.erasor_updater_destroy.restype = None
     L.erasor_updater_destroy.argtypes = [c_void_p]
+    L.erasor_updater_reset.argtypes = [c_void_p, c_void_p, c_size_t]
     L.erasor_updater_last_error.restype = c_char_p
     L.erasor_updater_last_error.argtypes = [c_void_p]
     L.erasor_updater_process_node.argtypes = [c_void_p, c_int, POINTER(c_double), c_void_p, c_size_t, c_int, POINTER(c_int)]
@@ -333,6 +334,10 @@ class Updater:
             self.close()
         except Exception:
             pass
+
+    def reset(self, initial_map):
+        m = _cloud(initial_map)
+        self._ck(self.L.erasor_updater_reset(self.h, m.ctypes.data, len(m)))
 
     def process_node(self, seq: int, odom7, lidar) -> bool:
         o = np.ascontiguousarray(odom7, dtype=np.float64)

@@ -493,13 +493,87 @@ k2_scatter(const ChunkDesc* __restrict__ chunks, uint32_t chunk_base, int F, con
     }
 }
 
+// Multi-warp variant: the CTA's W warps split the chunk into W contiguous sub-ranges.  Pass A counts each sub-range per
+// bin into the warp's own shared-memory row (match_any dedups a 32-point step, so no atomics); a column scan turns the
+// rows into absolute destinations (dst_start + earlier chunks + earlier warps); pass B re-walks the sub-range in order.
+// W x more parallelism per chunk than the one-warp kernel; needs W*(B+1)*4 bytes of shared memory.
+template <int W>
+__global__ void __launch_bounds__(W * 32)
+k2_scatter_mw(const ChunkDesc* __restrict__ chunks, uint32_t chunk_base, const uint16_t* __restrict__ bin_ids,
+              const float4* __restrict__ pts, const uint32_t* __restrict__ ch_cnt, const uint32_t* __restrict__ dst_start,
+              float4* __restrict__ out_pts, uint32_t* __restrict__ out_src, int B) {
+    extern __shared__ uint32_t s_tab[];   // [W][B+1]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t row = chunk_base + blockIdx.x;
+    const ChunkDesc cd = chunks[row];
+    const uint32_t* ds   = dst_start + (size_t)cd.frame * (B + 2);
+    const uint32_t* pref = ch_cnt + (size_t)row * (B + 1);
+    uint32_t* mine = s_tab + (size_t)warp * (B + 1);
+    for (int i = tid; i < W * (B + 1); i += W * 32) s_tab[i] = 0u;
+    __syncthreads();
+    const uint32_t sub = (((cd.len + W - 1) / W) + 31u) & ~31u;
+    const uint32_t s0 = min(cd.len, (uint32_t)warp * sub), s1 = min(cd.len, s0 + sub);
+    for (uint32_t i0 = s0; i0 < s1; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const bool valid = i < s1;
+        const unsigned vmask = __ballot_sync(FULL_MASK, valid);
+        if (valid) {
+            const uint16_t id = bin_ids[cd.begin + i];
+            const int key = (id == kNoBin16) ? B : (int)id;
+            const unsigned peers = __match_any_sync(vmask, key);
+            if (lane == __ffs(peers) - 1) mine[key] += __popc(peers);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int b = tid; b <= B; b += W * 32) {
+        const uint32_t d = ds[b];
+        uint32_t run = (d == kSkip) ? 0u : d + pref[b];
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const uint32_t c = s_tab[(size_t)w * (B + 1) + b];
+            s_tab[(size_t)w * (B + 1) + b] = (d == kSkip) ? kSkip : run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    const uint32_t local0 = cd.begin - cd.frame_begin;
+    for (uint32_t i0 = s0; i0 < s1; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const bool valid = i < s1;
+        const unsigned vmask = __ballot_sync(FULL_MASK, valid);
+        if (valid) {
+            const uint16_t id = bin_ids[cd.begin + i];
+            const int key = (id == kNoBin16) ? B : (int)id;
+            const unsigned peers = __match_any_sync(vmask, key);
+            const uint32_t base = mine[key];
+            __syncwarp(vmask);
+            if (base != kSkip) {
+                if (lane == __ffs(peers) - 1) mine[key] = base + __popc(peers);
+                const size_t o = (size_t)cd.frame_begin + base + __popc(peers & ((1u << lane) - 1u));
+                out_pts[o] = pts[cd.begin + i];
+                out_src[o] = local0 + i;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 cudaError_t launch_k2(cudaStream_t st, const ChunkDesc* chunks, uint32_t chunk_base, uint32_t n_chunks, int F,
                       const uint16_t* bin_ids, const float4* pts, const uint32_t* ch_cnt, const uint32_t* dst_start,
                       float4* out_pts, uint32_t* out_src, int B) {
     if (n_chunks == 0) return cudaSuccess;
+    constexpr int W = 8;
+    const size_t smem_mw = sizeof(uint32_t) * (size_t)W * (B + 1);
+    cudaError_t e;
+    if (smem_mw <= 200 * 1024) {
+        auto kern = k2_scatter_mw<W>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mw)) != cudaSuccess) return e;
+        kern<<<n_chunks, W * 32, smem_mw, st>>>(chunks, chunk_base, bin_ids, pts, ch_cnt, dst_start, out_pts, out_src, B);
+        return cudaGetLastError();
+    }
     const size_t smem = sizeof(uint32_t) * ((size_t)B + 1);
-    cudaError_t e = cudaFuncSetAttribute(k2_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k2_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     k2_scatter<<<n_chunks, 32, smem, st>>>(chunks, chunk_base, F, bin_ids, pts, ch_cnt, dst_start, out_pts, out_src, B);
     return cudaGetLastError();
 }

@@ -210,6 +210,23 @@ void erasor_updater_destroy(erasor_updater_t u) {
     delete u;
 }
 
+// re-arm the updater with a (new) initial map, keeping every device buffer: load_global_map again (OfflineMapUpdater.cpp:107-167)
+int erasor_updater_reset(erasor_updater_t u, const float* initial_map_xyzi, size_t n_map) {
+    if (!u || (n_map && !initial_map_xyzi)) { if (u) u->err = "null argument"; return ERASOR_E_INVALID; }
+    UCK(cudaSetDevice(u->device));
+    UCK(cudaStreamSynchronize(u->st));
+    Buf& dst = u->up.is_large_scale ? u->global_a : u->map_a;
+    UCK(dst.ensure(sizeof(float4) * std::max<size_t>(n_map, 1)));
+    if (n_map) UCK(cudaMemcpyAsync(dst.p, initial_map_xyzi, sizeof(float4) * n_map, cudaMemcpyHostToDevice, u->st));
+    UCK(cudaStreamSynchronize(u->st));
+    u->num_pcs_init = n_map;
+    u->n_map = u->up.is_large_scale ? 0 : n_map;
+    u->n_global = u->up.is_large_scale ? n_map : 0;
+    u->n_complement = 0; u->n_query = u->n_voi = u->n_out = u->n_rej = 0;
+    u->submap_uninit = true; u->stack_count = 0;
+    return ERASOR_OK;
+}
+
 erasor_handle_t erasor_updater_erasor(erasor_updater_t u) { return u ? u->er : nullptr; }
 
 // OfflineMapUpdater::callback_node (OfflineMapUpdater.cpp:203-330)

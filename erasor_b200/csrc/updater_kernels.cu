@@ -208,7 +208,7 @@ __global__ void k_vox_keys(const float4* __restrict__ in, uint32_t n, const VoxG
 }
 
 // ---- global stable LSD radix sort of (key, idx) pairs: 8-bit digits, one warp per 4096-element segment -------------
-constexpr int RS_SEG = 4096;
+constexpr int RS_SEG = 1024;   // one warp per segment: small segments = many warps in flight (the walk is latency-bound)
 __global__ void __launch_bounds__(32) k_rs_hist(const uint32_t* __restrict__ key, uint32_t n, int shift, uint32_t nseg, uint32_t* __restrict__ cnt /*[256][nseg]*/) {
     __shared__ uint32_t s_c[256];
     const int lane = threadIdx.x;

@@ -172,6 +172,8 @@ typedef struct {
 int  erasor_updater_create(const erasor_updater_params_t* up, const erasor_params_t* ep, const float* initial_map_xyzi, size_t n_map,
                            int device, erasor_updater_t* out);
 void erasor_updater_destroy(erasor_updater_t u);
+/* load_global_map again (:107-167) on a live updater: new initial map, counters reset, device buffers kept */
+int  erasor_updater_reset(erasor_updater_t u, const float* initial_map_xyzi, size_t n_map);
 const char* erasor_updater_last_error(erasor_updater_t u);
 /* replaces OfflineMapUpdater::callback_node(msg) (:203-330): seq = msg->header.seq, odom7 = msg->odom as x y z qx qy qz qw
  * (body -> origin), lidar = msg->lidar in the LIDAR frame.  *processed = 1 when the node was processed (every
