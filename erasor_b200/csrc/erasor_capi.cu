@@ -97,6 +97,7 @@ struct erasor_ctx {
     const float4* cur_map = nullptr;
     const float4* cur_qry = nullptr;
     std::vector<uint64_t> map_off, qry_off;
+    int      desc_mode = -1;                   // mode the uploaded chunk descriptors were built for (-1: none)
 
     // single-frame state machine
     int      stage = 0;                        // 0: nothing, 1: inputs set, 2: compared
@@ -148,7 +149,8 @@ uint32_t choose_chunk(const erasor_ctx* h, size_t total_points, int mode) {
     // Chunk = one CTA of K1 (and one warp of K2 in cloud mode).  Aim at one wave of K1 CTAs (table init / flush amortised).  In cloud mode the dense
     // per-chunk count rows cost 4*(B+1) bytes each, so keep the chunk at >= 5*B points (<= 5 % extra traffic).
     const size_t target = total_points / ((size_t)h->sm_count * 4) + 1;      // one wave of 4 resident CTAs per SM
-    size_t ch = std::max<size_t>(target, mode == 0 ? std::max<size_t>(2048, (size_t)5 * h->B) : (size_t)2048);
+    size_t ch = std::max<size_t>(target, std::max<size_t>(2048, (size_t)5 * h->B));
+    (void)mode;
     ch = std::min<size_t>(ch, 65536);
     ch = (ch + 127) & ~(size_t)127;
     return (uint32_t)ch;
@@ -162,6 +164,12 @@ int prepare_batch(erasor_ctx* h, const uint64_t* map_off, const uint64_t* qry_of
     for (int f = 0; f < F; ++f)
         if (map_off[f + 1] < map_off[f] || qry_off[f + 1] < qry_off[f]) { h->err = "offsets must be non-decreasing"; return ERASOR_E_INVALID; }
     const int B = h->B;
+    // same batch geometry as the previous call (the usual case when a caller streams equally-shaped batches):
+    // the chunk descriptors already on the device are still valid -- skip rebuild, upload and the staging sync
+    if (h->desc_mode == mode && h->F == F && h->map_off.size() == (size_t)F + 1 && h->qry_off.size() == (size_t)F + 1 &&
+        std::equal(map_off, map_off + F + 1, h->map_off.begin()) && std::equal(qry_off, qry_off + F + 1, h->qry_off.begin()))
+        return ERASOR_OK;
+    h->desc_mode = -1;
     h->F = F; h->NM = NM; h->NQ = NQ;
     h->map_off.assign(map_off, map_off + F + 1);
     h->qry_off.assign(qry_off, qry_off + F + 1);
@@ -195,7 +203,8 @@ int prepare_batch(erasor_ctx* h, const uint64_t* map_off, const uint64_t* qry_of
     CK(h->d_frame_off.ensure(sizeof(uint32_t) * foff.size()));
     CK(h->d_bin_map.ensure(sizeof(uint16_t) * std::max<size_t>(NM, 1)));
     CK(h->d_bin_qry.ensure(sizeof(uint16_t) * std::max<size_t>(NQ, 1)));
-    if (mode == 0) CK(h->d_chcnt.ensure(sizeof(uint32_t) * std::max<size_t>(n_chunks, 1) * (B + 1)));
+    CK(h->d_chcnt.ensure(sizeof(uint32_t) * std::max<size_t>(n_chunks, 1) * (B + 1)));
+    CK(h->d_map_sorted.ensure(sizeof(float4) * std::max<size_t>(NM, 1)));
     CK(h->d_zmin.ensure(sizeof(uint32_t) * 2 * (size_t)F * B));
     CK(h->d_zmax.ensure(sizeof(uint32_t) * 2 * (size_t)F * B));
     CK(h->d_cnt.ensure(sizeof(uint32_t) * 2 * (size_t)F * (B + 1)));
@@ -212,7 +221,6 @@ int prepare_batch(erasor_ctx* h, const uint64_t* map_off, const uint64_t* qry_of
     CK(h->d_map_src.ensure(sizeof(uint32_t) * std::max<size_t>(NM, 1)));
     CK(h->d_scratch.ensure((size_t)24 * std::max<size_t>(NM, 1) + 64));
     if (mode == 0) {
-        CK(h->d_map_sorted.ensure(sizeof(float4) * std::max<size_t>(NM, 1)));
         CK(h->d_qry_sorted.ensure(sizeof(float4) * std::max<size_t>(NQ, 1)));
         CK(h->d_qry_src.ensure(sizeof(uint32_t) * std::max<size_t>(NQ, 1)));
         CK(h->d_part.ensure(sizeof(float4) * std::max<size_t>(NM, 1)));
@@ -229,6 +237,7 @@ int prepare_batch(erasor_ctx* h, const uint64_t* map_off, const uint64_t* qry_of
     if (b0) CK(cudaMemcpyAsync(h->d_chunks.p, st, b0, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_chunk_range.p, st + b0, b1, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_frame_off.p, st + b0 + b1, b2, cudaMemcpyHostToDevice, h->stream));
+    h->desc_mode = mode;
     return ERASOR_OK;
 }
 
@@ -262,7 +271,7 @@ int run_k1(erasor_ctx* h, int mode) {
         if (h->n_chunks_map + h->n_chunks_qry) h->launches++;
         CK(launch_k1(h->stream, h->view, h->cur_map, h->cur_qry, h->d_chunks.as<ChunkDesc>(), (int)(h->n_chunks_map + h->n_chunks_qry),
                      h->d_bin_map.as<uint16_t>(), h->d_bin_qry.as<uint16_t>(), h->d_chcnt.as<uint32_t>(), h->d_zmin.as<uint32_t>(),
-                     h->d_zmax.as<uint32_t>(), h->d_cnt.as<uint32_t>(), B, F, mode == 0, h->d_fence.as<unsigned long long>()));
+                     h->d_zmax.as<uint32_t>(), h->d_cnt.as<uint32_t>(), B, F, true, h->d_fence.as<unsigned long long>()));
     }
     return ERASOR_OK;
 }
@@ -294,10 +303,10 @@ int run_compare(erasor_ctx* h, int version, int mode, uint8_t* keep_mask, uint8_
                          h->d_chcnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>() + (size_t)F * (B + 2), h->d_qry_sorted.as<float4>(),
                          h->d_qry_src.as<uint32_t>(), B));
         } else {
+            // mask mode: the same stable scatter, restricted by dst_start to the flagged bins
             if (h->n_chunks_map) h->launches++;
-            CK(launch_k2_gather(h->stream, h->d_chunks.as<ChunkDesc>(), h->n_chunks_map, B, h->d_bin_map.as<uint16_t>(),
-                                h->d_flag_slot.as<uint32_t>(), h->d_frame_rec_base.as<uint32_t>(), h->d_recs.as<FlagRec>(),
-                                h->rec_capacity, h->d_map_src.as<uint32_t>()));
+            CK(launch_k2(h->stream, h->d_chunks.as<ChunkDesc>(), 0u, h->n_chunks_map, F, h->d_bin_map.as<uint16_t>(), h->cur_map,
+                         h->d_chcnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>(), h->d_map_sorted.as<float4>(), h->d_map_src.as<uint32_t>(), B));
         }
     }
     {
@@ -310,7 +319,7 @@ int run_compare(erasor_ctx* h, int version, int mode, uint8_t* keep_mask, uint8_
         CK(cudaStreamWaitEvent(h->stream_b, h->ev_fork, 0));
         CK(cudaStreamWaitEvent(h->stream_c, h->ev_fork, 0));
         CK(launch_k4(h->stream, h->stream_b, h->stream_c, gp, h->d_recs.as<FlagRec>(), h->d_nrecs.as<uint32_t>(), h->rec_capacity,
-                     mode == 0 ? h->d_map_sorted.as<float4>() : nullptr, h->d_map_src.as<uint32_t>(), h->cur_map,
+                     h->d_map_sorted.as<float4>(), h->d_map_src.as<uint32_t>(), h->cur_map,
                      h->d_frame_off.as<uint32_t>(), mode == 0 ? h->d_part.as<float4>() : nullptr, keep_mask, ground_mask,
                      h->d_frame_rej.as<uint32_t>(), h->d_scratch.as<unsigned char>(), h->sm_count, h->d_fence.as<unsigned long long>()));
         CK(cudaEventRecord(h->ev_join_b, h->stream_b));

@@ -21,9 +21,27 @@
 #include "device_types.h"
 #include "kernels.h"
 
+#include <mutex>
+#include <unordered_map>
+
 namespace erasor {
 
 #define FULL_MASK 0xFFFFFFFFu
+
+// cudaFuncSetAttribute costs a few microseconds per call; the dynamic shared-memory ceiling of a kernel only ever has
+// to grow, so remember the largest value set per kernel and skip the call otherwise.
+template <class K>
+static cudaError_t ensure_dyn_smem(K kern, size_t bytes) {
+    static std::mutex mu;
+    static std::unordered_map<const void*, size_t> seen;
+    std::lock_guard<std::mutex> lock(mu);
+    const void* key = reinterpret_cast<const void*>(kern);
+    auto it = seen.find(key);
+    if (it != seen.end() && it->second >= bytes) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) seen[key] = bytes;
+    return e;
+}
 
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
     float4 v;
@@ -206,11 +224,11 @@ cudaError_t launch_k1(cudaStream_t st, const BinTablesView& T, const float4* map
     cudaError_t e;
     if (rows) {
         auto kern = k1_rpod_bin<THREADS, UNROLL, true>;
-        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
         kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence);
     } else {
         auto kern = k1_rpod_bin<THREADS, UNROLL, false>;
-        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
         kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence);
     }
     return cudaGetLastError();
@@ -275,22 +293,6 @@ k3_srt(SrtParams P, int F, const uint32_t* __restrict__ chunk_range /*[2][F+1]*/
     __shared__ uint32_t s_rec_base;
     const int f = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
 
-    // phase 0 (cloud mode only): in-place exclusive prefix of the per-chunk count rows over the frame's chunks;
-    // the per-bin totals themselves were accumulated by K1 into cnt[]
-    if (P.scatter_mode == 0) {
-        for (int c = 0; c < 2; ++c) {
-            const uint32_t c0 = chunk_range[c * (F + 1) + f], c1 = chunk_range[c * (F + 1) + f + 1];
-            for (int b = tid; b <= B; b += nt) {
-                uint32_t run = 0;
-                for (uint32_t k = c0; k < c1; ++k) {
-                    uint32_t* p = ch_cnt + (size_t)k * (B + 1) + b;
-                    const uint32_t v = *p;
-                    *p = run;
-                    run += v;
-                }
-            }
-        }
-    }
     const uint32_t* cm = cnt + ((size_t)0 * F + f) * (B + 1);
     const uint32_t* cq = cnt + ((size_t)1 * F + f) * (B + 1);
     const uint32_t* mnm = zmin + ((size_t)0 * F + f) * B; const uint32_t* mxm = zmax + ((size_t)0 * F + f) * B;
@@ -381,6 +383,24 @@ k3_srt(SrtParams P, int F, const uint32_t* __restrict__ chunk_range /*[2][F+1]*/
     }
     __syncthreads();
 
+    // in-place exclusive prefix of the per-chunk count rows over the frame's chunks, for the bins K2 will scatter:
+    // every bin of both clouds in cloud mode, the flagged map bins only in mask mode (the per-bin totals themselves
+    // were accumulated by K1 into cnt[])
+    for (int c = 0; c < 2; ++c) {
+        if (c == 1 && P.scatter_mode != 0) break;
+        const uint32_t c0 = chunk_range[c * (F + 1) + f], c1 = chunk_range[c * (F + 1) + f + 1];
+        for (int b = tid; b <= B; b += nt) {
+            const bool take = (P.scatter_mode == 0) || (b < B && (act_out[b] & 0x0F) == ACT_FLAG);
+            if (!take) continue;
+            uint32_t run = 0;
+            for (uint32_t k = c0; k < c1; ++k) {
+                uint32_t* p = ch_cnt + (size_t)k * (B + 1) + b;
+                const uint32_t v = *p;
+                *p = run;
+                run += v;
+            }
+        }
+    }
     // flagged bins, in bin order
     uint32_t* slot_out = flag_slot + (size_t)f * B;
     for (int b = tid; b < B; b += nt) s_sz[b] = ((act_out[b] & 0x0F) == ACT_FLAG) ? 1u : 0u;
@@ -439,7 +459,7 @@ cudaError_t launch_k3(cudaStream_t st, const SrtParams& P, int F, const uint32_t
                       uint8_t* status, uint8_t* action, uint32_t* flag_slot, uint32_t* n_flagged, uint32_t* frame_rec_base,
                       FlagRec* recs, uint32_t* n_recs, uint32_t rec_capacity) {
     const size_t smem = k3_smem_bytes(P.B);
-    cudaError_t e = cudaFuncSetAttribute(k3_srt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = ensure_dyn_smem(k3_srt, smem);
     if (e != cudaSuccess) return e;
     k3_srt<<<F, 1024, smem, st>>>(P, F, chunk_range, ch_cnt, zmin, zmax, frame_off, cnt, dst_start, status, action,
                                   flag_slot, n_flagged, frame_rec_base, recs, n_recs, rec_capacity);
@@ -568,12 +588,12 @@ cudaError_t launch_k2(cudaStream_t st, const ChunkDesc* chunks, uint32_t chunk_b
     cudaError_t e;
     if (smem_mw <= 200 * 1024) {
         auto kern = k2_scatter_mw<W>;
-        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mw)) != cudaSuccess) return e;
+        if ((e = ensure_dyn_smem(kern, smem_mw)) != cudaSuccess) return e;
         kern<<<n_chunks, W * 32, smem_mw, st>>>(chunks, chunk_base, bin_ids, pts, ch_cnt, dst_start, out_pts, out_src, B);
         return cudaGetLastError();
     }
     const size_t smem = sizeof(uint32_t) * ((size_t)B + 1);
-    if ((e = cudaFuncSetAttribute(k2_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    if ((e = ensure_dyn_smem(k2_scatter, smem)) != cudaSuccess) return e;
     k2_scatter<<<n_chunks, 32, smem, st>>>(chunks, chunk_base, F, bin_ids, pts, ch_cnt, dst_start, out_pts, out_src, B);
     return cudaGetLastError();
 }
@@ -1182,7 +1202,7 @@ static cudaError_t launch_k4_class(cudaStream_t st, const GpfParams& P, FlagRec*
     const uint32_t slice = (smem_bytes / NG) & ~15u;
     const uint32_t cap = (slice - 32) / 21u;
     auto kern = k4_rgpf<THREADS, G>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaError_t e = ensure_dyn_smem(kern, smem_bytes);
     if (e != cudaSuccess) return e;
     kern<<<grid, THREADS, smem_bytes, st>>>(P, recs, n_recs, rec_capacity, n_lo, n_hi, sorted_pts, sorted_src, in_pts, frame_off,
                                             part_pts, keep_mask, ground_mask, frame_rejected, gscratch, cap, slice, fence);
@@ -1351,7 +1371,7 @@ cudaError_t launch_k4b(cudaStream_t st, float leaf, int B, const FlagRec* recs, 
     constexpr uint32_t SMEM_BYTES = 72 * 1024;
     // 16 n (xyzi) + 4 n (key) + 4 (n+1) (voxel starts) + 4 np2 (<= 8n) <= 32 n + 16
     const uint32_t cap = (SMEM_BYTES - 64) / 32u;
-    cudaError_t e = cudaFuncSetAttribute(k4b_voxelize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaError_t e = ensure_dyn_smem(k4b_voxelize, SMEM_BYTES);
     if (e != cudaSuccess) return e;
     k4b_voxelize<<<grid, K4B_THREADS, SMEM_BYTES, st>>>(leaf, B, recs, n_recs, rec_capacity, cnt, dst_start, qry_sorted, part_pts,
                                                        vox_pts, vox_cnt, vox_start, gscratch, cap);
