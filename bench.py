@@ -294,16 +294,15 @@ def run_ours(args):
     # The path's one exchange (north_star): every rank folds its frames' keep-masks onto the global map
     # (a point survives if no frame rejected it) and the per-rank masks are all-gathered over NVLink.
     NG = len(map_world)
-    gidx = torch.from_numpy(np.concatenate(idxs).astype(np.int64)).to(dev)
+    gidx = torch.from_numpy(np.concatenate(idxs).astype(np.uint32).view(np.int32)).to(dev)      # uint32 indices for the fold kernel
     keep_g = torch.ones(NG, dtype=torch.uint8, device=dev)
     final_keep = [None]
 
     from erasor_b200 import dist as edist
 
     def exchange(keep_dev):
+        h.fold_keep_masks(keep_dev.data_ptr(), gidx.data_ptr(), NM, keep_g.data_ptr(), NG)   # library kernel on the handle's stream
         with torch.cuda.stream(xs):
-            keep_g.fill_(1)
-            keep_g.scatter_reduce_(0, gidx, keep_dev, reduce="amin")     # == edist.fold_masks, buffers reused
             final_keep[0] = edist.allgather_and(keep_g)                   # the single NCCL collective (no-op at N=1)
 
     def step_resident(i):

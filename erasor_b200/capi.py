@@ -25,7 +25,7 @@ EXPORTS = [
     "erasor_create", "erasor_destroy", "erasor_last_error", "erasor_abi_version", "erasor_stream", "erasor_synchronize",
     "erasor_set_inputs", "erasor_compare", "erasor_get_output_sizes", "erasor_get_static_estimate", "erasor_get_outliers",
     "erasor_get_max_range", "erasor_get_bins", "erasor_get_status", "erasor_get_planes", "erasor_get_static_mask",
-    "erasor_get_fence_counts", "erasor_process_frames", "erasor_get_frame_stats", "erasor_kernel_launch_count",
+    "erasor_get_fence_counts", "erasor_process_frames", "erasor_fold_keep_masks", "erasor_get_frame_stats", "erasor_kernel_launch_count",
     "erasor_get_kernel_time_ms", "erasor_reset_kernel_times", "erasor_get_rgpf_profile",
     "erasor_updater_create", "erasor_updater_destroy", "erasor_updater_reset", "erasor_updater_last_error", "erasor_updater_process_node",
     "erasor_updater_map_size", "erasor_updater_get_cloud", "erasor_updater_save_static_map", "erasor_updater_voxelize",
@@ -78,6 +78,7 @@ def _load():
     L.erasor_get_static_mask.argtypes = [c_void_p, POINTER(c_uint8), POINTER(c_uint8)]
     L.erasor_get_fence_counts.argtypes = [c_void_p, POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint64)]
     L.erasor_process_frames.argtypes = [c_void_p, c_void_p, POINTER(c_uint64), c_void_p, POINTER(c_uint64), c_int, c_void_p, c_int]
+    L.erasor_fold_keep_masks.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t]
     L.erasor_get_frame_stats.argtypes = [c_void_p, POINTER(c_uint32), POINTER(c_uint32)]
     L.erasor_kernel_launch_count.restype = c_uint64
     L.erasor_kernel_launch_count.argtypes = [c_void_p]
@@ -268,6 +269,10 @@ class Handle:
         self._ck(self.L.erasor_process_frames(self.h, c_void_p(map_ptr), mo.ctypes.data_as(POINTER(c_uint64)), c_void_p(query_ptr),
                                               qo.ctypes.data_as(POINTER(c_uint64)), F, c_void_p(keep_ptr), ptr_kind))
         self.n_frames = F
+
+    def fold_keep_masks(self, keep_ptr: int, voi_index_ptr: int, n: int, global_keep_ptr: int, n_global: int):
+        """device pointers; asynchronous on the handle's stream"""
+        self._ck(self.L.erasor_fold_keep_masks(self.h, c_void_p(keep_ptr), c_void_p(voi_index_ptr), n, c_void_p(global_keep_ptr), n_global))
 
     def frame_stats(self):
         F = self.n_frames

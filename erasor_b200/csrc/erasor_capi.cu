@@ -668,6 +668,17 @@ int erasor_process_frames(erasor_handle_t h, const float* map_xyzi, const uint64
     return ERASOR_OK;
 }
 
+// Multi-GPU exchange helper: fold the per-frame keep masks of erasor_process_frames onto the global
+// map (global_keep[voi_index[i]] = 0 where keep[i] == 0, everything else 1).  All pointers are DEVICE pointers; runs on
+// the handle's stream, asynchronously -- order your collective after erasor_stream(h).
+int erasor_fold_keep_masks(erasor_handle_t h, const uint8_t* keep_mask, const uint32_t* voi_index, size_t n, uint8_t* global_keep, size_t n_global) {
+    if (!h || !global_keep || (n && (!keep_mask || !voi_index))) { if (h) h->err = "null argument"; return ERASOR_E_INVALID; }
+    CK(cudaSetDevice(h->device));
+    h->launches++;
+    CK(launch_fold_keep(h->stream, keep_mask, voi_index, n, global_keep, n_global));
+    return ERASOR_OK;
+}
+
 int erasor_get_frame_stats(erasor_handle_t h, uint32_t* n_flagged_bins, uint32_t* n_rejected_points) {
     if (!h) return ERASOR_E_INVALID;
     if (h->F <= 0) { h->err = "no batch has run"; return ERASOR_E_STATE; }

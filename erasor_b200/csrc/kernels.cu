@@ -1513,4 +1513,17 @@ cudaError_t launch_init_tables(cudaStream_t st, uint32_t* zmin, uint32_t* zmax, 
     return cudaGetLastError();
 }
 
+// fold per-frame keep masks onto the global map: a map point survives unless some frame rejected it.
+// Only zeros are written, so concurrent writers need no atomics.
+__global__ void k_fold_keep(const uint8_t* __restrict__ keep, const uint32_t* __restrict__ voi_index, size_t n, uint8_t* __restrict__ global_keep) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && keep[i] == 0) global_keep[voi_index[i]] = 0;
+}
+cudaError_t launch_fold_keep(cudaStream_t st, const uint8_t* keep, const uint32_t* voi_index, size_t n, uint8_t* global_keep, size_t n_global) {
+    cudaError_t e = cudaMemsetAsync(global_keep, 1, n_global, st);
+    if (e != cudaSuccess || n == 0) return e;
+    k_fold_keep<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keep, voi_index, n, global_keep);
+    return cudaGetLastError();
+}
+
 }  // namespace erasor

@@ -57,4 +57,6 @@ cudaError_t launch_k5(cudaStream_t st, int B, int version, int skip_voxelize, co
                       const float4* part_pts, const float4* vox_pts, float4* arranged, float4* map_rej, float4* curr_rej,
                       CopyJob* jobs, uint32_t* out_sizes, uint32_t* tmp, int copy_grid);
 
+cudaError_t launch_fold_keep(cudaStream_t st, const uint8_t* keep, const uint32_t* voi_index, size_t n, uint8_t* global_keep, size_t n_global);
+
 }  // namespace erasor

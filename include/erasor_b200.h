@@ -135,6 +135,10 @@ int erasor_get_fence_counts(erasor_handle_t h, uint64_t* negzero_points, uint64_
 int erasor_process_frames(erasor_handle_t h, const float* map_xyzi, const uint64_t* map_offsets,
                           const float* query_xyzi, const uint64_t* query_offsets, int n_frames,
                           uint8_t* keep_mask, int ptr_kind);
+/* Multi-GPU exchange helper: fold the per-frame keep masks onto the global map (a point survives unless some frame
+ * rejected it): global_keep[] = 1, then global_keep[voi_index[i]] = 0 where keep_mask[i] == 0.  DEVICE pointers; asynchronous
+ * on the handle's stream (erasor_stream).  The all-gather of the folded masks is the path's single collective. */
+int erasor_fold_keep_masks(erasor_handle_t h, const uint8_t* keep_mask, const uint32_t* voi_index, size_t n, uint8_t* global_keep, size_t n_global);
 /* per-frame counters of the last erasor_process_frames: flagged bins and rejected points (host arrays of n_frames) */
 int erasor_get_frame_stats(erasor_handle_t h, uint32_t* n_flagged_bins, uint32_t* n_rejected_points);
 

@@ -171,3 +171,79 @@ def test_v3_with_in_bin_voxelization(capi, oracle_mod, small_workload, name):
         ocmp, _ = o.cloud(o.COMPLEMENT)
         assert np.array_equal(cmp_.view(np.uint32), ocmp.view(np.uint32))
         h.close()
+
+
+def test_fold_keep_masks(capi):
+    """The library's fold kernel (multi-GPU exchange helper) against the reference fold of erasor_b200/dist.py."""
+    import torch
+    from erasor_b200 import dist as D
+    p = P.preset("seq_05").replace(skip_voxelize=1)
+    h = capi.Handle(p)
+    g = torch.Generator().manual_seed(0)
+    n_global, n = 100000, 250000
+    idx = torch.randint(0, n_global, (n,), generator=g)
+    keep = (torch.rand(n, generator=g) > 0.05).to(torch.uint8)
+    expect = D.fold_masks(n_global, [idx], [keep]).numpy()
+    d_idx = idx.to(torch.int32).cuda()
+    d_keep = keep.cuda()
+    d_out = torch.zeros(n_global, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    h.fold_keep_masks(d_keep.data_ptr(), d_idx.data_ptr(), n, d_out.data_ptr(), n_global)
+    h.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), expect)
+    h.close()
+
+
+def test_full_size_dense_voi_properties(capi, oracle_mod, small_workload):
+    """BASELINE.json config 4 (large_scale_05.yaml geometry, ~50 M-point VoI): too big for the oracle, so the CUDA path is
+    checked through size-independent properties -- every point accounted for, the per-bin tables equal an independent
+    torch reduction over the returned bin ids, a 300 k-point sample of bin ids equals the oracle's (the bin of a point
+    does not depend on its neighbours), and the keep mask only ever clears points of flagged bins."""
+    import torch
+    p = P.preset("large_scale_05").replace(skip_voxelize=1)
+    base, q, _, _ = small_workload["frames"][2]
+    base = base[(base[:, 0].astype(np.float64) ** 2 + base[:, 1].astype(np.float64) ** 2) < 82.0 ** 2]
+    reps = int(np.ceil(50_000_000 / len(base)))
+    g = torch.Generator(device="cuda").manual_seed(5)
+    tb = torch.from_numpy(base).cuda()
+    M = tb.repeat(reps, 1)
+    M[:, :3] += (torch.rand((M.shape[0], 3), device="cuda", generator=g) - 0.5) * torch.tensor([0.19, 0.19, 0.02], device="cuda")
+    N = M.shape[0]
+    assert N >= 50_000_000
+    Q = torch.from_numpy(q).cuda()
+    h = capi.Handle(p)
+    h.set_inputs_device(M.data_ptr(), N, Q.data_ptr(), len(q))
+    bop, mn, mx, cnt = h.get_bins(0)
+    binned = bop >= 0
+    assert int(cnt.sum()) == int(binned.sum())                                    # N_m == sum |bin| + |complement|
+    B = p.num_bins
+    tb_ids = torch.from_numpy(bop).cuda().long()
+    sel = tb_ids >= 0
+    z = M[:, 2]
+    t_cnt = torch.bincount(tb_ids[sel], minlength=B)
+    assert torch.equal(t_cnt.cpu(), torch.from_numpy(cnt.astype(np.int64)))
+    t_mx = torch.full((B,), -float("inf"), device="cuda").scatter_reduce_(0, tb_ids[sel], z[sel], reduce="amax")
+    t_mn = torch.full((B,), float("inf"), device="cuda").scatter_reduce_(0, tb_ids[sel], z[sel], reduce="amin")
+    occ = cnt > 0
+    assert np.array_equal(t_mx.cpu().numpy()[occ], mx[occ]) and np.array_equal(t_mn.cpu().numpy()[occ], mn[occ])
+    # sample against the oracle
+    pick = torch.randperm(N, device="cuda", generator=g)[:300000]
+    sample = M[pick].cpu().numpy()
+    o = oracle_mod.Oracle(p)
+    o.run(sample, q[:10])
+    assert np.array_equal(o.bin_of_point(0), bop[pick.cpu().numpy()])
+    # the whole path at full size: mask mode, one frame
+    keep = torch.empty(N, dtype=torch.uint8, device="cuda")
+    mo = np.array([0, N], dtype=np.uint64)
+    qo = np.array([0, len(q)], dtype=np.uint64)
+    h.reset_kernel_times(True)
+    h.process_frames_ptr(M.data_ptr(), mo, Q.data_ptr(), qo, keep.data_ptr(), capi.PTR_DEVICE)
+    k1_ms, k1_n = h.kernel_time_ms(1)
+    nf, nr = h.frame_stats()
+    rejected = (keep == 0)
+    assert int(rejected.sum().item()) == int(nr[0])
+    assert nf[0] > 0 and nr[0] > 0
+    assert bool((tb_ids[rejected] >= 0).all().item())                              # only binned points can be rejected
+    print(f"[full size] N={N} K1 {k1_ms / max(1, k1_n):.3f} ms -> {16 * (N + len(q)) / (k1_ms / max(1, k1_n) * 1e-3) / 1e9:.0f} GB/s, "
+          f"flagged bins {int(nf[0])}, rejected {int(nr[0])}")
+    h.close()
