@@ -53,7 +53,7 @@ struct FlagRec {
     uint32_t n_seeds;
     uint32_t n_empty_fits;
     uint32_t n_ground_final;
-    uint32_t cursor;           // K2g append cursor (mask mode)
+    uint32_t cursor;           // reserved
     uint32_t pad_;
     double   lpr_height;
     double   normal_d[kMaxIter][4];

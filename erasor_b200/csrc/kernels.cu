@@ -5,8 +5,8 @@
 //   K3  k3_srt          per-bin totals, Scan Ratio Test, status / action codes, v3 neighbour pass,
 //                       scatter offsets, flagged-bin work list
 //                       (compare_vois_and_revert_ground[_w_block], erasor.cpp:346-427, 448-563, 573-595)
-//   K2  k2_scatter      stable counting-sort scatter of points into bin order (the per-bin
-//                       pcl::PointCloud push_back, erasor.cpp:89) -- all bins or flagged bins only
+//   K2  k2_scatter[_mw] stable counting-sort scatter of points into bin order (the per-bin
+//                       pcl::PointCloud push_back, erasor.cpp:89) -- all bins (cloud mode) or flagged bins only (mask mode)
 //   K4  k4_rgpf         Region-wise Ground Plane Fitting per flagged bin
 //                       (extract_ground / extract_initial_seeds_ / estimate_plane_, erasor.cpp:183-294)
 //   K5  k5_plan/k5_copy output assembly in the reference's order (r_pod2pc, get_static_estimate,
@@ -598,38 +598,6 @@ cudaError_t launch_k2(cudaStream_t st, const ChunkDesc* chunks, uint32_t chunk_b
     return cudaGetLastError();
 }
 
-// K2g (mask mode): append the source index of every map point that lies in a flagged bin to that bin's list, in
-// arbitrary order (one returning atomic per flagged point; flagged points are a few per cent).  K4 restores the
-// source order with a bitonic sort of the indices, so no per-chunk prefix table is needed in this mode.
-__global__ void __launch_bounds__(256)
-k2_gather_flagged(const ChunkDesc* __restrict__ chunks, int B, const uint16_t* __restrict__ bin_ids,
-                  const uint32_t* __restrict__ flag_slot /*[F][B]*/, const uint32_t* __restrict__ frame_rec_base /*[F]*/,
-                  FlagRec* __restrict__ recs, uint32_t rec_capacity, uint32_t* __restrict__ out_src) {
-    const ChunkDesc cd = chunks[blockIdx.x];
-    const uint32_t* slots = flag_slot + (size_t)cd.frame * B;
-    const uint32_t rbase = frame_rec_base[cd.frame];
-    const uint32_t local0 = cd.begin - cd.frame_begin;
-    for (uint32_t i = threadIdx.x; i < cd.len; i += 256) {
-        const uint16_t id = bin_ids[cd.begin + i];
-        if (id == kNoBin16) continue;
-        const uint32_t slot = __ldg(&slots[id]);
-        if (slot == kSkip) continue;
-        const uint32_t ri = rbase + slot;
-        if (ri >= rec_capacity) continue;
-        FlagRec& rc = recs[ri];
-        const uint32_t pos = atomicAdd(&rc.cursor, 1u);
-        out_src[rc.src_begin + pos] = local0 + i;
-    }
-}
-
-cudaError_t launch_k2_gather(cudaStream_t st, const ChunkDesc* chunks, uint32_t n_chunks_map, int B, const uint16_t* bin_ids,
-                             const uint32_t* flag_slot, const uint32_t* frame_rec_base, FlagRec* recs, uint32_t rec_capacity,
-                             uint32_t* out_src) {
-    if (n_chunks_map == 0) return cudaSuccess;
-    k2_gather_flagged<<<n_chunks_map, 256, 0, st>>>(chunks, B, bin_ids, flag_slot, frame_rec_base, recs, rec_capacity, out_src);
-    return cudaGetLastError();
-}
-
 // ============================================================================================
 // K4  R-GPF
 // ============================================================================================
@@ -964,27 +932,10 @@ __device__ __forceinline__ void k4_process_bin(const GpfParams& P, FlagRec& rc, 
     uint32_t prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define K4_TICK(slot) do { const long long t_now__ = clock64(); prof[slot] += (uint32_t)(t_now__ - t_prev); t_prev = t_now__; } while (0)
 
-    if (sorted_pts) {
-        // cloud mode: K2 already placed the bin's points contiguously in source order
-        for (uint32_t i = tid; i < n; i += G) {
-            const float4 p = sorted_pts[src_begin + i];
-            X[i] = p.x; Y[i] = p.y; Z[i] = p.z; ORD[i] = i;
-        }
-    } else {
-        // mask mode: K2g appended the bin's source indices in arbitrary order; restore source order first
-        for (uint32_t i = tid; i < n; i += G) ORD[i] = sorted_src[src_begin + i];
-        group_sync<G>();
-        const uint32_t flen = frame_off[rc.frame + 1] - fbase;
-        const int idx_bits = 32 - __clz(max(flen, 2u) - 1u);
-        const uint32_t* srt = group_radix_sort<G>(ORD, TMP, n, cnt_scratch, sh.warp, idx_bits, [](uint32_t v) { return v; });
-        for (uint32_t i = tid; i < n; i += G) {
-            const uint32_t s = srt[i];
-            sorted_src[src_begin + i] = s;
-            const float4 p = in_pts[fbase + s];
-            X[i] = p.x; Y[i] = p.y; Z[i] = p.z;
-        }
-        group_sync<G>();
-        for (uint32_t i = tid; i < n; i += G) ORD[i] = i;
+    // K2 placed the bin's points contiguously in source order (all bins in cloud mode, flagged bins only in mask mode)
+    for (uint32_t i = tid; i < n; i += G) {
+        const float4 p = sorted_pts[src_begin + i];
+        X[i] = p.x; Y[i] = p.y; Z[i] = p.z; ORD[i] = i;
     }
     group_sync<G>();
     K4_TICK(0);

@@ -31,17 +31,13 @@ cudaError_t launch_k3(cudaStream_t st, const SrtParams& P, int F, const uint32_t
                       uint8_t* status, uint8_t* action, uint32_t* flag_slot, uint32_t* n_flagged, uint32_t* frame_rec_base,
                       FlagRec* recs, uint32_t* n_recs, uint32_t rec_capacity);
 
-cudaError_t launch_k2_gather(cudaStream_t st, const ChunkDesc* chunks, uint32_t n_chunks_map, int B, const uint16_t* bin_ids,
-                             const uint32_t* flag_slot, const uint32_t* frame_rec_base, FlagRec* recs, uint32_t rec_capacity,
-                             uint32_t* out_src);
-
 cudaError_t launch_k2(cudaStream_t st, const ChunkDesc* chunks, uint32_t chunk_base, uint32_t n_chunks, int F,
                       const uint16_t* bin_ids, const float4* pts, const uint32_t* ch_cnt, const uint32_t* dst_start,
                       float4* out_pts, uint32_t* out_src, int B);
 
 int k4_num_launches();
-// sorted_pts != nullptr: cloud mode (bins contiguous in source order, from K2).  sorted_pts == nullptr: mask mode
-// (sorted_src holds K2g's unordered source indices; points are gathered from in_pts).
+// sorted_pts / sorted_src: K2's output (bins contiguous in source order + source index of every slot); in_pts is unused
+// since K2 also serves mask mode, kept in the signature for ABI stability of the launch wrapper.
 cudaError_t launch_k4(cudaStream_t st, cudaStream_t st_b, cudaStream_t st_c, const GpfParams& P, FlagRec* recs, const uint32_t* n_recs,
                       uint32_t rec_capacity, const float4* sorted_pts, uint32_t* sorted_src, const float4* in_pts, const uint32_t* frame_off,
                       float4* part_pts, uint8_t* keep_mask, uint8_t* ground_mask, uint32_t* frame_rejected, unsigned char* gscratch,
