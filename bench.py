@@ -34,6 +34,7 @@ import numpy as np  # noqa: E402
 
 FRAMES_PER_PASS = 20          # 161 nodes / removal_interval 8 (config/seq_05.yaml)
 N_INPUT_COPIES = 4            # rotate input copies so that consecutive steps never find their clouds in the 126 MB L2
+K1_DRAM_TRAFFIC_BYTES = 56.916e6 + 1.876e6   # ncu --set full, one launch of k1_rpod_bin on the default workload (profiles/r01)
 CACHE_DIR = os.environ.get("ERASOR_B200_CACHE", "/tmp/erasor_b200_cache")
 
 
@@ -142,7 +143,7 @@ def clocks_sampler_start(gpu_index: int):
     q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     try:
-        return subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(gpu_index)],
+        return subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "10", "-i", str(gpu_index)],
                                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
     except Exception:
         return None
@@ -339,6 +340,12 @@ def run_ours(args):
         return float(t.item()), h.kernel_launch_count() - l0
 
     sampler = clocks_sampler_start(local) if rank == 0 else None
+    if sampler is not None:
+        t_busy = time.perf_counter()
+        i_busy = 0
+        while time.perf_counter() - t_busy < 0.3:        # untimed: gives nvidia-smi (10 ms period) samples under this load
+            step_resident(i_busy)
+            i_busy += 1
     # --- value: resident inputs; K1 timed per launch with CUDA events on the library's stream ---
     h.reset_kernel_times(True)
     ms_res, launches = timed(step_resident, args.steps, args.warmup)
@@ -400,7 +407,9 @@ def run_ours(args):
                     "note": "pinned host clouds -> erasor_process_frames(PTR_HOST) -> pinned host keep mask"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k1_rpod_bin", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": K1_DRAM_TRAFFIC_BYTES if (world == 1 and args.frames == FRAMES_PER_PASS) else None,
+                         "traffic_source": "profiles/r01/ncu_raw_k1c.csv: dram__bytes_read.sum + dram__bytes_write.sum of one k1_rpod_bin launch on this workload",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": k1_bytes, "avg_launch_ms": k1_avg_ms, "launches_timed": int(k1_n),
                          "ms_per_step_with_event_timing": ms_res / args.steps},
             "cpu_baseline": {"value": nfr / cpu_dt, "unit": "scans/s", "cores": 1, "kind": "port",

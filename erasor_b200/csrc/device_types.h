@@ -54,7 +54,7 @@ struct FlagRec {
     uint32_t n_empty_fits;
     uint32_t n_ground_final;
     uint32_t cursor;           // reserved
-    uint32_t pad_;
+    uint32_t n_rejected;       // points handed to map_rejected (0 when gf_iter == 0: the reference fills no outliers then)
     double   lpr_height;
     double   normal_d[kMaxIter][4];
     uint32_t n_ground[kMaxIter];

@@ -439,7 +439,7 @@ k3_srt(SrtParams P, int F, const uint32_t* __restrict__ chunk_range /*[2][F+1]*/
                 FlagRec& rc = recs[ri];
                 rc.frame = f; rc.bin = b; rc.slot = slot; rc.n_points = cm[b];
                 rc.src_begin = frame_off[f] + s_sz[b];
-                rc.n_seeds = 0; rc.n_empty_fits = 0; rc.n_ground_final = 0; rc.lpr_height = 0.0; rc.cursor = 0u;
+                rc.n_seeds = 0; rc.n_empty_fits = 0; rc.n_ground_final = 0; rc.lpr_height = 0.0; rc.cursor = 0u; rc.n_rejected = 0u;
             }
         }
     }
@@ -1079,16 +1079,16 @@ __device__ __forceinline__ void k4_process_bin(const GpfParams& P, FlagRec& rc, 
         group_sync<G>();
     }
     if (tid == 0) {
-        rc.n_ground_final = m; rc.n_empty_fits = n_empty;
+        rc.n_ground_final = m; rc.n_empty_fits = n_empty; rc.n_rejected = (P.iters > 0) ? n - m : 0u;
         if (n_empty) atomicAdd(&fence[1], (unsigned long long)n_empty);
-        if (frame_rejected && P.iters > 0) atomicAdd(&frame_rejected[rc.frame], n - m);
+        if (frame_rejected) atomicAdd(&frame_rejected[rc.frame], n - m);
     }
 
     // ---- outputs ----
     if (keep_mask || ground_mask) {
         for (uint32_t i = tid; i < n; i += G) {
             const uint32_t s = sorted_src[src_begin + i];
-            if (keep_mask && !FLG[i] && P.iters > 0) keep_mask[fbase + s] = 0;
+            if (keep_mask && !FLG[i]) keep_mask[fbase + s] = 0;      // not in the selected bin any more (gf_iter == 0: dropped silently)
             if (ground_mask && FLG[i]) ground_mask[fbase + s] = 1;
         }
     }
@@ -1367,7 +1367,7 @@ k5_plan(int B, int version, int skip_voxelize, const uint32_t* __restrict__ cnt 
     }
     for (uint32_t s = tid; s < (uint32_t)B; s += nt) {
         gv[s] = (s < nflag) ? recs[s].n_ground_final : 0u;
-        rj[s] = (s < nflag) ? recs[s].n_points - recs[s].n_ground_final : 0u;
+        rj[s] = (s < nflag) ? recs[s].n_rejected : 0u;
     }
     __syncthreads();
     const uint32_t sel_total = block_excl_scan(sel, sel, B, s_part);
@@ -1402,7 +1402,7 @@ k5_plan(int B, int version, int skip_voxelize, const uint32_t* __restrict__ cnt 
         if (s < nflag) {
             const FlagRec& rc = recs[s];
             jg = CopyJob{part_pts + rc.src_begin, arranged + sel_total + gv[s], rc.n_ground_final, 0u};
-            jr = CopyJob{part_pts + rc.src_begin + rc.n_ground_final, map_rej + rj[s], rc.n_points - rc.n_ground_final, 0u};
+            jr = CopyJob{part_pts + rc.src_begin + rc.n_ground_final, map_rej + rj[s], rc.n_rejected, 0u};
         }
         jobs[2 * B + s] = jg; jobs[3 * B + s] = jr;
     }

@@ -247,3 +247,57 @@ def test_full_size_dense_voi_properties(capi, oracle_mod, small_workload):
     print(f"[full size] N={N} K1 {k1_ms / max(1, k1_n):.3f} ms -> {16 * (N + len(q)) / (k1_ms / max(1, k1_n) * 1e-3) / 1e9:.0f} GB/s, "
           f"flagged bins {int(nf[0])}, rejected {int(nr[0])}")
     h.close()
+
+
+@pytest.mark.parametrize("overrides", [
+    dict(gf_iter=1), dict(gf_iter=0), dict(minimum_num_pts=0), dict(minimum_num_pts=1, num_lowest_pts=0, gf_num_lpr=1),
+    dict(num_lowest_pts=1000000), dict(scan_ratio_threshold=0.9), dict(cov_mode=1), dict(gf_dist_thr=0.0), dict(gf_th_seeds_height=-5.0),
+])
+def test_parameter_edge_cases(capi, oracle_mod, small_workload, overrides):
+    """Parameter corners of R-GPF / SRT: single and zero plane-fit iterations, no minimum point count, LPR windows that
+    fall off the bin, thresholds that flag almost every bin, the PCL >= 1.11 covariance, seed windows that select nothing
+    (the App. B-3 empty-fit fence)."""
+    p = P.preset("seq_05").replace(skip_voxelize=1, **overrides)
+    m, q = _frame(small_workload, 3, p)
+    for version in (3, 2):
+        o = oracle_mod.Oracle(p.replace(version=version))
+        o.run(m, q)
+        h = capi.Handle(p.replace(version=version))
+        h.set_inputs(m, q)
+        h.compare(version)
+        assert np.array_equal(h.get_status(), o.status()[0].astype(np.float32))
+        gp, op = h.get_planes(), o.planes()
+        assert [g["bin"] for g in gp] == [x["bin"] for x in op]
+        for g, x in zip(gp, op):
+            assert np.array_equal(g["normal_d"], x["normal_d"]) and np.array_equal(g["n_ground"], x["n_ground"]), overrides
+        arr, cmp_ = h.get_static_estimate()
+        oarr, _ = o.cloud(o.ARRANGED)
+        assert arr.shape == oarr.shape and np.array_equal(arr.view(np.uint32), oarr.view(np.uint32)), (overrides, version)
+        mr, _ = h.get_outliers()
+        omr, _ = o.cloud(o.MAP_REJECTED)
+        assert mr.shape == omr.shape and np.array_equal(mr.view(np.uint32), omr.view(np.uint32))
+        if overrides.get("gf_th_seeds_height", 0) < 0:
+            assert h.fence_counts()["empty_plane_fits"] > 0 and sum(x["n_empty"] for x in op) > 0
+        h.close()
+
+
+def test_batch_masks_v2_and_ragged(capi, oracle_mod, small_workload):
+    """Mask mode with version 2, frames of very different sizes and an empty frame in the middle."""
+    p = P.preset("seq_00").replace(skip_voxelize=1, version=2)
+    fr = [_frame(small_workload, i, p) for i in (0, 2, 5)]
+    z = np.zeros((0, 4), dtype=np.float32)
+    frames = [fr[0], (z, z), (fr[1][0][:777], fr[1][1]), fr[2], (fr[2][0], z)]
+    mo = np.cumsum([0] + [len(m) for m, _ in frames]).astype(np.uint64)
+    qo = np.cumsum([0] + [len(q) for _, q in frames]).astype(np.uint64)
+    M = np.concatenate([m for m, _ in frames])
+    Q = np.concatenate([q for _, q in frames])
+    h = capi.Handle(p)
+    keep = h.process_frames(M, mo, Q, qo)
+    for f, (m, q) in enumerate(frames):
+        o = oracle_mod.Oracle(p)
+        o.run(m, q)
+        _, rej = o.cloud(o.MAP_REJECTED)
+        okeep = np.ones(len(m), dtype=np.uint8)
+        okeep[rej] = 0
+        assert np.array_equal(keep[int(mo[f]):int(mo[f + 1])], okeep), f"frame {f}"
+    h.close()
