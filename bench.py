@@ -350,6 +350,7 @@ def run_ours(args):
     h.reset_kernel_times(True)
     ms_res, launches = timed(step_resident, args.steps, args.warmup)
     k1_ms, k1_n = h.kernel_time_ms(1)
+    kernel_ms = {name: h.kernel_time_ms(i)[0] / max(1, h.kernel_time_ms(i)[1]) for i, name in ((1, 'k1_rpod_bin'), (2, 'k2_scatter'), (3, 'k3_srt'), (4, 'k4_rgpf_all_classes'))}
     # (the K1 events bracket warm-up launches too; they are the same work, so the per-launch mean is unaffected)
     h.reset_kernel_times(False)
     ms_res_plain, launches = timed(step_resident, args.steps, max(args.warmup, 3))
@@ -411,7 +412,9 @@ def run_ours(args):
                          "traffic_source": "profiles/r01/ncu_raw_k1c.csv: dram__bytes_read.sum + dram__bytes_write.sum of one k1_rpod_bin launch on this workload",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": k1_bytes, "avg_launch_ms": k1_avg_ms, "launches_timed": int(k1_n),
-                         "ms_per_step_with_event_timing": ms_res / args.steps},
+                         "ms_per_step_with_event_timing": ms_res / args.steps,
+                         "avg_ms_per_launch_by_cuda_events": {k: round(v, 5) for k, v in kernel_ms.items()},
+                         "share_of_step": round((k1_ms / max(1, k1_n)) / (ms_res / args.steps), 3)},
             "cpu_baseline": {"value": nfr / cpu_dt, "unit": "scans/s", "cores": 1, "kind": "port",
                              "sample": f"{nfr} frames ({reps} passes over this rank's {F} frames), oracle -O2, one core; "
                                        "reference cannot be compiled here (ROS/PCL/Eigen absent)"},

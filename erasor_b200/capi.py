@@ -262,13 +262,20 @@ class Handle:
         return keep
 
     def process_frames_ptr(self, map_ptr: int, map_offsets: np.ndarray, query_ptr: int, query_offsets: np.ndarray, keep_ptr: int, ptr_kind: int):
-        """Raw-pointer batch call (device tensors or pinned host memory); offsets are host uint64 arrays."""
-        mo = np.ascontiguousarray(map_offsets, dtype=np.uint64)
-        qo = np.ascontiguousarray(query_offsets, dtype=np.uint64)
-        F = len(mo) - 1
-        self._ck(self.L.erasor_process_frames(self.h, c_void_p(map_ptr), mo.ctypes.data_as(POINTER(c_uint64)), c_void_p(query_ptr),
-                                              qo.ctypes.data_as(POINTER(c_uint64)), F, c_void_p(keep_ptr), ptr_kind))
-        self.n_frames = F
+        """Raw-pointer batch call (device tensors or pinned host memory); offsets are host uint64 arrays.
+        The ctypes views of the offset arrays are cached per array object so that a caller streaming equally-shaped
+        batches pays one foreign call per step and nothing else."""
+        key = (id(map_offsets), id(query_offsets))
+        c = getattr(self, "_off_cache", None)
+        if c is None or c[0] != key:
+            mo = np.ascontiguousarray(map_offsets, dtype=np.uint64)
+            qo = np.ascontiguousarray(query_offsets, dtype=np.uint64)
+            c = (key, mo, qo, mo.ctypes.data_as(POINTER(c_uint64)), qo.ctypes.data_as(POINTER(c_uint64)), len(mo) - 1)
+            self._off_cache = c
+        rc = self.L.erasor_process_frames(self.h, map_ptr, c[3], query_ptr, c[4], c[5], keep_ptr, ptr_kind)
+        if rc != OK:
+            self._ck(rc)
+        self.n_frames = c[5]
 
     def fold_keep_masks(self, keep_ptr: int, voi_index_ptr: int, n: int, global_keep_ptr: int, n_global: int):
         """device pointers; asynchronous on the handle's stream"""

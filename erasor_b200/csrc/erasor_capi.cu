@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -22,11 +23,14 @@ namespace {
 
 thread_local std::string g_create_error;
 
+uint64_t g_alloc_epoch = 0;   // bumped on every device (re)allocation: captured graphs hold raw pointers
+
 struct DevBuf {
     void*  p = nullptr;
     size_t cap = 0;
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
+        ++g_alloc_epoch;
         if (p) { cudaFree(p); p = nullptr; cap = 0; }
         size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
@@ -98,6 +102,11 @@ struct erasor_ctx {
     const float4* cur_qry = nullptr;
     std::vector<uint64_t> map_off, qry_off;
     int      desc_mode = -1;                   // mode the uploaded chunk descriptors were built for (-1: none)
+    uint64_t desc_epoch = 0;                   // bumped whenever the descriptors are rebuilt (invalidates cached graphs)
+    struct StepGraph { const void* map; const void* qry; void* keep; int kind; uint64_t epoch, alloc; cudaGraphExec_t exec; };
+    std::vector<StepGraph> graphs;             // captured mask-mode steps, one per (pointers, geometry)
+    bool     use_graphs = true;
+    uint64_t graph_kernel_nodes = 0;
 
     // single-frame state machine
     int      stage = 0;                        // 0: nothing, 1: inputs set, 2: compared
@@ -238,6 +247,7 @@ int prepare_batch(erasor_ctx* h, const uint64_t* map_off, const uint64_t* qry_of
     CK(cudaMemcpyAsync(h->d_chunk_range.p, st + b0, b1, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_frame_off.p, st + b0 + b1, b2, cudaMemcpyHostToDevice, h->stream));
     h->desc_mode = mode;
+    h->desc_epoch++;
     return ERASOR_OK;
 }
 
@@ -373,6 +383,7 @@ int erasor_create(const erasor_params_t* params, int device, erasor_handle_t* ou
     if (device < 0 || device >= ndev) { g_create_error = "bad device index"; return ERASOR_E_INVALID; }
     erasor_ctx* h = new erasor_ctx();
     h->p = p; h->device = device; h->B = (int)Bll;
+    if (const char* ng = std::getenv("ERASOR_B200_NO_GRAPH")) h->use_graphs = !(ng[0] == '1');
     std::string terr;
     if (build_bin_tables(p, h->tables, terr) != 0) { g_create_error = terr; delete h; return ERASOR_E_INVALID; }
     auto fail = [&](const char* what, cudaError_t ce) {
@@ -414,6 +425,8 @@ void erasor_destroy(erasor_handle_t h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     drain_timers(h);
+    for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+    h->graphs.clear();
     DevBuf* bufs[] = {&h->d_ring, &h->d_pos, &h->d_neg, &h->d_map_in, &h->d_qry_in, &h->d_bin_map, &h->d_bin_qry, &h->d_chunks,
                       &h->d_chunk_range, &h->d_frame_off, &h->d_chcnt, &h->d_zmin, &h->d_zmax, &h->d_cnt, &h->d_dst_start, &h->d_status,
                       &h->d_action, &h->d_flag_slot, &h->d_nflag, &h->d_recs, &h->d_nrecs, &h->d_frame_rej, &h->d_map_sorted, &h->d_map_src,
@@ -648,20 +661,75 @@ int erasor_process_frames(erasor_handle_t h, const float* map_xyzi, const uint64
     int rc = prepare_batch(h, map_offsets, query_offsets, n_frames, 1);
     if (rc) return rc;
     if ((h->NM && !map_xyzi) || (h->NQ && !query_xyzi)) { h->err = "null cloud"; return ERASOR_E_INVALID; }
-    {
-        Scope whole(h, 0);
-        if ((rc = stage_inputs(h, map_xyzi, query_xyzi, ptr_kind))) return rc;
+    // the whole step (copies, memset, K1, K3, K2, the three concurrent K4 classes, mask / counter read-back) is a fixed
+    // launch sequence once the batch geometry and the buffers are known: capture it into a CUDA graph the first time and
+    // replay it afterwards (one launch instead of ~15 API calls; the kernels' dependencies become graph edges).
+    auto enqueue = [&]() -> int {
+        int r;
+        if ((r = stage_inputs(h, map_xyzi, query_xyzi, ptr_kind))) return r;
         uint8_t* d_keep = keep_mask;
-        if (ptr_kind != ERASOR_PTR_DEVICE) {
-            CK(h->d_keep.ensure(std::max<size_t>(h->NM, 1)));
-            d_keep = h->d_keep.as<uint8_t>();
-        }
+        if (ptr_kind != ERASOR_PTR_DEVICE) d_keep = h->d_keep.as<uint8_t>();
         if (h->NM) CK(cudaMemsetAsync(d_keep, 1, h->NM, h->stream));
-        if ((rc = run_k1(h, 1))) return rc;
-        if ((rc = run_compare(h, h->p.version, 1, d_keep, nullptr))) return rc;
+        if ((r = run_k1(h, 1))) return r;
+        if ((r = run_compare(h, h->p.version, 1, d_keep, nullptr))) return r;
         if (ptr_kind != ERASOR_PTR_DEVICE && h->NM)
             CK(cudaMemcpyAsync(keep_mask, d_keep, h->NM, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaMemcpyAsync(&h->n_recs_host, h->d_nrecs.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        return ERASOR_OK;
+    };
+    if (ptr_kind != ERASOR_PTR_DEVICE) {
+        CK(h->d_keep.ensure(std::max<size_t>(h->NM, 1)));
+        CK(h->d_map_in.ensure(sizeof(float4) * std::max<size_t>(h->NM, 1)));
+        CK(h->d_qry_in.ensure(sizeof(float4) * std::max<size_t>(h->NQ, 1)));
+    }
+    bool graphable = h->use_graphs && !h->timing;
+    if (graphable && ptr_kind != ERASOR_PTR_DEVICE) {
+        // host buffers must be pinned for copies to be capturable
+        cudaPointerAttributes a{};
+        const void* ptrs[3] = {map_xyzi, query_xyzi, keep_mask};
+        const size_t need[3] = {h->NM, h->NQ, h->NM};
+        for (int i = 0; i < 3 && graphable; ++i) {
+            if (!need[i]) continue;
+            if (cudaPointerGetAttributes(&a, ptrs[i]) != cudaSuccess || a.type != cudaMemoryTypeHost) { graphable = false; cudaGetLastError(); }
+        }
+    }
+    if (graphable) {
+        cudaGraphExec_t exec = nullptr;
+        for (auto& g : h->graphs)
+            if (g.map == map_xyzi && g.qry == query_xyzi && g.keep == keep_mask && g.kind == ptr_kind && g.epoch == h->desc_epoch && g.alloc == g_alloc_epoch) exec = g.exec;
+        if (!exec) {
+            // drop graphs of older geometries, bound the cache
+            for (size_t i = 0; i < h->graphs.size();) {
+                if (h->graphs[i].epoch != h->desc_epoch || h->graphs[i].alloc != g_alloc_epoch || h->graphs.size() > 16) { cudaGraphExecDestroy(h->graphs[i].exec); h->graphs.erase(h->graphs.begin() + i); }
+                else ++i;
+            }
+            cudaGraph_t graph = nullptr;
+            const uint64_t launches_before = h->launches;
+            CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+            rc = enqueue();
+            h->graph_kernel_nodes = h->launches - launches_before;
+            h->launches = launches_before;                              // captured, not launched
+            cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+            if (rc == ERASOR_OK && ce == cudaSuccess && graph) {
+                ce = cudaGraphInstantiate(&exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ce == cudaSuccess) h->graphs.push_back(erasor_ctx::StepGraph{map_xyzi, query_xyzi, keep_mask, ptr_kind, h->desc_epoch, g_alloc_epoch, exec});
+                else exec = nullptr;
+            } else {
+                if (graph) cudaGraphDestroy(graph);
+                exec = nullptr;
+            }
+            if (!exec) { cudaGetLastError(); h->use_graphs = false; }      // capture not possible here: fall back to plain launches for good
+        }
+        if (exec) {
+            CK(cudaGraphLaunch(exec, h->stream));
+            h->launches += h->graph_kernel_nodes;                        // kernel nodes of the graph: init, K1, K3, K2, K4 classes
+        } else if ((rc = enqueue())) {
+            return rc;
+        }
+    } else {
+        Scope whole(h, 0);
+        if ((rc = enqueue())) return rc;
     }
     CK(cudaStreamSynchronize(h->stream));
     if (h->n_recs_host > h->rec_capacity) { h->err = "flagged-bin records overflowed; split the batch"; return ERASOR_E_CAPACITY; }
