@@ -43,6 +43,28 @@ struct GpfParams {
     int    cov_mode;
 };
 
+// R-GPF work queue.  K3 appends every flagged-bin record to the bucket of its size; K4's three size classes
+// (A: one warp per bin, B: one 256-thread CTA per bin, C: one 1024-thread CTA per bin) walk their buckets from the
+// largest bins to the smallest through an atomic cursor, so the long bins start first and no group idles while
+// records of its class remain.
+constexpr uint32_t kClassAMax   = 512;     // class A: n <= 512          (register bitonic sort, 16 keys per lane)
+constexpr uint32_t kClassBMax   = 2560;    // class B: 512 < n <= 2560   (8 warps x 512 keys)
+constexpr int      kNumBuckets  = 9;       // 0: C | 1-4: B | 5-8: A
+constexpr int      kBucketC0 = 0, kBucketB0 = 1, kBucketA0 = 5;
+constexpr int      kQueueCursor = 16;      // queue[kQueueCursor + class] : next virtual index of the class (0 A, 1 B, 2 C)
+constexpr int      kQueueWords  = 32;      // queue[0 .. kNumBuckets) : records per bucket
+ERASOR_HD int rgpf_bucket_of(uint32_t n) {
+    if (n > kClassBMax) return 0;
+    if (n > 2048u) return 1;
+    if (n > 1536u) return 2;
+    if (n > 1024u) return 3;
+    if (n > kClassAMax) return 4;
+    if (n > 384u) return 5;
+    if (n > 256u) return 6;
+    if (n > 128u) return 7;
+    return 8;
+}
+
 // Per flagged bin record written by K3 and completed by K4
 struct FlagRec {
     uint32_t frame;

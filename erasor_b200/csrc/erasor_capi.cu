@@ -85,7 +85,7 @@ struct erasor_ctx {
     DevBuf d_bin_map, d_bin_qry;               // uint16 bin id per point
     DevBuf d_chunks, d_chunk_range, d_frame_off;
     DevBuf d_chcnt, d_zmin, d_zmax, d_cnt, d_dst_start, d_status, d_action, d_flag_slot, d_nflag;
-    DevBuf d_recs, d_nrecs, d_frame_rej, d_frame_rec_base;
+    DevBuf d_recs, d_nrecs, d_frame_rej, d_frame_rec_base, d_queue, d_bucket;
     DevBuf d_map_sorted, d_map_src, d_qry_sorted, d_qry_src, d_part, d_scratch;
     DevBuf d_keep, d_ground;
     DevBuf d_arranged, d_map_rej, d_curr_rej, d_jobs, d_out_sizes, d_k5tmp;
@@ -227,6 +227,8 @@ int prepare_batch(erasor_ctx* h, const uint64_t* map_off, const uint64_t* qry_of
     h->rec_capacity = (uint32_t)std::min<size_t>((size_t)F * B, (size_t)1 << 21);
     CK(h->d_recs.ensure(sizeof(FlagRec) * (size_t)h->rec_capacity));
     CK(h->d_nrecs.ensure(sizeof(uint32_t) * 4));
+    CK(h->d_queue.ensure(sizeof(uint32_t) * kQueueWords));
+    CK(h->d_bucket.ensure(sizeof(uint32_t) * (size_t)kNumBuckets * h->rec_capacity));
     CK(h->d_map_src.ensure(sizeof(uint32_t) * std::max<size_t>(NM, 1)));
     CK(h->d_scratch.ensure((size_t)24 * std::max<size_t>(NM, 1) + 64));
     if (mode == 0) {
@@ -274,7 +276,8 @@ int run_k1(erasor_ctx* h, int mode) {
     {
         h->launches++;
         CK(launch_init_tables(h->stream, h->d_zmin.as<uint32_t>(), h->d_zmax.as<uint32_t>(), 2 * (size_t)F * B,
-                              h->d_cnt.as<uint32_t>(), 2 * (size_t)F * (B + 1), h->d_nrecs.as<uint32_t>(), h->d_frame_rej.as<uint32_t>(), F));
+                              h->d_cnt.as<uint32_t>(), 2 * (size_t)F * (B + 1), h->d_nrecs.as<uint32_t>(), h->d_frame_rej.as<uint32_t>(), F,
+                              h->d_queue.as<uint32_t>()));
     }
     {
         Scope s(h, 1);
@@ -300,7 +303,8 @@ int run_compare(erasor_ctx* h, int version, int mode, uint8_t* keep_mask, uint8_
         CK(launch_k3(h->stream, sp, F, h->d_chunk_range.as<uint32_t>(), h->d_chcnt.as<uint32_t>(), h->d_zmin.as<uint32_t>(),
                      h->d_zmax.as<uint32_t>(), h->d_frame_off.as<uint32_t>(), h->d_cnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>(),
                      h->d_status.as<uint8_t>(), h->d_action.as<uint8_t>(), h->d_flag_slot.as<uint32_t>(), h->d_nflag.as<uint32_t>(),
-                     h->d_frame_rec_base.as<uint32_t>(), h->d_recs.as<FlagRec>(), h->d_nrecs.as<uint32_t>(), h->rec_capacity));
+                     h->d_frame_rec_base.as<uint32_t>(), h->d_recs.as<FlagRec>(), h->d_nrecs.as<uint32_t>(), h->rec_capacity,
+                     h->d_queue.as<uint32_t>(), h->d_bucket.as<uint32_t>()));
     }
     {
         Scope s(h, 2);
@@ -328,7 +332,7 @@ int run_compare(erasor_ctx* h, int version, int mode, uint8_t* keep_mask, uint8_
         CK(cudaEventRecord(h->ev_fork, h->stream));
         CK(cudaStreamWaitEvent(h->stream_b, h->ev_fork, 0));
         CK(cudaStreamWaitEvent(h->stream_c, h->ev_fork, 0));
-        CK(launch_k4(h->stream, h->stream_b, h->stream_c, gp, h->d_recs.as<FlagRec>(), h->d_nrecs.as<uint32_t>(), h->rec_capacity,
+        CK(launch_k4(h->stream, h->stream_b, h->stream_c, gp, h->d_recs.as<FlagRec>(), h->d_queue.as<uint32_t>(), h->d_bucket.as<uint32_t>(), h->rec_capacity,
                      h->d_map_sorted.as<float4>(), h->d_map_src.as<uint32_t>(), h->cur_map,
                      h->d_frame_off.as<uint32_t>(), mode == 0 ? h->d_part.as<float4>() : nullptr, keep_mask, ground_mask,
                      h->d_frame_rej.as<uint32_t>(), h->d_scratch.as<unsigned char>(), h->sm_count, h->d_fence.as<unsigned long long>()));
@@ -429,7 +433,7 @@ void erasor_destroy(erasor_handle_t h) {
     h->graphs.clear();
     DevBuf* bufs[] = {&h->d_ring, &h->d_pos, &h->d_neg, &h->d_map_in, &h->d_qry_in, &h->d_bin_map, &h->d_bin_qry, &h->d_chunks,
                       &h->d_chunk_range, &h->d_frame_off, &h->d_chcnt, &h->d_zmin, &h->d_zmax, &h->d_cnt, &h->d_dst_start, &h->d_status,
-                      &h->d_action, &h->d_flag_slot, &h->d_nflag, &h->d_recs, &h->d_nrecs, &h->d_frame_rej, &h->d_map_sorted, &h->d_map_src,
+                      &h->d_action, &h->d_flag_slot, &h->d_nflag, &h->d_recs, &h->d_nrecs, &h->d_queue, &h->d_bucket, &h->d_frame_rej, &h->d_map_sorted, &h->d_map_src,
                       &h->d_qry_sorted, &h->d_qry_src, &h->d_part, &h->d_scratch, &h->d_keep, &h->d_ground, &h->d_arranged, &h->d_map_rej,
                       &h->d_curr_rej, &h->d_jobs, &h->d_out_sizes, &h->d_k5tmp, &h->d_fence, &h->d_vox, &h->d_vox_cnt, &h->d_vox_start,
                       &h->d_vox_scratch, &h->d_frame_rec_base};
@@ -472,6 +476,7 @@ int erasor_compare(erasor_handle_t h, int version, int frame) {
     (void)frame;   // the reference uses it only for a commented-out csv dump (erasor.cpp:341-343)
     if (!h) return ERASOR_E_INVALID;
     if (h->stage < 1) { h->err = "erasor_compare before erasor_set_inputs"; return ERASOR_E_STATE; }
+    if (h->stage > 1) { h->err = "erasor_compare called twice: set_inputs -> exactly one compare (OfflineMapUpdater.cpp:266-272)"; return ERASOR_E_STATE; }
     if (version != 2 && version != 3) { h->err = "Other version is not implemented!"; return ERASOR_E_INVALID; }
     CK(cudaSetDevice(h->device));
     const int B = h->B;

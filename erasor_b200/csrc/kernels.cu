@@ -284,7 +284,8 @@ k3_srt(SrtParams P, int F, const uint32_t* __restrict__ chunk_range /*[2][F+1]*/
        const uint32_t* __restrict__ cnt /*[2][F][B+1]*/, uint32_t* __restrict__ dst_start /*[2][F][B+2]*/,
        uint8_t* __restrict__ status /*[F][B]*/, uint8_t* __restrict__ action /*[F][B]*/,
        uint32_t* __restrict__ flag_slot /*[F][B]*/, uint32_t* __restrict__ n_flagged /*[F]*/, uint32_t* __restrict__ frame_rec_base /*[F]*/,
-       FlagRec* __restrict__ recs, uint32_t* __restrict__ n_recs, uint32_t rec_capacity) {
+       FlagRec* __restrict__ recs, uint32_t* __restrict__ n_recs, uint32_t rec_capacity,
+       uint32_t* __restrict__ queue /*[kQueueWords]*/, uint32_t* __restrict__ bucket_list /*[kNumBuckets][rec_capacity]*/) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int B = P.B, R = P.R, S = P.S;
     uint32_t* s_sz   = reinterpret_cast<uint32_t*>(smem_raw);          // B+2
@@ -440,6 +441,10 @@ k3_srt(SrtParams P, int F, const uint32_t* __restrict__ chunk_range /*[2][F+1]*/
                 rc.frame = f; rc.bin = b; rc.slot = slot; rc.n_points = cm[b];
                 rc.src_begin = frame_off[f] + s_sz[b];
                 rc.n_seeds = 0; rc.n_empty_fits = 0; rc.n_ground_final = 0; rc.lpr_height = 0.0; rc.cursor = 0u; rc.n_rejected = 0u;
+                if (cm[b] != 0u) {   // hand the record to the R-GPF size bucket (order inside a bucket is irrelevant: bins are independent)
+                    const int bk = rgpf_bucket_of(cm[b]);
+                    bucket_list[(size_t)bk * rec_capacity + atomicAdd(&queue[bk], 1u)] = ri;
+                }
             }
         }
     }
@@ -457,12 +462,12 @@ size_t k3_smem_bytes(int B) { return sizeof(uint32_t) * ((size_t)B + 2 + 34) + (
 cudaError_t launch_k3(cudaStream_t st, const SrtParams& P, int F, const uint32_t* chunk_range, uint32_t* ch_cnt,
                       const uint32_t* zmin, const uint32_t* zmax, const uint32_t* frame_off, const uint32_t* cnt, uint32_t* dst_start,
                       uint8_t* status, uint8_t* action, uint32_t* flag_slot, uint32_t* n_flagged, uint32_t* frame_rec_base,
-                      FlagRec* recs, uint32_t* n_recs, uint32_t rec_capacity) {
+                      FlagRec* recs, uint32_t* n_recs, uint32_t rec_capacity, uint32_t* queue, uint32_t* bucket_list) {
     const size_t smem = k3_smem_bytes(P.B);
     cudaError_t e = ensure_dyn_smem(k3_srt, smem);
     if (e != cudaSuccess) return e;
     k3_srt<<<F, 1024, smem, st>>>(P, F, chunk_range, ch_cnt, zmin, zmax, frame_off, cnt, dst_start, status, action,
-                                  flag_slot, n_flagged, frame_rec_base, recs, n_recs, rec_capacity);
+                                  flag_slot, n_flagged, frame_rec_base, recs, n_recs, rec_capacity, queue, bucket_list);
     return cudaGetLastError();
 }
 
@@ -901,6 +906,215 @@ __device__ __forceinline__ uint32_t* group_radix_sort(uint32_t* A, uint32_t* Bf,
     return src;
 }
 
+// order-preserving 32-bit encoding of z for the R-GPF sort (-0.0 folded onto +0.0: a.z < b.z treats them as equal)
+__device__ __forceinline__ uint32_t z_sort_key(float z) {
+    uint32_t u = __float_as_uint(z);
+    if (u == 0x80000000u) u = 0u;
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// Bitonic sorting network over NW*32*E 64-bit values held in registers, position p = gtid*E + r (gtid = thread of the
+// group).  Stages with j < E are compare-exchanges between registers of one thread, stages with E <= j < 32E go
+// through shuffles, and (NW > 1) stages with j >= 32E exchange through shared memory, half of the registers at a
+// time so that the exchange buffer (32*NW*E/2 values) fits in the bin's 8n-byte order area.  Register indices are
+// compile-time constants throughout (the per-warp network is straight-line code; only the cross-warp levels loop).
+// Values are (z key << 32 | source index): distinct, so the unstable network yields the stable order std::sort by z
+// would give with ties in source order (sort_mode 1).
+// compare-exchange as min / max with a selectable direction (IMNMX with a predicate operand for 32-bit values)
+#define K4_CMPX(a_, b_, asc_) do { const auto lo__ = min((a_), (b_)); const auto hi__ = max((a_), (b_)); \
+                                   (a_) = (asc_) ? lo__ : hi__; (b_) = (asc_) ? hi__ : lo__; } while (0)
+
+// stages j = E/2 .. 1 inside the thread, block direction asc
+template <int E, class T>
+__device__ __forceinline__ void bitonic_lane_stages(T (&v)[E], bool asc) {
+#pragma unroll
+    for (int j = E >> 1; j > 0; j >>= 1) {
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+            if ((r & j) == 0) K4_CMPX(v[r], v[r | j], asc);
+        }
+    }
+}
+// stages j = DMAX*E .. E across lanes (d = j / E), block direction asc
+template <int E, int DMAX, class T>
+__device__ __forceinline__ void bitonic_shfl_stages(T (&v)[E], int lane, bool asc) {
+#pragma unroll
+    for (int d = DMAX; d > 0; d >>= 1) {
+        const bool keep_min = ((lane & d) == 0) == asc;
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+            const T o = __shfl_xor_sync(FULL_MASK, v[r], d);
+            v[r] = keep_min ? min(v[r], o) : max(v[r], o);
+        }
+    }
+}
+// full sort of the warp's 32E positions; the top-level direction is asc_top, lower levels follow the network
+template <int E, class T>
+__device__ __forceinline__ void bitonic_warp_sort(T (&v)[E], int lane, bool asc_top) {
+    // k < E: inside the thread, direction from the register index
+#pragma unroll
+    for (int k = 2; k < E; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int r = 0; r < E; ++r) {
+                if ((r & j) == 0) K4_CMPX(v[r], v[r | j], (r & k) == 0);
+            }
+        }
+    }
+    // k = E .. 32E: direction from the lane (top level: asc_top)
+    bitonic_lane_stages<E>(v, (lane & 1) == 0);                                                     // k = E
+    bitonic_shfl_stages<E, 1>(v, lane, (lane & 2) == 0);  bitonic_lane_stages<E>(v, (lane & 2) == 0);    // k = 2E
+    bitonic_shfl_stages<E, 2>(v, lane, (lane & 4) == 0);  bitonic_lane_stages<E>(v, (lane & 4) == 0);    // k = 4E
+    bitonic_shfl_stages<E, 4>(v, lane, (lane & 8) == 0);  bitonic_lane_stages<E>(v, (lane & 8) == 0);    // k = 8E
+    bitonic_shfl_stages<E, 8>(v, lane, (lane & 16) == 0); bitonic_lane_stages<E>(v, (lane & 16) == 0);   // k = 16E
+    bitonic_shfl_stages<E, 16>(v, lane, asc_top);         bitonic_lane_stages<E>(v, asc_top);            // k = 32E
+}
+// the whole group's network: per-warp sort, then (NW > 1) the cross-warp levels through xbuf (32*NW*E/2 values of T)
+template <int E, int NW, class T>
+__device__ __forceinline__ void bitonic_group_sort(T (&v)[E], T* xbuf) {
+    const int gtid = (NW == 1) ? (threadIdx.x & 31) : threadIdx.x;
+    const int lane = gtid & 31, warp = gtid >> 5;
+    bitonic_warp_sort<E>(v, lane, (NW == 1) ? true : ((warp & 1) == 0));
+    if (NW > 1) {
+        constexpr int H = E / 2;
+#pragma unroll 1
+        for (int lvl = 2; lvl <= NW; lvl <<= 1) {            // k = 32E * lvl; block direction of the level: warp bit `lvl`
+            const bool asc = (warp & lvl) == 0;              // (lvl == NW: always ascending)
+#pragma unroll 1
+            for (int dw = lvl >> 1; dw > 0; dw >>= 1) {      // stages j = 32E * dw: partner warp = warp ^ dw
+                const bool keep_min = ((warp & dw) == 0) == asc;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                    for (int r = 0; r < H; ++r) xbuf[(warp * H + r) * 32 + lane] = v[h * H + r];
+                    __syncthreads();
+#pragma unroll
+                    for (int r = 0; r < H; ++r) {
+                        const T o = xbuf[((warp ^ dw) * H + r) * 32 + lane];
+                        v[h * H + r] = keep_min ? min(v[h * H + r], o) : max(v[h * H + r], o);
+                    }
+                    __syncthreads();
+                }
+            }
+            bitonic_shfl_stages<E, 16>(v, lane, asc);
+            bitonic_lane_stages<E>(v, asc);
+        }
+    }
+}
+
+// z-sort, exact 64-bit version: values (z key << 32 | source index).  ORD[0..n) <- source indices in (z, index) order.
+// Requires n <= NW*32*E.  For NW > 1, ORD must start an 8-byte aligned area of at least 8n bytes (the exchange buffer).
+// Not inlined: one copy of each network serves the shared-memory and the global-scratch variants of the caller.
+template <int E, int NW>
+__device__ __noinline__ void group_bitonic_zsort(const float* Z, uint32_t* ORD, uint32_t n) {
+    constexpr int G = NW * 32;
+    const int gtid = (NW == 1) ? (threadIdx.x & 31) : threadIdx.x;
+    unsigned long long v[E];
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const uint32_t e = (uint32_t)r * G + gtid;       // any placement works: the network sorts positions, ties carry the index
+        v[r] = (e < n) ? (((unsigned long long)z_sort_key(Z[e]) << 32) | e) : ~0ull;
+    }
+    bitonic_group_sort<E, NW>(v, reinterpret_cast<unsigned long long*>(ORD));
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const uint32_t pos = (uint32_t)gtid * E + r;
+        if (pos < n) ORD[pos] = (uint32_t)v[r];
+    }
+    if (NW == 1) __syncwarp(); else __syncthreads();
+}
+
+// z-sort, packed 32-bit version (4x fewer instructions than the 64-bit network).  Each point becomes one word
+//   (q << IB) | source index,   q = min(uint((z - zmin) * QMAX / (zmax - zmin)), QMAX)   (23 bits for a warp, 20 for a CTA):
+// q is monotone in z, so after sorting the words the order is exact except inside runs of equal q, which are still in
+// source-index order.  Those runs are short (q resolves the bin's z range to 2^-23 / 2^-20, about one float ulp) and
+// are finished by an odd-even transposition on the full (z key, index) pairs, restricted to the listed positions p
+// with q[p] == q[p+1].  More than list_cap such positions: returns false and the caller runs the 64-bit network.
+// s_red: 2*NW + 2 words of scratch (CTA groups).
+template <int E, int NW>
+__device__ __noinline__ bool group_packed_zsort(const float* Z, uint32_t* ORD, uint32_t n, uint32_t* list, uint32_t list_cap, uint32_t* s_red) {
+    constexpr int G  = NW * 32;
+    constexpr int IB = (NW == 1) ? 9 : 12;
+    constexpr uint32_t QMAX = (1u << (32 - IB)) - 1u, IMASK = (1u << IB) - 1u;
+    const int gtid = (NW == 1) ? (threadIdx.x & 31) : threadIdx.x;
+    const int lane = gtid & 31, warp = gtid >> 5;
+    float z[E];
+    float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const uint32_t e = (uint32_t)r * G + gtid;
+        z[r] = (e < n) ? Z[e] : 0.0f;
+        if (e < n) { mn = fminf(mn, z[r]); mx = fmaxf(mx, z[r]); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(FULL_MASK, mn, o)); mx = fmaxf(mx, __shfl_xor_sync(FULL_MASK, mx, o)); }
+    if (NW > 1) {
+        if (lane == 0) { s_red[warp] = __float_as_uint(mn); s_red[NW + warp] = __float_as_uint(mx); }
+        if (gtid == 0) s_red[2 * NW] = 0u;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { mn = fminf(mn, __uint_as_float(s_red[w])); mx = fmaxf(mx, __uint_as_float(s_red[NW + w])); }
+    }
+    const float D = __fsub_rn(mx, mn);
+    float scale = (D > 0.0f) ? __fdiv_rn((float)QMAX, D) : 0.0f;
+    if (!(scale <= 3.0e38f)) scale = 0.0f;
+    auto q_of = [&](float zz) -> uint32_t { return min(__float2uint_rz(__fmul_rn(__fsub_rn(zz, mn), scale)), QMAX); };
+    uint32_t v[E];
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const uint32_t e = (uint32_t)r * G + gtid;
+        v[r] = (e < n) ? ((q_of(z[r]) << IB) | e) : 0xFFFFFFFFu;      // a pad equals a real word only when no pad exists (n == 32*NW*E)
+    }
+    bitonic_group_sort<E, NW>(v, ORD);
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const uint32_t pos = (uint32_t)gtid * E + r;
+        if (pos < n) ORD[pos] = v[r] & IMASK;
+    }
+    if (NW == 1) __syncwarp(); else __syncthreads();
+    // positions whose successor shares q
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const uint32_t pos = (uint32_t)gtid * E + r;
+        bool same = false;
+        if (pos + 1u < n) {
+            const uint32_t qn = (r + 1 < E) ? (v[(r + 1 < E) ? r + 1 : r] >> IB) : q_of(Z[ORD[pos + 1u]]);
+            same = (v[r] >> IB) == qn;
+        }
+        if (NW == 1) {
+            const unsigned bal = __ballot_sync(FULL_MASK, same);
+            if (same) { const uint32_t s = cnt + __popc(bal & ((1u << lane) - 1u)); if (s < list_cap) list[s] = pos; }
+            cnt += __popc(bal);
+        } else if (same) {
+            const uint32_t s = atomicAdd(&s_red[2 * NW], 1u);
+            if (s < list_cap) list[s] = pos;
+        }
+    }
+    if (NW == 1) __syncwarp(); else { __syncthreads(); cnt = s_red[2 * NW]; }
+    if (cnt > list_cap) return false;
+    if (cnt == 0u) return true;
+    for (;;) {
+        bool swapped = false;
+#pragma unroll 1
+        for (uint32_t phase = 0; phase < 2u; ++phase) {
+            for (uint32_t t = gtid; t < cnt; t += G) {
+                const uint32_t pp = list[t];
+                if ((pp & 1u) == phase) {
+                    const uint32_t ia = ORD[pp], ib = ORD[pp + 1u];
+                    const uint32_t ka = z_sort_key(Z[ia]), kb = z_sort_key(Z[ib]);
+                    if (ka > kb || (ka == kb && ia > ib)) { ORD[pp] = ib; ORD[pp + 1u] = ia; swapped = true; }
+                }
+            }
+            if (NW == 1) __syncwarp(); else __syncthreads();
+        }
+        const bool any = (NW == 1) ? (__any_sync(FULL_MASK, swapped) != 0) : (__syncthreads_or(swapped ? 1 : 0) != 0);
+        if (!any) break;
+    }
+    return true;
+}
+
 struct K4Shared {
     float    normal[3];
     uint32_t pad_;
@@ -920,12 +1134,14 @@ __device__ __forceinline__ void k4_process_bin(const GpfParams& P, FlagRec& rc, 
     const int tid = group_tid<G>(), lane = tid & 31, warp = tid >> 5;
     const uint32_t n = rc.n_points, src_begin = rc.src_begin;
     const uint32_t fbase = frame_off[rc.frame];
-    float*    X   = reinterpret_cast<float*>(base);
+    // slice layout: [ORD n u32][TMP n u32 (CTA groups only)][X][Y][Z n f32 each][FLG n u8]; ORD|TMP is also the 8n-byte
+    // exchange area of the class-B sort, hence first (the slice base is 16-byte aligned)
+    uint32_t* ORD = reinterpret_cast<uint32_t*>(base);
+    uint32_t* TMP = ORD + n;
+    float*    X   = reinterpret_cast<float*>((G == 32) ? TMP : TMP + n);
     float*    Y   = X + n;
     float*    Z   = Y + n;
-    uint32_t* ORD = reinterpret_cast<uint32_t*>(Z + n);
-    uint32_t* TMP = ORD + n;
-    uint8_t*  FLG = reinterpret_cast<uint8_t*>(TMP + n);
+    uint8_t*  FLG = reinterpret_cast<uint8_t*>(Z + n);
     constexpr int TILE = (G == 32) ? 64 : 256;
     float*    PRD = prd;                          // 9 x (TILE + 1) floats, always shared memory
     long long t_prev = clock64();
@@ -935,19 +1151,28 @@ __device__ __forceinline__ void k4_process_bin(const GpfParams& P, FlagRec& rc, 
     // K2 placed the bin's points contiguously in source order (all bins in cloud mode, flagged bins only in mask mode)
     for (uint32_t i = tid; i < n; i += G) {
         const float4 p = sorted_pts[src_begin + i];
-        X[i] = p.x; Y[i] = p.y; Z[i] = p.z; ORD[i] = i;
+        X[i] = p.x; Y[i] = p.y; Z[i] = p.z;
+        if (G > 256) ORD[i] = i;
     }
     group_sync<G>();
     K4_TICK(0);
 
     // std::sort by z (erasor.cpp:240), ties in source order: stable radix sort on the order-preserving encoding of z
     // (-0.0 is folded onto +0.0 first: the comparator a.z < b.z treats them as equal)
-    {
-        uint32_t* zs = group_radix_sort<G>(ORD, TMP, n, cnt_scratch, sh.warp, 32, [&](uint32_t id) {
-            uint32_t u = __float_as_uint(Z[id]);
-            if (u == 0x80000000u) u = 0u;
-            return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-        });
+    if constexpr (G == 32) {
+        // class A (n <= 512): the warp sorts in registers; the collision list lives in the (still unused) product tile
+        uint32_t* lst = reinterpret_cast<uint32_t*>(PRD);
+        if (n <= 128u)      { if (!group_packed_zsort<4, 1>(Z, ORD, n, lst, 256u, sh.warp))  group_bitonic_zsort<4, 1>(Z, ORD, n); }
+        else if (n <= 256u) { if (!group_packed_zsort<8, 1>(Z, ORD, n, lst, 256u, sh.warp))  group_bitonic_zsort<8, 1>(Z, ORD, n); }
+        else                { if (!group_packed_zsort<16, 1>(Z, ORD, n, lst, 256u, sh.warp)) group_bitonic_zsort<16, 1>(Z, ORD, n); }
+    } else if constexpr (G == 256) {
+        // class B (n <= 4096): eight warps, cross-warp stages through the ORD|TMP area
+        uint32_t* lst = reinterpret_cast<uint32_t*>(PRD);
+        if (n <= 1024u)      { if (!group_packed_zsort<4, 8>(Z, ORD, n, lst, 1024u, sh.warp))  group_bitonic_zsort<4, 8>(Z, ORD, n); }
+        else if (n <= 2048u) { if (!group_packed_zsort<8, 8>(Z, ORD, n, lst, 1024u, sh.warp))  group_bitonic_zsort<8, 8>(Z, ORD, n); }
+        else                 { if (!group_packed_zsort<16, 8>(Z, ORD, n, lst, 1024u, sh.warp)) group_bitonic_zsort<16, 8>(Z, ORD, n); }
+    } else {
+        uint32_t* zs = group_radix_sort<G>(ORD, TMP, n, cnt_scratch, sh.warp, 32, [&](uint32_t id) { return z_sort_key(Z[id]); });
         if (zs != ORD) { TMP = ORD; ORD = zs; }
     }
     K4_TICK(1);
@@ -1108,13 +1333,14 @@ __device__ __forceinline__ void k4_process_bin(const GpfParams& P, FlagRec& rc, 
 #undef K4_TICK
 }
 
-// Records are served to size classes: a launch handles bins with n_lo < n_points <= n_hi.
-// G == 32: every warp of the CTA is a group with its own shared-memory slice (slice_bytes); bins are dealt to warps.
+// One launch per size class.  Groups pull records of the class from the bucketed queue (largest bins first) through
+// an atomic cursor until the class is drained.
+// G == 32: every warp of the CTA is a group with its own shared-memory slice (slice_bytes).
 // G == THREADS: the CTA is the group; bins above smem_cap_points work in their slice of the global scratch.
 template <int THREADS, int G>
-__global__ void __launch_bounds__(THREADS)
-k4_rgpf(GpfParams P, FlagRec* __restrict__ recs, const uint32_t* __restrict__ n_recs, uint32_t rec_capacity,
-        uint32_t n_lo, uint32_t n_hi, const float4* __restrict__ sorted_pts, uint32_t* __restrict__ sorted_src,
+__global__ void __launch_bounds__(THREADS, (THREADS == 256) ? 3 : 1)
+k4_rgpf(GpfParams P, FlagRec* __restrict__ recs, uint32_t* __restrict__ queue, const uint32_t* __restrict__ bucket_list,
+        uint32_t rec_capacity, int bk0, int bk1, int cls, const float4* __restrict__ sorted_pts, uint32_t* __restrict__ sorted_src,
         const float4* __restrict__ in_pts, const uint32_t* __restrict__ frame_off /*map cloud [F+1]*/,
         float4* __restrict__ part_pts /*nullable*/, uint8_t* __restrict__ keep_mask /*nullable*/,
         uint8_t* __restrict__ ground_mask /*nullable*/, uint32_t* __restrict__ frame_rejected /*[F] nullable*/,
@@ -1123,16 +1349,38 @@ k4_rgpf(GpfParams P, FlagRec* __restrict__ recs, const uint32_t* __restrict__ n_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NG = THREADS / G;
     constexpr int TILE = (G == 32) ? 64 : 256;
+    constexpr int NCNT = (G > 256) ? 8 * G : 1;          // radix counters: only the class-C sort uses them
     __shared__ K4Shared sh[NG];
     __shared__ float    s_prd[NG][9 * (TILE + 1)];
-    __shared__ uint32_t s_cnt[NG][8 * G];
-    const uint32_t nrec = min(*n_recs, rec_capacity);
+    __shared__ uint32_t s_cnt[NG][NCNT];
+    __shared__ uint32_t s_fetch;
     const int grp = (G == 32) ? (threadIdx.x >> 5) : 0;
-    const uint32_t first = blockIdx.x * NG + grp, stride = gridDim.x * NG;
-    for (uint32_t w = first; w < nrec; w += stride) {
+    uint32_t bcnt[4] = {0u, 0u, 0u, 0u}, total = 0u;     // a class spans at most four buckets
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (bk0 + k < bk1) { bcnt[k] = min(queue[bk0 + k], rec_capacity); total += bcnt[k]; }
+    }
+    for (;;) {
+        uint32_t i;
+        if (G == 32) {
+            i = 0u;
+            if ((threadIdx.x & 31) == 0) i = atomicAdd(&queue[kQueueCursor + cls], 1u);
+            i = __shfl_sync(FULL_MASK, i, 0);
+        } else {
+            if (threadIdx.x == 0) s_fetch = atomicAdd(&queue[kQueueCursor + cls], 1u);
+            __syncthreads();
+            i = s_fetch;
+            __syncthreads();
+        }
+        if (i >= total) break;
+        int bk = bk0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (bk == bk0 + k && i >= bcnt[k]) { i -= bcnt[k]; ++bk; }
+        }
+        const uint32_t w = bucket_list[(size_t)bk * rec_capacity + i];
         FlagRec& rc = recs[w];
         const uint32_t n = rc.n_points;
-        if (n <= n_lo || n > n_hi) continue;
         if (n <= smem_cap_points)
             k4_process_bin<G, true>(P, rc, smem_raw + (size_t)grp * slice_bytes, s_prd[grp], s_cnt[grp], sh[grp], sorted_pts, sorted_src, in_pts,
                                     frame_off, part_pts, keep_mask, ground_mask, frame_rejected, fence);
@@ -1143,43 +1391,48 @@ k4_rgpf(GpfParams P, FlagRec* __restrict__ recs, const uint32_t* __restrict__ n_
 }
 
 template <int THREADS, int G>
-static cudaError_t launch_k4_class(cudaStream_t st, const GpfParams& P, FlagRec* recs, const uint32_t* n_recs, uint32_t rec_capacity,
-                                   uint32_t n_lo, uint32_t n_hi, uint32_t smem_bytes, const float4* sorted_pts, uint32_t* sorted_src,
-                                   const float4* in_pts, const uint32_t* frame_off, float4* part_pts, uint8_t* keep_mask,
-                                   uint8_t* ground_mask, uint32_t* frame_rejected, unsigned char* gscratch, int grid,
+static cudaError_t launch_k4_class(cudaStream_t st, const GpfParams& P, FlagRec* recs, uint32_t* queue, const uint32_t* bucket_list,
+                                   uint32_t rec_capacity, int bk0, int bk1, int cls, uint32_t smem_bytes, const float4* sorted_pts,
+                                   uint32_t* sorted_src, const float4* in_pts, const uint32_t* frame_off, float4* part_pts,
+                                   uint8_t* keep_mask, uint8_t* ground_mask, uint32_t* frame_rejected, unsigned char* gscratch, int grid,
                                    unsigned long long* fence) {
-    // per bin: 12 n (xyz) + 4 n (order) + 4 n (ping-pong) + n (flags) = 21 n
+    // per bin: 12 n (xyz) + 4 n (order) + n (flags) = 17 n for warp groups, + 4 n (second half of the order / exchange area) = 21 n
     constexpr int NG = THREADS / G;
+    constexpr uint32_t per_pt = (G == 32) ? 17u : 21u;
     const uint32_t slice = (smem_bytes / NG) & ~15u;
-    const uint32_t cap = (slice - 32) / 21u;
+    const uint32_t cap = (slice - 32) / per_pt;
     auto kern = k4_rgpf<THREADS, G>;
     cudaError_t e = ensure_dyn_smem(kern, smem_bytes);
     if (e != cudaSuccess) return e;
-    kern<<<grid, THREADS, smem_bytes, st>>>(P, recs, n_recs, rec_capacity, n_lo, n_hi, sorted_pts, sorted_src, in_pts, frame_off,
+    kern<<<grid, THREADS, smem_bytes, st>>>(P, recs, queue, bucket_list, rec_capacity, bk0, bk1, cls, sorted_pts, sorted_src, in_pts, frame_off,
                                             part_pts, keep_mask, ground_mask, frame_rejected, gscratch, cap, slice, fence);
     return cudaGetLastError();
 }
 
 int k4_num_launches() { return 3; }
 
-cudaError_t launch_k4(cudaStream_t st, cudaStream_t st_b, cudaStream_t st_c, const GpfParams& P, FlagRec* recs, const uint32_t* n_recs,
-                      uint32_t rec_capacity, const float4* sorted_pts, uint32_t* sorted_src, const float4* in_pts, const uint32_t* frame_off,
-                      float4* part_pts, uint8_t* keep_mask, uint8_t* ground_mask, uint32_t* frame_rejected, unsigned char* gscratch,
-                      int sm_count, unsigned long long* fence) {
+cudaError_t launch_k4(cudaStream_t st, cudaStream_t st_b, cudaStream_t st_c, const GpfParams& P, FlagRec* recs, uint32_t* queue,
+                      const uint32_t* bucket_list, uint32_t rec_capacity, const float4* sorted_pts, uint32_t* sorted_src, const float4* in_pts,
+                      const uint32_t* frame_off, float4* part_pts, uint8_t* keep_mask, uint8_t* ground_mask, uint32_t* frame_rejected,
+                      unsigned char* gscratch, int sm_count, unsigned long long* fence) {
     // The three size classes touch disjoint bins, so they run concurrently on three streams (the caller forks / joins).
+    // Shared memory is sized so that one class-A CTA (8 bins) and two class-B CTAs are resident per SM at the same time:
+    //   A  8 x 8.75 KB slices + 18.7 KB products  ~ 90 KB      B  52.6 KB + 9.3 KB products ~ 62 KB each   (A + 2B ~ 214 KB of 227 KB)
+    // Class C wants most of an SM: it is issued first so that its CTAs (which exit at once when the class is empty, the
+    // usual case for KITTI-sized maps) do not have to wait for shared memory held by A and B.
+    static_assert(kClassAMax <= 512 && kClassBMax <= 4096, "sort networks: 16 keys per lane");
     cudaError_t e;
-    // class A: n <= 512, one warp per bin, 8 warps per CTA with 9 KB slices (512 pts: 12*512 + 8*512 + 512 = 10.5 KB -> cap 438;
-    //          bins between the slice cap and 512 points use the global scratch)
-    e = launch_k4_class<256, 32>(st, P, recs, n_recs, rec_capacity, 0u, 512u, 8 * 11 * 1024, sorted_pts, sorted_src, in_pts, frame_off,
-                                 part_pts, keep_mask, ground_mask, frame_rejected, gscratch, sm_count * 2, fence);
+    // class C: n > 2560, one 1024-thread CTA with most of an SM's shared memory; beyond ~8.7 k points global scratch
+    e = launch_k4_class<1024, 1024>(st_c, P, recs, queue, bucket_list, rec_capacity, kBucketC0, kBucketB0, 2, 180 * 1024, sorted_pts, sorted_src,
+                                    in_pts, frame_off, part_pts, keep_mask, ground_mask, frame_rejected, gscratch, sm_count, fence);
     if (e != cudaSuccess) return e;
     // class B: 512 < n <= 2560, one 256-thread CTA per bin
-    e = launch_k4_class<256, 256>(st_b, P, recs, n_recs, rec_capacity, 512u, 2560u, 54 * 1024, sorted_pts, sorted_src, in_pts, frame_off,
-                                  part_pts, keep_mask, ground_mask, frame_rejected, gscratch, sm_count * 3, fence);
+    e = launch_k4_class<256, 256>(st_b, P, recs, queue, bucket_list, rec_capacity, kBucketB0, kBucketA0, 1, 21 * kClassBMax + 64, sorted_pts,
+                                  sorted_src, in_pts, frame_off, part_pts, keep_mask, ground_mask, frame_rejected, gscratch, sm_count * 2, fence);
     if (e != cudaSuccess) return e;
-    // class C: anything larger, one 1024-thread CTA with most of an SM's shared memory; beyond ~8.7 k points global scratch
-    return launch_k4_class<1024, 1024>(st_c, P, recs, n_recs, rec_capacity, 2560u, 0xFFFFFFFFu, 180 * 1024, sorted_pts, sorted_src, in_pts,
-                                       frame_off, part_pts, keep_mask, ground_mask, frame_rejected, gscratch, sm_count, fence);
+    // class A: n <= 512, one warp per bin, 8 warps per CTA
+    return launch_k4_class<256, 32>(st, P, recs, queue, bucket_list, rec_capacity, kBucketA0, kNumBuckets, 0, 8 * (17 * kClassAMax + 48), sorted_pts,
+                                    sorted_src, in_pts, frame_off, part_pts, keep_mask, ground_mask, frame_rejected, gscratch, sm_count, fence);
 }
 
 // ============================================================================================
@@ -1448,19 +1701,20 @@ cudaError_t launch_k5(cudaStream_t st, int B, int version, int skip_voxelize, co
 // small utilities
 // ============================================================================================
 __global__ void k_init_tables(uint32_t* zmin, uint32_t* zmax, size_t n, uint32_t* cnt, size_t n_cnt, uint32_t* n_recs,
-                              uint32_t* frame_rejected, int F) {
+                              uint32_t* frame_rejected, int F, uint32_t* queue) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (size_t)kQueueWords) queue[i] = 0u;
     if (i < n) { zmin[i] = 0xFFFFFFFFu; zmax[i] = 0u; }
     if (i < n_cnt) cnt[i] = 0u;
     if (i == 0) *n_recs = 0u;
     if (frame_rejected && i < (size_t)F) frame_rejected[i] = 0u;
 }
 cudaError_t launch_init_tables(cudaStream_t st, uint32_t* zmin, uint32_t* zmax, size_t n, uint32_t* cnt, size_t n_cnt, uint32_t* n_recs,
-                               uint32_t* frame_rejected, int F) {
+                               uint32_t* frame_rejected, int F, uint32_t* queue) {
     size_t m = n > (size_t)F ? n : (size_t)F;
     m = m > n_cnt ? m : n_cnt;
     const int blocks = (int)((m + 255) / 256);
-    k_init_tables<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(zmin, zmax, n, cnt, n_cnt, n_recs, frame_rejected, F);
+    k_init_tables<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(zmin, zmax, n, cnt, n_cnt, n_recs, frame_rejected, F, queue);
     return cudaGetLastError();
 }
 

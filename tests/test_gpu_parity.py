@@ -301,3 +301,51 @@ def test_batch_masks_v2_and_ragged(capi, oracle_mod, small_workload):
         okeep[rej] = 0
         assert np.array_equal(keep[int(mo[f]):int(mo[f + 1])], okeep), f"frame {f}"
     h.close()
+
+
+def _crafted_bin_frame(rng, n_ground, z_kind, sector_deg=15.0, r0=20.0):
+    """One map bin that the Scan Ratio Test flags (tall object over ground, low query bin), with a chosen z distribution of
+    its ground points; returns (map, query).  Everything sits inside one ring / sector of the seq_05 geometry."""
+    th = np.deg2rad(sector_deg) + rng.uniform(-0.02, 0.02, n_ground)
+    r = r0 + rng.uniform(0.2, 3.0, n_ground)
+    if z_kind == "dup":            # a handful of distinct heights, many exact duplicates
+        z = rng.choice(np.array([-1.0, -0.95, -0.9, -0.9000001, -0.0, 0.0], dtype=np.float32), n_ground)
+    elif z_kind == "equal":        # every point at the same height
+        z = np.full(n_ground, -0.9, dtype=np.float32)
+    elif z_kind == "ulp":          # clusters a few ulps wide next to a wide outlier range (coarse q cells)
+        z = (np.float32(-0.9) + rng.integers(0, 7, n_ground).astype(np.float32) * np.float32(6e-8)).astype(np.float32)
+    else:                          # rough ground
+        z = rng.normal(-0.9, 0.04, n_ground).astype(np.float32)
+    g = np.stack([r * np.cos(th), r * np.sin(th), z, np.full(n_ground, 40.0)], axis=1).astype(np.float32)
+    n_obj = 60
+    tho = np.deg2rad(sector_deg) + rng.uniform(-0.01, 0.01, n_obj)
+    ro = r0 + rng.uniform(1.0, 2.0, n_obj)
+    obj = np.stack([ro * np.cos(tho), ro * np.sin(tho), rng.uniform(-0.7, 2.0, n_obj), np.full(n_obj, 252.0)], axis=1).astype(np.float32)
+    m = rng.permutation(np.concatenate([g, obj]))
+    nq = 40
+    thq = np.deg2rad(sector_deg) + rng.uniform(-0.02, 0.02, nq)
+    rq = r0 + rng.uniform(0.2, 3.0, nq)
+    q = np.stack([rq * np.cos(thq), rq * np.sin(thq), rng.normal(-0.9, 0.03, nq), np.full(nq, 40.0)], axis=1).astype(np.float32)
+    return m, q
+
+
+@pytest.mark.parametrize("z_kind", ["rough", "dup", "equal", "ulp"])
+@pytest.mark.parametrize("n_ground", [60, 190, 450, 600, 1200, 2400, 3500])
+def test_rgpf_sort_classes_and_ties(capi, oracle_mod, z_kind, n_ground):
+    """R-GPF's z-sort (erasor.cpp:240) across the three size classes of K4 with tie-heavy and ulp-wide height distributions:
+    the packed 32-bit network + exact fix-up, its 64-bit fallback and the radix sort must all give std::stable_sort's order
+    (plane normals, ground counts and the retained cloud are compared bit for bit)."""
+    rng = np.random.default_rng(1000 + n_ground)
+    p = P.preset("seq_05").replace(skip_voxelize=1, version=3)
+    m, q = _crafted_bin_frame(rng, n_ground, z_kind)
+    o, h = _run_both(capi, oracle_mod, p, m, q)
+    h.compare(3)
+    gp, op = h.get_planes(), o.planes()
+    assert len(op) >= 1, "the crafted bin must be flagged"
+    assert [g["bin"] for g in gp] == [x["bin"] for x in op]
+    for g, x in zip(gp, op):
+        assert np.array_equal(g["normal_d"], x["normal_d"]) and np.array_equal(g["n_ground"], x["n_ground"]), (z_kind, n_ground)
+    arr, _ = h.get_static_estimate()
+    oarr, _ = o.cloud(o.ARRANGED)
+    assert arr.shape == oarr.shape and np.array_equal(arr.view(np.uint32), oarr.view(np.uint32))
+    h.close()
