@@ -26,7 +26,7 @@ EXPORTS = [
     "erasor_set_inputs", "erasor_compare", "erasor_get_output_sizes", "erasor_get_static_estimate", "erasor_get_outliers",
     "erasor_get_max_range", "erasor_get_bins", "erasor_get_status", "erasor_get_planes", "erasor_get_static_mask",
     "erasor_get_fence_counts", "erasor_process_frames", "erasor_fold_keep_masks", "erasor_get_frame_stats", "erasor_kernel_launch_count",
-    "erasor_get_kernel_time_ms", "erasor_reset_kernel_times", "erasor_get_rgpf_profile",
+    "erasor_get_kernel_time_ms", "erasor_reset_kernel_times", "erasor_get_rgpf_profile", "erasor_get_srt_profile",
     "erasor_updater_create", "erasor_updater_destroy", "erasor_updater_reset", "erasor_updater_last_error", "erasor_updater_process_node",
     "erasor_updater_map_size", "erasor_updater_get_cloud", "erasor_updater_save_static_map", "erasor_updater_voxelize",
     "erasor_updater_erasor", "erasor_updater_kernel_launch_count",
@@ -85,6 +85,7 @@ def _load():
     L.erasor_get_kernel_time_ms.argtypes = [c_void_p, c_int, POINTER(c_double), POINTER(c_uint64)]
     L.erasor_reset_kernel_times.argtypes = [c_void_p, c_int]
     L.erasor_get_rgpf_profile.argtypes = [c_void_p, POINTER(c_uint32), POINTER(c_uint32), POINTER(c_size_t)]
+    L.erasor_get_srt_profile.argtypes = [c_void_p, POINTER(c_uint32)]
     L.erasor_updater_create.argtypes = [POINTER(UpdaterParamsC), POINTER(ErasorParamsC), c_void_p, c_size_t, c_int, POINTER(c_void_p)]
     L.erasor_updater_destroy.restype = None
     L.erasor_updater_destroy.argtypes = [c_void_p]
@@ -293,6 +294,11 @@ class Handle:
 
     def reset_kernel_times(self, enable: bool):
         self._ck(self.L.erasor_reset_kernel_times(self.h, 1 if enable else 0))
+
+    def srt_profile(self):
+        out = np.zeros(8, dtype=np.uint32)
+        self._ck(self.L.erasor_get_srt_profile(self.h, out.ctypes.data_as(POINTER(c_uint32))))
+        return out
 
     def rgpf_profile(self):
         n = c_size_t(0)

@@ -154,14 +154,25 @@ void drain_timers(erasor_ctx* h) {
     }
 }
 
-uint32_t choose_chunk(const erasor_ctx* h, size_t total_points, int mode) {
-    // Chunk = one CTA of K1 (and one warp of K2 in cloud mode).  Aim at one wave of K1 CTAs (table init / flush amortised).  In cloud mode the dense
-    // per-chunk count rows cost 4*(B+1) bytes each, so keep the chunk at >= 5*B points (<= 5 % extra traffic).
-    const size_t target = total_points / ((size_t)h->sm_count * 4) + 1;      // one wave of 4 resident CTAs per SM
-    size_t ch = std::max<size_t>(target, std::max<size_t>(2048, (size_t)5 * h->B));
-    (void)mode;
-    ch = std::min<size_t>(ch, 65536);
-    ch = (ch + 127) & ~(size_t)127;
+uint32_t choose_chunk(const erasor_ctx* h, const uint64_t* map_off, const uint64_t* qry_off, int F) {
+    // Chunk = one CTA of K1 and of K2.  Aim at ONE wave of CTAs (4 resident per SM for both kernels): a second, nearly empty
+    // wave costs a whole CTA latency.  Frames are chunked separately, so the count is taken over the real frame sizes.
+    // The dense per-chunk count rows cost 4*(B+1) bytes each: keep the chunk at >= 5*B points (<= 5 % extra traffic).
+    const size_t total = (size_t)(map_off[F] + qry_off[F]);
+    const size_t slots = (size_t)h->sm_count * 4;
+    auto count = [&](size_t ch) {
+        size_t n = 0;
+        for (int f = 0; f < F; ++f) n += (size_t)((map_off[f + 1] - map_off[f] + ch - 1) / ch) + (size_t)((qry_off[f + 1] - qry_off[f] + ch - 1) / ch);
+        return n;
+    };
+    const size_t cap = 65536;
+    size_t ch = std::max<size_t>(total / slots + 1, std::max<size_t>(2048, (size_t)5 * h->B));
+    ch = std::min<size_t>((ch + 127) & ~(size_t)127, cap);
+    if (count(cap) <= slots) {
+        while (ch < cap && count(ch) > slots) ch = std::min<size_t>(cap, (ch + std::max<size_t>(128, ch / 64) + 127) & ~(size_t)127);
+    } else {
+        ch = cap;      // several waves anyway
+    }
     return (uint32_t)ch;
 }
 
@@ -182,7 +193,7 @@ int prepare_batch(erasor_ctx* h, const uint64_t* map_off, const uint64_t* qry_of
     h->F = F; h->NM = NM; h->NQ = NQ;
     h->map_off.assign(map_off, map_off + F + 1);
     h->qry_off.assign(qry_off, qry_off + F + 1);
-    const uint32_t CH = choose_chunk(h, NM + NQ, mode);
+    const uint32_t CH = choose_chunk(h, map_off, qry_off, F);
 
     std::vector<ChunkDesc> chunks;
     std::vector<uint32_t>  range(2 * (size_t)(F + 1)), foff(2 * (size_t)(F + 1));
@@ -781,6 +792,15 @@ int erasor_get_rgpf_profile(erasor_handle_t h, uint32_t* n_points, uint32_t* pro
         if (n_points) n_points[i] = recs[i].n_points;
         if (prof8) for (int k = 0; k < 8; ++k) prof8[i * 8 + k] = recs[i].prof[k];
     }
+    return ERASOR_OK;
+}
+
+int erasor_get_srt_profile(erasor_handle_t h, uint32_t* cycles8) {
+    if (!h || !cycles8) return ERASOR_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    if (!h->d_queue.p) { h->err = "no run yet"; return ERASOR_E_STATE; }
+    CK(cudaMemcpy(cycles8, h->d_queue.as<uint32_t>() + 20, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost));
     return ERASOR_OK;
 }
 

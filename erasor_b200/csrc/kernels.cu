@@ -301,6 +301,8 @@ k3_srt(SrtParams P, int F, const uint32_t* __restrict__ chunk_range /*[2][F+1]*/
     uint8_t* st_out  = status + (size_t)f * B;
     uint8_t* act_out = action + (size_t)f * B;
     const bool min_pts_neg = P.minimum_num_pts < 0;     // size_t < int comparison wraps (App. B-9)
+    long long t_prev = clock64();                       // phase profile of frame 0 (erasor_get_srt_profile)
+#define K3_TICK(slot) do { if (f == 0 && tid == 0) { const long long t__ = clock64(); queue[20 + (slot)] = (uint32_t)(t__ - t_prev); t_prev = t__; } } while (0)
 
     if (P.version == 3) {
         // pass 1 (erasor.cpp:448-486)
@@ -383,6 +385,7 @@ k3_srt(SrtParams P, int F, const uint32_t* __restrict__ chunk_range /*[2][F+1]*/
         }
     }
     __syncthreads();
+    K3_TICK(0);
 
     // in-place exclusive prefix of the per-chunk count rows over the frame's chunks, for the bins K2 will scatter:
     // every bin of both clouds in cloud mode, the flagged map bins only in mask mode (the per-bin totals themselves
@@ -393,15 +396,21 @@ k3_srt(SrtParams P, int F, const uint32_t* __restrict__ chunk_range /*[2][F+1]*/
         for (int b = tid; b <= B; b += nt) {
             const bool take = (P.scatter_mode == 0) || (b < B && (act_out[b] & 0x0F) == ACT_FLAG);
             if (!take) continue;
+            // eight rows per round trip: the loads of a batch are independent, only the running sum is serial
             uint32_t run = 0;
-            for (uint32_t k = c0; k < c1; ++k) {
-                uint32_t* p = ch_cnt + (size_t)k * (B + 1) + b;
-                const uint32_t v = *p;
-                *p = run;
-                run += v;
+            for (uint32_t k0 = c0; k0 < c1; k0 += 8u) {
+                uint32_t v[8];
+#pragma unroll
+                for (uint32_t u = 0; u < 8u; ++u) v[u] = (k0 + u < c1) ? ch_cnt[(size_t)(k0 + u) * (B + 1) + b] : 0u;
+#pragma unroll
+                for (uint32_t u = 0; u < 8u; ++u) {
+                    if (k0 + u < c1) { ch_cnt[(size_t)(k0 + u) * (B + 1) + b] = run; run += v[u]; }
+                }
             }
         }
     }
+    __syncthreads();
+    K3_TICK(1);
     // flagged bins, in bin order
     uint32_t* slot_out = flag_slot + (size_t)f * B;
     for (int b = tid; b < B; b += nt) s_sz[b] = ((act_out[b] & 0x0F) == ACT_FLAG) ? 1u : 0u;
@@ -415,6 +424,7 @@ k3_srt(SrtParams P, int F, const uint32_t* __restrict__ chunk_range /*[2][F+1]*/
     for (int b = tid; b < B; b += nt) slot_out[b] = ((act_out[b] & 0x0F) == ACT_FLAG) ? s_sz[b] : kSkip;
     __syncthreads();
     const uint32_t rec_base = s_rec_base;
+    K3_TICK(2);
 
     // scatter offsets, map cloud: every bin + complement (mode 0) or flagged bins only (mode 1)
     uint32_t* dsm = dst_start + ((size_t)0 * F + f) * (B + 2);
@@ -431,6 +441,7 @@ k3_srt(SrtParams P, int F, const uint32_t* __restrict__ chunk_range /*[2][F+1]*/
     }
     if (tid == 0) dsm[B + 1] = tot_m;
     __syncthreads();
+    K3_TICK(3);
     // flagged-bin records for K4
     for (int b = tid; b < B; b += nt) {
         if ((act_out[b] & 0x0F) == ACT_FLAG) {
@@ -449,12 +460,15 @@ k3_srt(SrtParams P, int F, const uint32_t* __restrict__ chunk_range /*[2][F+1]*/
         }
     }
     __syncthreads();
+    K3_TICK(4);
     // query cloud: all binned points (mode 0) or nothing (mode 1)
     for (int b = tid; b <= B; b += nt) s_sz[b] = (P.scatter_mode == 0 && b < B) ? cq[b] : 0u;
     __syncthreads();
     const uint32_t tot_q = block_excl_scan(s_sz, s_sz, B + 1, s_part);
     for (int b = tid; b <= B; b += nt) dsq[b] = (P.scatter_mode == 0 && b < B) ? s_sz[b] : kSkip;
     if (tid == 0) dsq[B + 1] = tot_q;
+    K3_TICK(5);
+#undef K3_TICK
 }
 
 size_t k3_smem_bytes(int B) { return sizeof(uint32_t) * ((size_t)B + 2 + 34) + (size_t)B + 16; }
@@ -523,36 +537,51 @@ k2_scatter(const ChunkDesc* __restrict__ chunks, uint32_t chunk_base, int F, con
 // rows into absolute destinations (dst_start + earlier chunks + earlier warps); pass B re-walks the sub-range in order.
 // W x more parallelism per chunk than the one-warp kernel; needs W*(B+1)*4 bytes of shared memory.
 template <int W>
-__global__ void __launch_bounds__(W * 32)
+__global__ void __launch_bounds__(W * 32, 4)      // 4 CTAs per SM: the chunking aims at one wave of sm_count * 4 CTAs
 k2_scatter_mw(const ChunkDesc* __restrict__ chunks, uint32_t chunk_base, const uint16_t* __restrict__ bin_ids,
               const float4* __restrict__ pts, const uint32_t* __restrict__ ch_cnt, const uint32_t* __restrict__ dst_start,
               float4* __restrict__ out_pts, uint32_t* __restrict__ out_src, int B) {
-    extern __shared__ uint32_t s_tab[];   // [W][B+1]
+    extern __shared__ uint32_t s_tab[];   // [W][B+1] per-warp counters / destinations, then [B+1] the frame's dst_start row
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t row = chunk_base + blockIdx.x;
     const ChunkDesc cd = chunks[row];
     const uint32_t* ds   = dst_start + (size_t)cd.frame * (B + 2);
     const uint32_t* pref = ch_cnt + (size_t)row * (B + 1);
     uint32_t* mine = s_tab + (size_t)warp * (B + 1);
+    uint32_t* s_ds = s_tab + (size_t)W * (B + 1);
     for (int i = tid; i < W * (B + 1); i += W * 32) s_tab[i] = 0u;
+    for (int b = tid; b <= B; b += W * 32) s_ds[b] = ds[b];
     __syncthreads();
     const uint32_t sub = (((cd.len + W - 1) / W) + 31u) & ~31u;
     const uint32_t s0 = min(cd.len, (uint32_t)warp * sub), s1 = min(cd.len, s0 + sub);
-    for (uint32_t i0 = s0; i0 < s1; i0 += 32) {
-        const uint32_t i = i0 + lane;
-        const bool valid = i < s1;
-        const unsigned vmask = __ballot_sync(FULL_MASK, valid);
-        if (valid) {
-            const uint16_t id = bin_ids[cd.begin + i];
-            const int key = (id == kNoBin16) ? B : (int)id;
-            const unsigned peers = __match_any_sync(vmask, key);
-            if (lane == __ffs(peers) - 1) mine[key] += __popc(peers);
+    const uint16_t* ids = bin_ids + cd.begin;
+    // Both passes walk the sub-range 256 points (8 steps of 32) at a time; the bin ids of the next block are loaded while
+    // the current one is processed, so that no step waits on global memory.  Only points of scattered bins (dst_start !=
+    // kSkip: every bin in cloud mode, the flagged ~10 % in mask mode) take part in the match_any ranking.
+    uint16_t cur[8], nxt[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const uint32_t i = s0 + (uint32_t)u * 32u + lane; cur[u] = (i < s1) ? ids[i] : kNoBin16; }
+    for (uint32_t i0 = s0; i0 < s1; i0 += 256u) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const uint32_t i = i0 + 256u + (uint32_t)u * 32u + lane; nxt[u] = (i < s1) ? ids[i] : kNoBin16; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const uint32_t i = i0 + (uint32_t)u * 32u + lane;
+            const int  key  = (cur[u] == kNoBin16) ? B : (int)cur[u];
+            const bool take = (i < s1) && (s_ds[key] != kSkip);
+            const unsigned tmask = __ballot_sync(FULL_MASK, take);
+            if (take) {
+                const unsigned peers = __match_any_sync(tmask, key);
+                if (lane == __ffs(peers) - 1) mine[key] += __popc(peers);
+            }
+            __syncwarp();
         }
-        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
     }
     __syncthreads();
     for (int b = tid; b <= B; b += W * 32) {
-        const uint32_t d = ds[b];
+        const uint32_t d = s_ds[b];
         uint32_t run = (d == kSkip) ? 0u : d + pref[b];
 #pragma unroll
         for (int w = 0; w < W; ++w) {
@@ -563,24 +592,47 @@ k2_scatter_mw(const ChunkDesc* __restrict__ chunks, uint32_t chunk_base, const u
     }
     __syncthreads();
     const uint32_t local0 = cd.begin - cd.frame_begin;
-    for (uint32_t i0 = s0; i0 < s1; i0 += 32) {
-        const uint32_t i = i0 + lane;
-        const bool valid = i < s1;
-        const unsigned vmask = __ballot_sync(FULL_MASK, valid);
-        if (valid) {
-            const uint16_t id = bin_ids[cd.begin + i];
-            const int key = (id == kNoBin16) ? B : (int)id;
-            const unsigned peers = __match_any_sync(vmask, key);
-            const uint32_t base = mine[key];
-            __syncwarp(vmask);
-            if (base != kSkip) {
+    const float4* src = pts + cd.begin;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const uint32_t i = s0 + (uint32_t)u * 32u + lane; cur[u] = (i < s1) ? ids[i] : kNoBin16; }
+    for (uint32_t i0 = s0; i0 < s1; i0 += 256u) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const uint32_t i = i0 + 256u + (uint32_t)u * 32u + lane; nxt[u] = (i < s1) ? ids[i] : kNoBin16; }
+        uint32_t dst[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const uint32_t i = i0 + (uint32_t)u * 32u + lane;
+            const int      key  = (cur[u] == kNoBin16) ? B : (int)cur[u];
+            const uint32_t base = (i < s1) ? mine[key] : kSkip;
+            const bool     take = base != kSkip;
+            const unsigned tmask = __ballot_sync(FULL_MASK, take);      // also orders the reads of mine[] before the updates below
+            dst[u] = kSkip;
+            if (take) {
+                const unsigned peers = __match_any_sync(tmask, key);
                 if (lane == __ffs(peers) - 1) mine[key] = base + __popc(peers);
-                const size_t o = (size_t)cd.frame_begin + base + __popc(peers & ((1u << lane) - 1u));
-                out_pts[o] = pts[cd.begin + i];
-                out_src[o] = local0 + i;
+                dst[u] = base + __popc(peers & ((1u << lane) - 1u));
+            }
+            __syncwarp();
+        }
+        // the copies of the block, four at a time: all loads of a group in flight before its first store
+#pragma unroll
+        for (int g = 0; g < 8; g += 4) {
+            float4 pv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (dst[g + u] != kSkip) pv[u] = src[i0 + (uint32_t)(g + u) * 32u + lane];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (dst[g + u] != kSkip) {
+                    const size_t o = (size_t)cd.frame_begin + dst[g + u];
+                    out_pts[o] = pv[u];
+                    out_src[o] = local0 + i0 + (uint32_t)(g + u) * 32u + lane;
+                }
             }
         }
-        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
     }
 }
 
@@ -589,7 +641,7 @@ cudaError_t launch_k2(cudaStream_t st, const ChunkDesc* chunks, uint32_t chunk_b
                       float4* out_pts, uint32_t* out_src, int B) {
     if (n_chunks == 0) return cudaSuccess;
     constexpr int W = 8;
-    const size_t smem_mw = sizeof(uint32_t) * (size_t)W * (B + 1);
+    const size_t smem_mw = sizeof(uint32_t) * (size_t)(W + 1) * (B + 1);
     cudaError_t e;
     if (smem_mw <= 200 * 1024) {
         auto kern = k2_scatter_mw<W>;
@@ -1381,12 +1433,17 @@ k4_rgpf(GpfParams P, FlagRec* __restrict__ recs, uint32_t* __restrict__ queue, c
         const uint32_t w = bucket_list[(size_t)bk * rec_capacity + i];
         FlagRec& rc = recs[w];
         const uint32_t n = rc.n_points;
-        if (n <= smem_cap_points)
+        if constexpr (G <= 256) {
+            // classes A and B: the launch sizes the slices for the class maximum (kClassAMax / kClassBMax), so the bin always fits
             k4_process_bin<G, true>(P, rc, smem_raw + (size_t)grp * slice_bytes, s_prd[grp], s_cnt[grp], sh[grp], sorted_pts, sorted_src, in_pts,
                                     frame_off, part_pts, keep_mask, ground_mask, frame_rejected, fence);
-        else
+        } else if (n <= smem_cap_points) {
+            k4_process_bin<G, true>(P, rc, smem_raw + (size_t)grp * slice_bytes, s_prd[grp], s_cnt[grp], sh[grp], sorted_pts, sorted_src, in_pts,
+                                    frame_off, part_pts, keep_mask, ground_mask, frame_rejected, fence);
+        } else {
             k4_process_bin<G, false>(P, rc, gscratch + (size_t)rc.src_begin * 24u, s_prd[grp], s_cnt[grp], sh[grp], sorted_pts, sorted_src, in_pts,
                                      frame_off, part_pts, keep_mask, ground_mask, frame_rejected, fence);
+        }
     }
 }
 
@@ -1401,6 +1458,7 @@ static cudaError_t launch_k4_class(cudaStream_t st, const GpfParams& P, FlagRec*
     constexpr uint32_t per_pt = (G == 32) ? 17u : 21u;
     const uint32_t slice = (smem_bytes / NG) & ~15u;
     const uint32_t cap = (slice - 32) / per_pt;
+    if ((G == 32 && cap < kClassAMax) || (G == 256 && cap < kClassBMax)) return cudaErrorInvalidConfiguration;   // A / B have no scratch path
     auto kern = k4_rgpf<THREADS, G>;
     cudaError_t e = ensure_dyn_smem(kern, smem_bytes);
     if (e != cudaSuccess) return e;

@@ -146,6 +146,9 @@ int erasor_get_frame_stats(erasor_handle_t h, uint32_t* n_flagged_bins, uint32_t
 /* per flagged bin of the last run: point count and SM cycles per R-GPF phase (load + index sort, z sort, seeds,
  * accumulate, SVD + plane, classify + compact, outputs) plus the Jacobi sweep count in slot 7.  *n in: capacity, out: count. */
 int erasor_get_rgpf_profile(erasor_handle_t h, uint32_t* n_points, uint32_t* prof8, size_t* n);
+/* SM cycles per phase of the SRT kernel (K3), frame 0 of the last run: status passes, chunk-row prefixes, flagged-bin scan +
+ * record base, map scatter offsets, records + R-GPF queue, query scatter offsets; slots 6-7 reserved (host array of 8). */
+int erasor_get_srt_profile(erasor_handle_t h, uint32_t* cycles8);
 /* number of kernels this library launched on the handle since creation */
 uint64_t erasor_kernel_launch_count(erasor_handle_t h);
 /* CUDA-event time (ms) spent in the binning kernel (K1) since the last reset, and its launch count */

@@ -17,3 +17,4 @@ for lo, hi in ((0, 128), (128, 512), (512, 1024), (1024, 4096)):
     sel = (npts > lo) & (npts <= hi)
     if sel.any():
         print(f"n in ({lo},{hi}]: {sel.sum()} bins; mean cycles per phase:", {k: int(prof[sel, i].mean()) for i, k in enumerate(names)}, "total", int(prof[sel, :7].sum(1).mean()), "max total", int(prof[sel, :7].sum(1).max()))
+print("K3 phase cycles (frame 0): status, chunk prefix, flag scan+base, map offsets, records+queue, query offsets:", h.srt_profile()[:6].tolist())
