@@ -81,6 +81,20 @@ __device__ __forceinline__ void k1_aggregate(int key, uint32_t zenc, int lane, u
     const int      prev  = __shfl_up_sync(FULL_MASK, key, 1);
     const bool     head  = (lane == 0) || (key != prev);
     const unsigned heads = __ballot_sync(FULL_MASK, head);
+    if (__popc(heads) >= 8) {
+        // incoherent input (a VoI cropped from an arbitrarily ordered map): runs are too short for the scan to pay --
+        // three shared-memory atomics per lane, at most a few lanes per address
+        if (key >= 0) {
+            if (key < B) {
+                atomicMin(&s_mn[key], zenc);
+                atomicMax(&s_mx[key], zenc);
+                atomicAdd(&s_cnt[key], 1u);
+            } else {
+                atomicAdd(&s_cnt[B], 1u);
+            }
+        }
+        return;
+    }
     const unsigned above = heads & ~((2u << lane) - 1u);      // run heads at lanes > lane (lane 31: mask 0)
     const int      e     = above ? (__ffs(above) - 1) : 32;   // my run is [.., e)
     uint32_t mn = zenc, mx = zenc;
@@ -308,11 +322,12 @@ k3_srt(SrtParams P, int F, const uint32_t* __restrict__ chunk_range /*[2][F+1]*/
         // pass 1 (erasor.cpp:448-486)
         for (int b = tid; b < B; b += nt) {
             const uint32_t mc = cm[b], qc = cq[b];
+            const uint32_t zmx_m = mxm[b], zmn_m = mnm[b], zmx_q = mxq[b], zmn_q = mnq[b];   // one round trip for all six tables
             uint8_t st = ST_LITTLE;
             if (mc != 0u && !(min_pts_neg || qc < (uint32_t)P.minimum_num_pts)) {
                 // empty curr bin keeps the reference's sentinels: max_h = -INF, min_h = +INF (erasor.h:3)
-                const double map_dh  = (double)ordered_to_float(mxm[b]) - (double)ordered_to_float(mnm[b]);
-                const double curr_dh = (qc != 0u) ? (double)ordered_to_float(mxq[b]) - (double)ordered_to_float(mnq[b])
+                const double map_dh  = (double)ordered_to_float(zmx_m) - (double)ordered_to_float(zmn_m);
+                const double curr_dh = (qc != 0u) ? (double)ordered_to_float(zmx_q) - (double)ordered_to_float(zmn_q)
                                                   : (-10000000000000.0 - 10000000000000.0);
                 const double ratio   = std_min_d(map_dh / curr_dh, curr_dh / map_dh);
                 if (qc != 0u) {
@@ -416,14 +431,13 @@ k3_srt(SrtParams P, int F, const uint32_t* __restrict__ chunk_range /*[2][F+1]*/
     for (int b = tid; b < B; b += nt) s_sz[b] = ((act_out[b] & 0x0F) == ACT_FLAG) ? 1u : 0u;
     __syncthreads();
     const uint32_t nflag = block_excl_scan(s_sz, s_sz, B, s_part);
+    uint32_t rec_base_reg = 0u;      // thread 0: the atomic's round trip overlaps the map-offset scan below
     if (tid == 0) {
         n_flagged[f] = nflag;
-        s_rec_base   = nflag ? atomicAdd(n_recs, nflag) : 0u;
-        frame_rec_base[f] = s_rec_base;
+        rec_base_reg = nflag ? atomicAdd(n_recs, nflag) : 0u;
     }
     for (int b = tid; b < B; b += nt) slot_out[b] = ((act_out[b] & 0x0F) == ACT_FLAG) ? s_sz[b] : kSkip;
     __syncthreads();
-    const uint32_t rec_base = s_rec_base;
     K3_TICK(2);
 
     // scatter offsets, map cloud: every bin + complement (mode 0) or flagged bins only (mode 1)
@@ -439,8 +453,9 @@ k3_srt(SrtParams P, int F, const uint32_t* __restrict__ chunk_range /*[2][F+1]*/
         const bool take = (P.scatter_mode == 0) || (b < B && (act_out[b] & 0x0F) == ACT_FLAG);
         dsm[b] = take ? s_sz[b] : kSkip;
     }
-    if (tid == 0) dsm[B + 1] = tot_m;
+    if (tid == 0) { dsm[B + 1] = tot_m; s_rec_base = rec_base_reg; frame_rec_base[f] = rec_base_reg; }
     __syncthreads();
+    const uint32_t rec_base = s_rec_base;
     K3_TICK(3);
     // flagged-bin records for K4
     for (int b = tid; b < B; b += nt) {
@@ -462,11 +477,16 @@ k3_srt(SrtParams P, int F, const uint32_t* __restrict__ chunk_range /*[2][F+1]*/
     __syncthreads();
     K3_TICK(4);
     // query cloud: all binned points (mode 0) or nothing (mode 1)
-    for (int b = tid; b <= B; b += nt) s_sz[b] = (P.scatter_mode == 0 && b < B) ? cq[b] : 0u;
-    __syncthreads();
-    const uint32_t tot_q = block_excl_scan(s_sz, s_sz, B + 1, s_part);
-    for (int b = tid; b <= B; b += nt) dsq[b] = (P.scatter_mode == 0 && b < B) ? s_sz[b] : kSkip;
-    if (tid == 0) dsq[B + 1] = tot_q;
+    if (P.scatter_mode == 0) {
+        for (int b = tid; b <= B; b += nt) s_sz[b] = (b < B) ? cq[b] : 0u;
+        __syncthreads();
+        const uint32_t tot_q = block_excl_scan(s_sz, s_sz, B + 1, s_part);
+        for (int b = tid; b <= B; b += nt) dsq[b] = (b < B) ? s_sz[b] : kSkip;
+        if (tid == 0) dsq[B + 1] = tot_q;
+    } else {
+        for (int b = tid; b <= B; b += nt) dsq[b] = kSkip;
+        if (tid == 0) dsq[B + 1] = 0u;
+    }
     K3_TICK(5);
 #undef K3_TICK
 }
