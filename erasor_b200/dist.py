@@ -33,12 +33,13 @@ def fold_masks(n_global: int, voi_indices: Sequence[torch.Tensor], keep_masks: S
     return keep_g
 
 
-def allgather_and(keep_g: torch.Tensor) -> torch.Tensor:
-    """The path's single collective: all-gather the per-rank masks and AND them (every rank gets the final mask)."""
+def allgather_and(keep_g: torch.Tensor, gather_buf: torch.Tensor | None = None) -> torch.Tensor:
+    """The path's single collective: all-gather the per-rank masks and AND them (every rank gets the final mask).
+    gather_buf: optional reusable (world, n) uint8 buffer (a streaming caller double-buffers it)."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return keep_g
     world = dist.get_world_size()
-    buf = torch.empty((world, keep_g.numel()), dtype=torch.uint8, device=keep_g.device)
+    buf = gather_buf if gather_buf is not None else torch.empty((world, keep_g.numel()), dtype=torch.uint8, device=keep_g.device)
     dist.all_gather_into_tensor(buf.view(-1), keep_g.contiguous())
     return buf.amin(dim=0)
 
