@@ -302,7 +302,7 @@ def run_ours(args):
 
     from erasor_b200 import dist as edist
 
-    # Every step folds its frames' masks onto keep_g (library kernel, no communication).  The job's single collective -- the
+    # Every step folds its frames' masks onto keep_g (library kernel in the step's own submission, no communication).  The job's single collective -- the
     # all-gather of the folded masks -- runs once after the last step of a timed block, inside the timed region.  Steps never
     # contain a collective, so ranks may run different numbers of untimed steps (the clock-sampling warm loop on rank 0).
     def fold(keep_dev):
@@ -312,16 +312,14 @@ def run_ours(args):
         with torch.cuda.stream(xs):
             final_keep[0] = edist.allgather_and(keep_g, gather_buf)        # the single NCCL collective (no-op at N=1)
 
+    fold_args = (gidx.data_ptr(), keep_g.data_ptr(), NG) if world > 1 else None     # N > 1: erasor_process_frames_fold (one submission)
+
     def step_resident(i):
         c = i % N_INPUT_COPIES
-        h.process_frames_ptr(dM[c].data_ptr(), mo, dQ[c].data_ptr(), qo, dK.data_ptr(), capi.PTR_DEVICE)
-        if world > 1:
-            fold(dK)
+        h.process_frames_ptr(dM[c].data_ptr(), mo, dQ[c].data_ptr(), qo, dK.data_ptr(), capi.PTR_DEVICE, fold_args)
 
     def step_host(i):
-        h.process_frames_ptr(hM.data_ptr(), mo, hQ.data_ptr(), qo, hK.data_ptr(), capi.PTR_HOST)
-        if world > 1:
-            fold(dK)
+        h.process_frames_ptr(hM.data_ptr(), mo, hQ.data_ptr(), qo, hK.data_ptr(), capi.PTR_HOST, fold_args)
 
     def barrier():
         if world > 1:

@@ -25,7 +25,7 @@ EXPORTS = [
     "erasor_create", "erasor_destroy", "erasor_last_error", "erasor_abi_version", "erasor_stream", "erasor_synchronize",
     "erasor_set_inputs", "erasor_compare", "erasor_get_output_sizes", "erasor_get_static_estimate", "erasor_get_outliers",
     "erasor_get_max_range", "erasor_get_bins", "erasor_get_status", "erasor_get_planes", "erasor_get_static_mask",
-    "erasor_get_fence_counts", "erasor_process_frames", "erasor_fold_keep_masks", "erasor_get_frame_stats", "erasor_kernel_launch_count",
+    "erasor_get_fence_counts", "erasor_process_frames", "erasor_process_frames_fold", "erasor_fold_keep_masks", "erasor_get_frame_stats", "erasor_kernel_launch_count",
     "erasor_get_kernel_time_ms", "erasor_reset_kernel_times", "erasor_get_rgpf_profile", "erasor_get_srt_profile",
     "erasor_updater_create", "erasor_updater_destroy", "erasor_updater_reset", "erasor_updater_last_error", "erasor_updater_process_node",
     "erasor_updater_map_size", "erasor_updater_get_cloud", "erasor_updater_save_static_map", "erasor_updater_voxelize",
@@ -78,6 +78,8 @@ def _load():
     L.erasor_get_static_mask.argtypes = [c_void_p, POINTER(c_uint8), POINTER(c_uint8)]
     L.erasor_get_fence_counts.argtypes = [c_void_p, POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint64)]
     L.erasor_process_frames.argtypes = [c_void_p, c_void_p, POINTER(c_uint64), c_void_p, POINTER(c_uint64), c_int, c_void_p, c_int]
+    L.erasor_process_frames_fold.argtypes = [c_void_p, c_void_p, POINTER(c_uint64), c_void_p, POINTER(c_uint64), c_int, c_void_p, c_int,
+                                             c_void_p, c_void_p, c_size_t]
     L.erasor_fold_keep_masks.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t]
     L.erasor_get_frame_stats.argtypes = [c_void_p, POINTER(c_uint32), POINTER(c_uint32)]
     L.erasor_kernel_launch_count.restype = c_uint64
@@ -262,7 +264,8 @@ class Handle:
         self.n_frames = F
         return keep
 
-    def process_frames_ptr(self, map_ptr: int, map_offsets: np.ndarray, query_ptr: int, query_offsets: np.ndarray, keep_ptr: int, ptr_kind: int):
+    def process_frames_ptr(self, map_ptr: int, map_offsets: np.ndarray, query_ptr: int, query_offsets: np.ndarray, keep_ptr: int, ptr_kind: int,
+                           fold=None):
         """Raw-pointer batch call (device tensors or pinned host memory); offsets are host uint64 arrays.
         The ctypes views of the offset arrays are cached per array object so that a caller streaming equally-shaped
         batches pays one foreign call per step and nothing else."""
@@ -273,7 +276,10 @@ class Handle:
             qo = np.ascontiguousarray(query_offsets, dtype=np.uint64)
             c = (key, mo, qo, mo.ctypes.data_as(POINTER(c_uint64)), qo.ctypes.data_as(POINTER(c_uint64)), len(mo) - 1)
             self._off_cache = c
-        rc = self.L.erasor_process_frames(self.h, map_ptr, c[3], query_ptr, c[4], c[5], keep_ptr, ptr_kind)
+        if fold is None:
+            rc = self.L.erasor_process_frames(self.h, map_ptr, c[3], query_ptr, c[4], c[5], keep_ptr, ptr_kind)
+        else:       # fold = (voi_index device ptr, global_keep device ptr, n_global): process + fold in one submission
+            rc = self.L.erasor_process_frames_fold(self.h, map_ptr, c[3], query_ptr, c[4], c[5], keep_ptr, ptr_kind, fold[0], fold[1], fold[2])
         if rc != OK:
             self._ck(rc)
         self.n_frames = c[5]

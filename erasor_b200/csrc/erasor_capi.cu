@@ -103,7 +103,8 @@ struct erasor_ctx {
     std::vector<uint64_t> map_off, qry_off;
     int      desc_mode = -1;                   // mode the uploaded chunk descriptors were built for (-1: none)
     uint64_t desc_epoch = 0;                   // bumped whenever the descriptors are rebuilt (invalidates cached graphs)
-    struct StepGraph { const void* map; const void* qry; void* keep; int kind; uint64_t epoch, alloc; cudaGraphExec_t exec; };
+    struct StepGraph { const void* map; const void* qry; void* keep; int kind; uint64_t epoch, alloc; cudaGraphExec_t exec;
+                       const void* fold_index; const void* fold_global; size_t fold_n; };
     std::vector<StepGraph> graphs;             // captured mask-mode steps, one per (pointers, geometry)
     bool     use_graphs = true;
     uint64_t graph_kernel_nodes = 0;
@@ -669,8 +670,12 @@ int erasor_get_fence_counts(erasor_handle_t h, uint64_t* negzero_points, uint64_
     return ERASOR_OK;
 }
 
-int erasor_process_frames(erasor_handle_t h, const float* map_xyzi, const uint64_t* map_offsets, const float* query_xyzi,
-                          const uint64_t* query_offsets, int n_frames, uint8_t* keep_mask, int ptr_kind) {
+namespace {
+// erasor_process_frames, optionally followed (same stream / same graph, before the host synchronises) by the fold of the
+// fresh masks onto the global map
+int process_frames_impl(erasor_handle_t h, const float* map_xyzi, const uint64_t* map_offsets, const float* query_xyzi,
+                        const uint64_t* query_offsets, int n_frames, uint8_t* keep_mask, int ptr_kind,
+                        const uint32_t* fold_index, uint8_t* fold_global, size_t fold_n_global) {
     if (!h || !map_offsets || !query_offsets || !keep_mask) { if (h) h->err = "null argument"; return ERASOR_E_INVALID; }
     CK(cudaSetDevice(h->device));
     h->stage = 0;
@@ -688,6 +693,10 @@ int erasor_process_frames(erasor_handle_t h, const float* map_xyzi, const uint64
         if (h->NM) CK(cudaMemsetAsync(d_keep, 1, h->NM, h->stream));
         if ((r = run_k1(h, 1))) return r;
         if ((r = run_compare(h, h->p.version, 1, d_keep, nullptr))) return r;
+        if (fold_global) {
+            h->launches++;
+            CK(launch_fold_keep(h->stream, d_keep, fold_index, h->NM, fold_global, fold_n_global));
+        }
         if (ptr_kind != ERASOR_PTR_DEVICE && h->NM)
             CK(cudaMemcpyAsync(keep_mask, d_keep, h->NM, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaMemcpyAsync(&h->n_recs_host, h->d_nrecs.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -712,7 +721,8 @@ int erasor_process_frames(erasor_handle_t h, const float* map_xyzi, const uint64
     if (graphable) {
         cudaGraphExec_t exec = nullptr;
         for (auto& g : h->graphs)
-            if (g.map == map_xyzi && g.qry == query_xyzi && g.keep == keep_mask && g.kind == ptr_kind && g.epoch == h->desc_epoch && g.alloc == g_alloc_epoch) exec = g.exec;
+            if (g.map == map_xyzi && g.qry == query_xyzi && g.keep == keep_mask && g.kind == ptr_kind && g.epoch == h->desc_epoch && g.alloc == g_alloc_epoch &&
+                g.fold_index == fold_index && g.fold_global == fold_global && g.fold_n == fold_n_global) exec = g.exec;
         if (!exec) {
             // drop graphs of older geometries, bound the cache
             for (size_t i = 0; i < h->graphs.size();) {
@@ -729,7 +739,7 @@ int erasor_process_frames(erasor_handle_t h, const float* map_xyzi, const uint64
             if (rc == ERASOR_OK && ce == cudaSuccess && graph) {
                 ce = cudaGraphInstantiate(&exec, graph, 0);
                 cudaGraphDestroy(graph);
-                if (ce == cudaSuccess) h->graphs.push_back(erasor_ctx::StepGraph{map_xyzi, query_xyzi, keep_mask, ptr_kind, h->desc_epoch, g_alloc_epoch, exec});
+                if (ce == cudaSuccess) h->graphs.push_back(erasor_ctx::StepGraph{map_xyzi, query_xyzi, keep_mask, ptr_kind, h->desc_epoch, g_alloc_epoch, exec, fold_index, fold_global, fold_n_global});
                 else exec = nullptr;
             } else {
                 if (graph) cudaGraphDestroy(graph);
@@ -750,6 +760,20 @@ int erasor_process_frames(erasor_handle_t h, const float* map_xyzi, const uint64
     CK(cudaStreamSynchronize(h->stream));
     if (h->n_recs_host > h->rec_capacity) { h->err = "flagged-bin records overflowed; split the batch"; return ERASOR_E_CAPACITY; }
     return ERASOR_OK;
+}
+}  // namespace
+
+int erasor_process_frames(erasor_handle_t h, const float* map_xyzi, const uint64_t* map_offsets, const float* query_xyzi,
+                          const uint64_t* query_offsets, int n_frames, uint8_t* keep_mask, int ptr_kind) {
+    return process_frames_impl(h, map_xyzi, map_offsets, query_xyzi, query_offsets, n_frames, keep_mask, ptr_kind, nullptr, nullptr, 0);
+}
+
+int erasor_process_frames_fold(erasor_handle_t h, const float* map_xyzi, const uint64_t* map_offsets, const float* query_xyzi,
+                               const uint64_t* query_offsets, int n_frames, uint8_t* keep_mask, int ptr_kind,
+                               const uint32_t* voi_index, uint8_t* global_keep, size_t n_global) {
+    if (!h) return ERASOR_E_INVALID;
+    if (!voi_index || !global_keep) { h->err = "null fold argument"; return ERASOR_E_INVALID; }
+    return process_frames_impl(h, map_xyzi, map_offsets, query_xyzi, query_offsets, n_frames, keep_mask, ptr_kind, voi_index, global_keep, n_global);
 }
 
 // Multi-GPU exchange helper: fold the per-frame keep masks of erasor_process_frames onto the global

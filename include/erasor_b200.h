@@ -139,6 +139,12 @@ int erasor_process_frames(erasor_handle_t h, const float* map_xyzi, const uint64
  * rejected it): global_keep[] = 1, then global_keep[voi_index[i]] = 0 where keep_mask[i] == 0.  DEVICE pointers; asynchronous
  * on the handle's stream (erasor_stream).  The all-gather of the folded masks is the path's single collective. */
 int erasor_fold_keep_masks(erasor_handle_t h, const uint8_t* keep_mask, const uint32_t* voi_index, size_t n, uint8_t* global_keep, size_t n_global);
+/* erasor_process_frames followed by erasor_fold_keep_masks of the fresh masks in the same submission (same stream, same CUDA
+ * graph, before the host synchronises): what a rank of the frame-sharded job runs per batch.  voi_index / global_keep: DEVICE. */
+int erasor_process_frames_fold(erasor_handle_t h, const float* map_xyzi, const uint64_t* map_offsets,
+                               const float* query_xyzi, const uint64_t* query_offsets, int n_frames,
+                               uint8_t* keep_mask, int ptr_kind,
+                               const uint32_t* voi_index, uint8_t* global_keep, size_t n_global);
 /* per-frame counters of the last erasor_process_frames: flagged bins and rejected points (host arrays of n_frames) */
 int erasor_get_frame_stats(erasor_handle_t h, uint32_t* n_flagged_bins, uint32_t* n_rejected_points);
 

@@ -349,3 +349,39 @@ def test_rgpf_sort_classes_and_ties(capi, oracle_mod, z_kind, n_ground):
     oarr, _ = o.cloud(o.ARRANGED)
     assert arr.shape == oarr.shape and np.array_equal(arr.view(np.uint32), oarr.view(np.uint32))
     h.close()
+
+
+def test_process_frames_fold_matches_separate_calls(capi, small_workload):
+    """erasor_process_frames_fold == erasor_process_frames followed by erasor_fold_keep_masks (device and pinned-host clouds,
+    repeated calls so that the cached CUDA graph is replayed)."""
+    import torch
+    p = P.preset("seq_05").replace(skip_voxelize=1)
+    fr = [_frame(small_workload, i, p) for i in (1, 3, 4)]
+    mo = np.cumsum([0] + [len(m) for m, _ in fr]).astype(np.uint64)
+    qo = np.cumsum([0] + [len(q) for _, q in fr]).astype(np.uint64)
+    M = np.concatenate([m for m, _ in fr]); Q = np.concatenate([q for _, q in fr])
+    n_global = 50000
+    rng = np.random.default_rng(11)
+    idx = rng.integers(0, n_global, len(M)).astype(np.uint32)
+    h = capi.Handle(p)
+    dM, dQ = torch.from_numpy(M).cuda(), torch.from_numpy(Q).cuda()
+    dI = torch.from_numpy(idx.view(np.int32)).cuda()
+    keep_a = torch.empty(len(M), dtype=torch.uint8, device="cuda"); keep_b = torch.empty_like(keep_a)
+    g_a = torch.zeros(n_global, dtype=torch.uint8, device="cuda"); g_b = torch.zeros_like(g_a)
+    h.process_frames_ptr(dM.data_ptr(), mo, dQ.data_ptr(), qo, keep_a.data_ptr(), capi.PTR_DEVICE)
+    h.fold_keep_masks(keep_a.data_ptr(), dI.data_ptr(), len(M), g_a.data_ptr(), n_global)
+    torch.cuda.synchronize()
+    for _ in range(3):
+        g_b.zero_()
+        h.process_frames_ptr(dM.data_ptr(), mo, dQ.data_ptr(), qo, keep_b.data_ptr(), capi.PTR_DEVICE, (dI.data_ptr(), g_b.data_ptr(), n_global))
+        torch.cuda.synchronize()
+        assert torch.equal(keep_a, keep_b) and torch.equal(g_a, g_b)
+    assert int((g_a == 0).sum().item()) > 0
+    hM, hQ = torch.from_numpy(M).pin_memory(), torch.from_numpy(Q).pin_memory()
+    hK = torch.empty(len(M), dtype=torch.uint8).pin_memory()
+    for _ in range(2):
+        g_b.zero_()
+        h.process_frames_ptr(hM.data_ptr(), mo, hQ.data_ptr(), qo, hK.data_ptr(), capi.PTR_HOST, (dI.data_ptr(), g_b.data_ptr(), n_global))
+        torch.cuda.synchronize()
+        assert torch.equal(keep_a.cpu(), hK) and torch.equal(g_a, g_b)
+    h.close()
