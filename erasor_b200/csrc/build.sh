@@ -21,3 +21,5 @@ echo "built: $(ls ../_lib)"
 # C++ host-class demo (include/erasor/erasor.hpp over the C ABI)
 g++ -std=c++17 -O2 -o ../_lib/erasor_cpp_demo ../../examples/erasor_cpp_demo.cpp -L../_lib -lerasor_b200 -Wl,-rpath,'$ORIGIN' \
     -L/usr/local/cuda/lib64 -Wl,-rpath,/usr/local/cuda/lib64
+# micro-benchmark behind profiles/r01/microbench_match_any.txt
+$NVCC $ARCH -O3 -o ../_lib/mb_match ../../scripts/mb_match.cu
