@@ -1214,17 +1214,29 @@ __device__ __forceinline__ void k4_process_bin(const GpfParams& P, FlagRec& rc, 
     float*    Y   = X + n;
     float*    Z   = Y + n;
     uint8_t*  FLG = reinterpret_cast<uint8_t*>(Z + n);
-    constexpr int TILE = (G == 32) ? 64 : 256;
-    float*    PRD = prd;                          // 9 x (TILE + 1) floats, always shared memory
+    constexpr int HT = (G == 32) ? 32 : 128;      // half tile of the covariance accumulation
+    constexpr int PB = 9 * (HT + 1);
+    float*    PRD = prd;                          // two buffers of 9 x (HT + 1) floats, always shared memory
     long long t_prev = clock64();
     uint32_t prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define K4_TICK(slot) do { const long long t_now__ = clock64(); prof[slot] += (uint32_t)(t_now__ - t_prev); t_prev = t_now__; } while (0)
 
     // K2 placed the bin's points contiguously in source order (all bins in cloud mode, flagged bins only in mask mode)
-    for (uint32_t i = tid; i < n; i += G) {
-        const float4 p = sorted_pts[src_begin + i];
-        X[i] = p.x; Y[i] = p.y; Z[i] = p.z;
-        if (G > 256) ORD[i] = i;
+    for (uint32_t i0 = tid; i0 < n; i0 += 4u * G) {
+        float4 p[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {                      // four independent loads in flight per thread
+            const uint32_t i = i0 + (uint32_t)u * G;
+            if (i < n) p[u] = sorted_pts[src_begin + i];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t i = i0 + (uint32_t)u * G;
+            if (i < n) {
+                X[i] = p[u].x; Y[i] = p[u].y; Z[i] = p[u].z;
+                if (G > 256) ORD[i] = i;
+            }
+        }
     }
     group_sync<G>();
     K4_TICK(0);
@@ -1286,41 +1298,78 @@ __device__ __forceinline__ void k4_process_bin(const GpfParams& P, FlagRec& rc, 
     for (int it = 0; it < P.iters; ++it) {
         // ---- estimate_plane_ over ORD[0..m) (erasor.cpp:183-198) ----
         // pcl::computeMeanAndCovarianceMatrix: nine float accumulators walked in list order.  The nine products of a
-        // tile of list elements are computed by the whole group into shared memory (row stride TILE+1: conflict-free
-        // for the nine summing lanes), then lane L of warp 0 adds row L in order: the serial FADD chain is fed by
-        // independent, prefetchable shared-memory loads (4-5 cycles per element instead of a dependent gather).
+        // half tile of list elements are staged in shared memory (row stride HT+1: conflict-free for the nine summing
+        // lanes), then lane L of warp 0 adds row L in order: the serial FADD chain is fed by independent, prefetchable
+        // shared-memory loads (4-5 cycles per element instead of a dependent gather).
         float K0 = 0.0f, K1 = 0.0f, K2 = 0.0f;
         if (P.cov_mode == 1 && m > 0) { const uint32_t f0 = ORD[0]; K0 = X[f0]; K1 = Y[f0]; K2 = Z[f0]; }
         float acc = 0.0f;
-        for (uint32_t base_i = 0; base_i < m; base_i += TILE) {
-            const uint32_t cntk = min((uint32_t)TILE, m - base_i);
-            for (uint32_t k = tid; k < cntk; k += G) {
-                const uint32_t idx = ORD[base_i + k];
-                const float x = FS(X[idx], K0), y = FS(Y[idx], K1), z = FS(Z[idx], K2);
-                PRD[0 * (TILE + 1) + k] = FM(x, x);
-                PRD[1 * (TILE + 1) + k] = FM(x, y);
-                PRD[2 * (TILE + 1) + k] = FM(x, z);
-                PRD[3 * (TILE + 1) + k] = FM(y, y);
-                PRD[4 * (TILE + 1) + k] = FM(y, z);
-                PRD[5 * (TILE + 1) + k] = FM(z, z);
-                PRD[6 * (TILE + 1) + k] = x;
-                PRD[7 * (TILE + 1) + k] = y;
-                PRD[8 * (TILE + 1) + k] = z;
-            }
-            group_sync<G>();
-            if (warp == 0 && lane < 9) {
-                const float* row = PRD + lane * (TILE + 1);
-                uint32_t k = 0;
-                for (; k + 16 <= cntk; k += 16) {
-                    float q[16];
+        if (m > 0) {
+            // PRD holds two buffers of 9 x (HT + 1): while the nine lanes add the rows of one buffer in order, the next
+            // HT list elements are staged into the other.  A warp group does both in one instruction stream (the staging
+            // loads are in flight under the serial FADD chain; every lane runs the chain, lanes >= 9 on a copy of row 8,
+            // so that there is no branch between the two); in a CTA group warp 0 adds and the next 128 threads stage.
+            auto stage_prod = [&](float x, float y, float z, float* buf, uint32_t k) {
+                x = FS(x, K0); y = FS(y, K1); z = FS(z, K2);
+                buf[0 * (HT + 1) + k] = FM(x, x);
+                buf[1 * (HT + 1) + k] = FM(x, y);
+                buf[2 * (HT + 1) + k] = FM(x, z);
+                buf[3 * (HT + 1) + k] = FM(y, y);
+                buf[4 * (HT + 1) + k] = FM(y, z);
+                buf[5 * (HT + 1) + k] = FM(z, z);
+                buf[6 * (HT + 1) + k] = x;
+                buf[7 * (HT + 1) + k] = y;
+                buf[8 * (HT + 1) + k] = z;
+            };
+            auto chain = [&](const float* buf, uint32_t cntk) {
+                const float* row = buf + min(lane, 8) * (HT + 1);
+                if (cntk == (uint32_t)HT) {
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) q[u] = row[k + u];
+                    for (int k = 0; k < HT; k += 16) {
+                        float q[16];
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) acc = FA(acc, q[u]);
+                        for (int u = 0; u < 16; ++u) q[u] = row[k + u];
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) acc = FA(acc, q[u]);
+                    }
+                } else {
+                    for (uint32_t k = 0; k < cntk; k += 16u) {
+                        float q[16];
+#pragma unroll
+                        for (uint32_t u = 0; u < 16u; ++u) q[u] = row[min(k + u, (uint32_t)HT)];
+#pragma unroll
+                        for (uint32_t u = 0; u < 16u; ++u) { if (k + u < cntk) acc = FA(acc, q[u]); }
+                    }
                 }
-                for (; k < cntk; ++k) acc = FA(acc, row[k]);
+            };
+            {   // prologue: list elements [0, HT) -> buffer 0
+                const uint32_t k = (G == 32) ? (uint32_t)lane : (uint32_t)tid;
+                if (k < (uint32_t)HT) { const uint32_t idx = ORD[min(k, m - 1u)]; stage_prod(X[idx], Y[idx], Z[idx], PRD, k); }
             }
             group_sync<G>();
+            uint32_t t = 0;
+            for (uint32_t base_i = 0; base_i < m; base_i += HT, ++t) {
+                float* cur = PRD + (t & 1u) * PB;
+                float* nxt = PRD + ((t & 1u) ^ 1u) * PB;
+                const uint32_t cntk = min((uint32_t)HT, m - base_i);
+                const bool more = base_i + HT < m;                      // group-uniform
+                if (G == 32) {
+                    float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+                    if (more) { const uint32_t idx = ORD[min(base_i + HT + lane, m - 1u)]; sx = X[idx]; sy = Y[idx]; sz = Z[idx]; }
+                    chain(cur, cntk);
+                    if (more) stage_prod(sx, sy, sz, nxt, (uint32_t)lane);
+                    __syncwarp();
+                } else {
+                    if (warp == 0) {
+                        chain(cur, cntk);
+                    } else if (more && tid - 32 < HT) {
+                        const uint32_t k = (uint32_t)tid - 32u;
+                        const uint32_t idx = ORD[min(base_i + HT + k, m - 1u)];
+                        stage_prod(X[idx], Y[idx], Z[idx], nxt, k);
+                    }
+                    __syncthreads();
+                }
+            }
         }
         if (warp == 0) {
             if (lane < 9 && m != 0) acc = FD(acc, (float)m);
@@ -1359,12 +1408,13 @@ __device__ __forceinline__ void k4_process_bin(const GpfParams& P, FlagRec& rc, 
         const float n0 = sh.normal[0], n1 = sh.normal[1], n2 = sh.normal[2];
         const double thd = sh.thd;
         // ---- classify every point of the bin in source order (erasor.cpp:265-281) ----
-        for (uint32_t i = tid; i < n; i += G) {
+        // (classification fused into the stable compaction: one pass over the bin instead of two)
+        m = k4_compact<G>(n, ORD, sh.warp, [&](uint32_t i) {
             const float r = FA(FA(FM(X[i], n0), FM(Y[i], n1)), FM(Z[i], n2));
-            FLG[i] = ((double)r < thd) ? 1 : 0;
-        }
-        group_sync<G>();
-        m = k4_compact<G>(n, ORD, sh.warp, [&](uint32_t i) { return FLG[i] != 0; });
+            const bool  g = (double)r < thd;
+            FLG[i] = g ? 1 : 0;
+            return g;
+        });
         if (tid == 0 && it < kMaxIter) rc.n_ground[it] = m;
         K4_TICK(5);
     }
@@ -1383,10 +1433,21 @@ __device__ __forceinline__ void k4_process_bin(const GpfParams& P, FlagRec& rc, 
 
     // ---- outputs ----
     if (keep_mask || ground_mask) {
-        for (uint32_t i = tid; i < n; i += G) {
-            const uint32_t s = sorted_src[src_begin + i];
-            if (keep_mask && !FLG[i]) keep_mask[fbase + s] = 0;      // not in the selected bin any more (gf_iter == 0: dropped silently)
-            if (ground_mask && FLG[i]) ground_mask[fbase + s] = 1;
+        for (uint32_t i0 = tid; i0 < n; i0 += 4u * G) {
+            uint32_t s[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {                  // four independent index loads in flight per thread
+                const uint32_t i = i0 + (uint32_t)u * G;
+                s[u] = (i < n) ? sorted_src[src_begin + i] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t i = i0 + (uint32_t)u * G;
+                if (i < n) {
+                    if (keep_mask && !FLG[i]) keep_mask[fbase + s[u]] = 0;      // not in the selected bin any more (gf_iter == 0: dropped silently)
+                    if (ground_mask && FLG[i]) ground_mask[fbase + s[u]] = 1;
+                }
+            }
         }
     }
     if (part_pts) {
@@ -1420,10 +1481,10 @@ k4_rgpf(GpfParams P, FlagRec* __restrict__ recs, uint32_t* __restrict__ queue, c
         unsigned long long* __restrict__ fence) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NG = THREADS / G;
-    constexpr int TILE = (G == 32) ? 64 : 256;
+    constexpr int HT = (G == 32) ? 32 : 128;
     constexpr int NCNT = (G > 256) ? 8 * G : 1;          // radix counters: only the class-C sort uses them
     __shared__ K4Shared sh[NG];
-    __shared__ float    s_prd[NG][9 * (TILE + 1)];
+    __shared__ float    s_prd[NG][2 * 9 * (HT + 1)];
     __shared__ uint32_t s_cnt[NG][NCNT];
     __shared__ uint32_t s_fetch;
     const int grp = (G == 32) ? (threadIdx.x >> 5) : 0;
