@@ -36,6 +36,13 @@ int main(int argc, char** argv) {
         erasor.get_outliers(map_rejected, query_rejected);
         std::cout << "ERASOR Input: " << map_voi.size() << " = " << map_static_estimate.size() << " + "
                   << map_egocentric_complement.size() << " - " << map_rejected.size() << std::endl;
+        // the frame-independent batch mode on the same pair, twice in one submission: one keep byte per map point per frame
+        const auto keep = erasor.process_frames({map_voi, map_voi}, {query_voi, query_voi});
+        size_t rejected0 = 0, rejected1 = 0;
+        for (uint8_t k : keep[0]) rejected0 += (k == 0);
+        for (uint8_t k : keep[1]) rejected1 += (k == 0);
+        std::cout << "batch mode: " << rejected0 << " / " << rejected1 << " map points rejected (cloud mode: " << map_rejected.size() << ")" << std::endl;
+        if (rejected0 != rejected1 || (p.gf_iter > 0 && rejected0 != map_rejected.size())) { std::cerr << "batch / cloud mode disagree" << std::endl; return 1; }
     } catch (const std::exception& e) {
         std::cerr << e.what() << std::endl;
         return 1;

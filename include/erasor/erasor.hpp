@@ -9,6 +9,8 @@
 // Everything the methods compute runs in the sm_100a kernels behind the C ABI; this header holds no
 // arithmetic.  The rviz / debug publishers of the reference (erasor.h:67-77) are not mirrored.
 #pragma once
+#include <algorithm>
+#include <cstdint>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -69,6 +71,26 @@ public:
                                   reinterpret_cast<float*>(curr_rejected.data()), nq, &nq, ERASOR_PTR_HOST));
     }
     double get_max_range() { return erasor_get_max_range(h_); }               // erasor.cpp:628
+
+    // Frame-independent batch mode (no counterpart in the reference; BASELINE.json north_star): F independent
+    // (map VoI, query VoI) pairs in one submission.  keep[f][i] == 0 where frame f rejects the i-th point of its map VoI.
+    std::vector<std::vector<uint8_t>> process_frames(const std::vector<PointCloud>& map_vois, const std::vector<PointCloud>& query_vois) {
+        if (map_vois.size() != query_vois.size() || map_vois.empty()) throw std::invalid_argument("ERASOR: one query VoI per map VoI");
+        const size_t F = map_vois.size();
+        std::vector<uint64_t> mo(F + 1, 0), qo(F + 1, 0);
+        for (size_t f = 0; f < F; ++f) { mo[f + 1] = mo[f] + map_vois[f].size(); qo[f + 1] = qo[f] + query_vois[f].size(); }
+        PointCloud m(mo[F]), q(qo[F]);
+        for (size_t f = 0; f < F; ++f) {
+            std::copy(map_vois[f].begin(), map_vois[f].end(), m.begin() + static_cast<std::ptrdiff_t>(mo[f]));
+            std::copy(query_vois[f].begin(), query_vois[f].end(), q.begin() + static_cast<std::ptrdiff_t>(qo[f]));
+        }
+        std::vector<uint8_t> keep(mo[F] ? mo[F] : 1);
+        check(erasor_process_frames(h_, reinterpret_cast<const float*>(m.data()), mo.data(), reinterpret_cast<const float*>(q.data()), qo.data(),
+                                    static_cast<int>(F), keep.data(), ERASOR_PTR_HOST));
+        std::vector<std::vector<uint8_t>> out(F);
+        for (size_t f = 0; f < F; ++f) out[f].assign(keep.begin() + static_cast<std::ptrdiff_t>(mo[f]), keep.begin() + static_cast<std::ptrdiff_t>(mo[f + 1]));
+        return out;
+    }
 
     // what the reference exposes as /SCDR/debug/polygons_marker likelihoods (erasor.cpp:439-441,570);
     // index = sector * num_rings + ring

@@ -90,3 +90,28 @@ def test_cpp_driver_matches_oracle_pass(tmp_path, oracle_mod):
     a, b = E.evaluate(m0, result), E.evaluate(m0, ref)
     assert abs(a["PR"] - b["PR"]) < 1e-9 and abs(a["RR"] - b["RR"]) < 1e-9
     assert b["RR"] > 20.0
+
+
+@pytest.mark.parametrize("version", [3, 2])
+def test_cpp_class_demo(tmp_path, version):
+    """examples/erasor_cpp_demo: the reference's call sequence through the header-only C++ class (`erasor/erasor.hpp`), then the
+    batch mode on the same pair; the binary itself checks that both modes reject the same number of map points.  The sizes it
+    prints must be the oracle's."""
+    from oracle import oracle_py
+    demo = os.path.join(ROOT, "erasor_b200", "_lib", "erasor_cpp_demo")
+    assert os.path.exists(demo), "build first: erasor_b200/csrc/build.sh"
+    p = P.preset("seq_05").replace(version=version)
+    w = synth.make_frames(seed=3, n_frames=2, preset_max_range=p.max_range, n_map_nodes=24, n_beams=32, n_az=600,
+                          length=30.0, n_dynamic=4, query_voxel=0.2, map_stride=2)
+    m, q = w["frames"][1][0], w["frames"][1][1]
+    m.astype(np.float32).tofile(tmp_path / "map.f32")
+    q.astype(np.float32).tofile(tmp_path / "query.f32")
+    r = subprocess.run([demo, str(tmp_path / "map.f32"), str(tmp_path / "query.f32"), str(version)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    o = oracle_py.Oracle(p)
+    o.run(m, q)
+    arr, _ = o.cloud(o.ARRANGED)
+    cmp_, _ = o.cloud(o.COMPLEMENT)
+    rej, _ = o.cloud(o.MAP_REJECTED)
+    assert f"ERASOR Input: {len(m)} = {len(arr)} + {len(cmp_)} - {len(rej)}" in r.stdout, r.stdout
+    assert "batch mode:" in r.stdout
