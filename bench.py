@@ -34,7 +34,7 @@ import numpy as np  # noqa: E402
 
 FRAMES_PER_PASS = 20          # 161 nodes / removal_interval 8 (config/seq_05.yaml)
 N_INPUT_COPIES = 4            # rotate input copies so that consecutive steps never find their clouds in the 126 MB L2
-K1_DRAM_TRAFFIC_BYTES = 56.862208e6 + 1.975808e6   # ncu --set full, one launch of k1_rpod_bin on the default workload (profiles/r01/ncu_step_full_raw.csv)
+K1_DRAM_TRAFFIC_BYTES = 56.861952e6 + 2.707712e6   # ncu --set full, one launch of k1_rpod_bin on the default workload (profiles/r01/ncu_step_full_raw.csv)
 CACHE_DIR = os.environ.get("ERASOR_B200_CACHE", "/tmp/erasor_b200_cache")
 
 
