@@ -30,6 +30,14 @@ def _worker(rank, world, port, n_global, vois, masks, out_dir):
     mine = D.shard_frames(len(vois), rank, world)
     final = D.static_map_mask(n_global, [vois[f] for f in mine], [masks[f] for f in mine])
     np.save(os.path.join(out_dir, f"final_{rank}.npy"), final.numpy())
+    # the streaming form bench.py uses: fold per batch, then ONE all-gather into a caller-owned buffer; repeating the
+    # collective with the same buffer must give the same mask
+    keep_g = D.fold_masks(n_global, [torch.from_numpy(np.asarray(vois[f]).astype(np.int64)) for f in mine],
+                          [torch.from_numpy(np.asarray(masks[f]).astype(np.uint8)) for f in mine])
+    buf = torch.empty((world, n_global), dtype=torch.uint8)
+    again = D.allgather_and(keep_g, buf)
+    again2 = D.allgather_and(keep_g, buf)
+    assert torch.equal(again, final) and torch.equal(again2, final)
     dist.barrier()
     dist.destroy_process_group()
 
