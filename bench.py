@@ -204,6 +204,31 @@ def _ref_frame(i):
     return _W["o"].run(_W["maps"][i], _W["qs"][i])
 
 
+def usable_cores():
+    """CPUs this process can actually use: the affinity mask capped by the cgroup CPU quota (a container that sees 128 CPUs
+    with cpu.max = 16 CPUs is throttled to 16; more worker processes than that only add contention)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    note = f"{n} CPUs in the affinity mask"
+    quota = None
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:                       # cgroup v2: "<quota|max> <period>"
+            q, per = f.read().split()
+            if q != "max":
+                quota = float(q) / float(per)
+    except (OSError, ValueError):
+        try:
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f, open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as g:   # cgroup v1
+                q, per = float(f.read()), float(g.read())
+                if q > 0:
+                    quota = q / per
+        except (OSError, ValueError):
+            pass
+    if quota is not None and quota < n:
+        n = max(1, int(quota))
+        note += f", cgroup quota {quota:g} CPUs"
+    return n, note
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -213,12 +238,12 @@ def run_reference(args):
     from oracle import oracle_py
     oracle_py.build()
     p, map_world, maps, qs, _ = load_workload(0, 1, FRAMES_PER_PASS)
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores, cores_note = usable_cores()
     ctx = mp.get_context("fork")
     with ctx.Pool(cores, initializer=_ref_init, initargs=(dataclasses.asdict(p), maps, qs)) as pool:
-        # a step = enough frames to give every host core one (the 20-frame pass repeated): the reference is
+        # a step = the 20-frame pass repeated until every worker has ~4 frames (balanced waves): the reference is
         # single-threaded, so "all the host threads it can use" means independent frames in parallel processes
-        reps = max(1, -(-cores // len(maps)))
+        reps = max(1, -(-4 * cores // len(maps)))
         idx = list(range(len(maps))) * reps
         for _ in range(args.warmup):
             pool.map(_ref_frame, idx, chunksize=1)
@@ -234,7 +259,7 @@ def run_reference(args):
         "dtype": "f32 points, f64 index/SRT arithmetic", "data": "synthetic",
         "config": workload_config(p, maps, qs, 1),
         "cpu_baseline": {"value": sps, "unit": "scans/s", "cores": cores, "kind": "port",
-                         "sample": f"{len(idx)} frames per step x {args.steps} steps, one oracle process per core "
+                         "sample": f"{len(idx)} frames per step x {args.steps} steps, one oracle process per usable core ({cores_note}) "
                                    "(the reference itself is single-threaded and cannot be compiled here: needs ROS/PCL/Eigen)"},
         "e2e": {"value": sps, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
