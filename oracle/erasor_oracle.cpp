@@ -939,4 +939,51 @@ void OfflineMapUpdater::save_static_map(float voxel_size, Cloud& map_to_be_saved
     voxelize_preserving_labels(src, map_to_be_saved, voxel_size);
 }
 
+// ----------------------------------------------------------------------------
+// mapgen (src/mapgen/mapgen.hpp), ROS stripped
+// ----------------------------------------------------------------------------
+void NaiveMapGen::accum_point_cloud(const double odom[7], const Cloud& lidar) {
+    // tf_lidar2origin (:209-214): identity with z + 1.73
+    const float tf_lidar2origin[16] = {1, 0, 0, 0,  0, 1, 0, 0,  0, 0, 1, 1.73f,  0, 0, 0, 1};
+    // "To remove some noisy points in the vicinity of the vehicles" (:218-229): float threshold, double distance
+    const float max_dist_square = static_cast<float>(std::pow(2.7, 2));            // CAR_BODY_SIZE 2.7 (:8)
+    Cloud outliers;
+    outliers.reserve(lidar.size());
+    for (const auto& pt : lidar) {
+        const double dist_square = std::pow(static_cast<double>(pt.x), 2) + std::pow(static_cast<double>(pt.y), 2);
+        if (!(dist_square < max_dist_square)) outliers.push_back(pt);               // inliers are dropped
+    }
+    Cloud lifted, world;
+    transform_point_cloud(outliers, lifted, tf_lidar2origin);                       // :231-232
+    float pose[16];
+    geo_pose_to_matrix(odom, pose);                                                 // :234
+    transform_point_cloud(lifted, world, pose);                                     // :236-237
+    voxelize_preserving_labels(world, cloud_curr, 0.2);                             // :239 (fixed 0.2, not leafsize)
+    if (is_initial_) {
+        cloud_map   = cloud_curr;                                                   // :241-243
+        is_initial_ = false;
+    } else {
+        cloud_map.insert(cloud_map.end(), cloud_curr.begin(), cloud_curr.end());    // :245
+        if (is_large_scale_) {
+            if (cnt_voxel_++ % 500 == 0) {                                          // :247-258
+                Cloud vox;
+                voxelize_preserving_labels(cloud_map, vox, leafsize_);
+                cloud_maps.push_back(vox);
+                cloud_map.clear();
+            }
+        }
+    }
+}
+
+void NaiveMapGen::save_naive_map(Cloud& original, Cloud& voxelized) const {
+    original.clear();
+    if (is_large_scale_) {                                                          // :275-281
+        for (const auto& submap : cloud_maps) original.insert(original.end(), submap.begin(), submap.end());
+        original.insert(original.end(), cloud_map.begin(), cloud_map.end());
+    } else {
+        original = cloud_map;                                                       // :283
+    }
+    voxelize_preserving_labels(original, voxelized, leafsize_);                     // :296
+}
+
 }  // namespace oracle

@@ -245,4 +245,24 @@ private:
     size_t num_pcs_init_ = 0;
 };
 
+
+// ---------------------------------------------------------------------------
+// mapgen, ROS stripped (src/mapgen/mapgen.hpp:198-309; driver src/mapgen/main.cpp:40-49): the naive map builder that
+// produces the path's input map.  Per node: drop the points within CAR_BODY_SIZE of the sensor, lift by 1.73 m,
+// move to the map frame with the node's pose, voxelize at 0.2 m, append; at the end voxelize the whole map at `leafsize`.
+// ---------------------------------------------------------------------------
+class NaiveMapGen {
+public:
+    NaiveMapGen(float leafsize, bool is_large_scale) : leafsize_(leafsize), is_large_scale_(is_large_scale) {}
+    void accum_point_cloud(const double odom[7], const Cloud& lidar);     // accumPointCloud, mapgen.hpp:198-263
+    void save_naive_map(Cloud& original, Cloud& voxelized) const;          // saveNaiveMap, mapgen.hpp:271-307
+    Cloud cloud_map, cloud_curr;                                           // :38-39 (getPointClouds :265-269)
+    std::vector<Cloud> cloud_maps;                                         // :37 (large-scale submaps)
+private:
+    float leafsize_;
+    bool  is_large_scale_;
+    bool  is_initial_ = true;                                              // :33
+    int   cnt_voxel_  = 0;                                                 // function-static in the reference (:248)
+};
+
 }  // namespace oracle

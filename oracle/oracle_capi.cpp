@@ -197,4 +197,21 @@ size_t oracle_updater_save_static_map(void* h, float voxel_size, float* out_xyzi
     return from_cloud(out, out_xyzi, nullptr, cap);
 }
 
+// ---- mapgen ----
+void* oracle_mapgen_create(float leafsize, int is_large_scale) { return new NaiveMapGen(leafsize, is_large_scale != 0); }
+void  oracle_mapgen_destroy(void* g) { delete static_cast<NaiveMapGen*>(g); }
+void  oracle_mapgen_accum(void* g, const double* odom7, const float* xyzi, size_t n) {
+    Cloud c; to_cloud(xyzi, n, 0u, c);
+    static_cast<NaiveMapGen*>(g)->accum_point_cloud(odom7, c);
+}
+// which: 0 cloud_map, 1 cloud_curr, 2 saved original, 3 saved voxelized
+size_t oracle_mapgen_get(void* g, int which, float* out_xyzi, size_t cap) {
+    auto* m = static_cast<NaiveMapGen*>(g);
+    if (which == 0) return from_cloud(m->cloud_map, out_xyzi, nullptr, cap);
+    if (which == 1) return from_cloud(m->cloud_curr, out_xyzi, nullptr, cap);
+    Cloud orig, vox;
+    m->save_naive_map(orig, vox);
+    return from_cloud(which == 2 ? orig : vox, out_xyzi, nullptr, cap);
+}
+
 }  // extern "C"

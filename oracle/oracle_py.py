@@ -83,6 +83,12 @@ def _bind(L):
     L.oracle_jacobi_svd.argtypes = [fp, fp, fp]
     L.oracle_voxelize.restype = c_size_t
     L.oracle_voxelize.argtypes = [fp, c_size_t, c_double, fp, c_size_t]
+    L.oracle_mapgen_create.restype = c_void_p
+    L.oracle_mapgen_create.argtypes = [ctypes.c_float, c_int]
+    L.oracle_mapgen_destroy.argtypes = [c_void_p]
+    L.oracle_mapgen_accum.argtypes = [c_void_p, POINTER(c_double), fp, c_size_t]
+    L.oracle_mapgen_get.restype = c_size_t
+    L.oracle_mapgen_get.argtypes = [c_void_p, c_int, fp, c_size_t]
     L.oracle_transform.argtypes = [fp, c_size_t, fp, fp]
     L.oracle_pose_to_matrix.argtypes = [POINTER(c_double), fp]
     L.oracle_invert4.argtypes = [fp, fp]
@@ -306,3 +312,34 @@ class OracleUpdater:
         out = np.empty((n, 4), dtype=np.float32)
         k = self.L.oracle_updater_save_static_map(self.h, voxel_size, _fptr(out), n)
         return out[:k].copy()
+
+
+class OracleMapGen:
+    """The restated naive map builder (src/mapgen/mapgen.hpp:198-309)."""
+    CLOUD_MAP, CLOUD_CURR, SAVED_ORIGINAL, SAVED_VOXELIZED = range(4)
+
+    def __init__(self, leafsize: float, is_large_scale: bool = False):
+        self.L = lib()
+        self.h = c_void_p(self.L.oracle_mapgen_create(leafsize, 1 if is_large_scale else 0))
+
+    def accum(self, odom7, lidar):
+        o = np.ascontiguousarray(odom7, dtype=np.float64)
+        c = _as_cloud(lidar)
+        self.L.oracle_mapgen_accum(self.h, o.ctypes.data_as(POINTER(c_double)), _fptr(c), len(c))
+
+    def cloud(self, which: int) -> np.ndarray:
+        n = self.L.oracle_mapgen_get(self.h, which, None, 0)
+        out = np.empty((max(n, 1), 4), dtype=np.float32)
+        self.L.oracle_mapgen_get(self.h, which, _fptr(out), n)
+        return out[:n].copy()
+
+    def close(self):
+        if self.h:
+            self.L.oracle_mapgen_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
