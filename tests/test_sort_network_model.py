@@ -94,7 +94,7 @@ def _place(words, n, E, G, pad):
 
 
 @pytest.mark.parametrize("E", [4, 8, 16])
-@pytest.mark.parametrize("NW", [1, 8])
+@pytest.mark.parametrize("NW", [1, 4, 8])      # 4: the 128-thread class planned in DESIGN.md section 10
 def test_network_64bit_is_a_stable_sort(E, NW):
     rng = np.random.default_rng(E * 10 + NW)
     G, N = NW * 32, NW * 32 * E
