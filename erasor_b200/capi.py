@@ -25,7 +25,11 @@ EXPORTS = [
     "erasor_create", "erasor_destroy", "erasor_last_error", "erasor_abi_version", "erasor_stream", "erasor_synchronize",
     "erasor_set_inputs", "erasor_compare", "erasor_get_output_sizes", "erasor_get_static_estimate", "erasor_get_outliers",
     "erasor_get_max_range", "erasor_get_bins", "erasor_get_status", "erasor_get_planes", "erasor_get_static_mask",
-    "erasor_get_fence_counts", "erasor_process_frames", "erasor_process_frames_fold", "erasor_fold_keep_masks", "erasor_get_frame_stats", "erasor_kernel_launch_count",
+    "erasor_get_fence_counts", "erasor_process_frames", "erasor_process_frames_async", "erasor_wait", "erasor_process_frames_fold",
+    "erasor_process_frames_fold_async", "erasor_fold_keep_masks", "erasor_reset_keep_mask", "erasor_get_frame_stats", "erasor_kernel_launch_count",
+    "erasor_map_create", "erasor_map_destroy", "erasor_map_size", "erasor_map_reset_keep", "erasor_map_get_keep", "erasor_map_keep_device",
+    "erasor_map_points_device", "erasor_attach_map", "erasor_process_nodes", "erasor_process_nodes_async", "erasor_get_node_stats",
+    "erasor_comm_unique_id", "erasor_comm_init", "erasor_comm_destroy", "erasor_allgather_and_keep", "erasor_and_keep_masks",
     "erasor_get_kernel_time_ms", "erasor_reset_kernel_times", "erasor_get_rgpf_profile", "erasor_get_srt_profile",
     "erasor_updater_create", "erasor_updater_destroy", "erasor_updater_reset", "erasor_updater_last_error", "erasor_updater_process_node",
     "erasor_updater_map_size", "erasor_updater_get_cloud", "erasor_updater_save_static_map", "erasor_updater_voxelize",
@@ -81,6 +85,30 @@ def _load():
     L.erasor_process_frames_fold.argtypes = [c_void_p, c_void_p, POINTER(c_uint64), c_void_p, POINTER(c_uint64), c_int, c_void_p, c_int,
                                              c_void_p, c_void_p, c_size_t]
     L.erasor_fold_keep_masks.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t]
+    L.erasor_process_frames_async.argtypes = L.erasor_process_frames.argtypes
+    L.erasor_process_frames_fold_async.argtypes = L.erasor_process_frames_fold.argtypes
+    L.erasor_wait.argtypes = [c_void_p]
+    L.erasor_reset_keep_mask.argtypes = [c_void_p, c_void_p, c_size_t]
+    L.erasor_map_create.argtypes = [c_void_p, c_size_t, c_int, c_int, POINTER(c_void_p)]
+    L.erasor_map_destroy.restype = None
+    L.erasor_map_destroy.argtypes = [c_void_p]
+    L.erasor_map_size.restype = c_size_t
+    L.erasor_map_size.argtypes = [c_void_p]
+    L.erasor_map_reset_keep.argtypes = [c_void_p]
+    L.erasor_map_get_keep.argtypes = [c_void_p, c_void_p, c_int]
+    L.erasor_map_keep_device.restype = c_void_p
+    L.erasor_map_keep_device.argtypes = [c_void_p]
+    L.erasor_map_points_device.restype = c_void_p
+    L.erasor_map_points_device.argtypes = [c_void_p]
+    L.erasor_attach_map.argtypes = [c_void_p, c_void_p]
+    L.erasor_process_nodes.argtypes = [c_void_p, POINTER(c_double), c_void_p, POINTER(c_uint64), c_int, c_double, c_void_p, c_void_p, c_int]
+    L.erasor_process_nodes_async.argtypes = L.erasor_process_nodes.argtypes
+    L.erasor_get_node_stats.argtypes = [c_void_p, POINTER(c_uint32), POINTER(c_uint32), POINTER(c_uint32)]
+    L.erasor_comm_unique_id.argtypes = [c_void_p]
+    L.erasor_comm_init.argtypes = [c_void_p, c_void_p, c_int, c_int]
+    L.erasor_comm_destroy.argtypes = [c_void_p]
+    L.erasor_allgather_and_keep.argtypes = [c_void_p, c_void_p, c_size_t]
+    L.erasor_and_keep_masks.argtypes = [c_void_p, c_void_p, c_int, c_size_t, c_void_p]
     L.erasor_get_frame_stats.argtypes = [c_void_p, POINTER(c_uint32), POINTER(c_uint32)]
     L.erasor_kernel_launch_count.restype = c_uint64
     L.erasor_kernel_launch_count.argtypes = [c_void_p]
@@ -265,7 +293,7 @@ class Handle:
         return keep
 
     def process_frames_ptr(self, map_ptr: int, map_offsets: np.ndarray, query_ptr: int, query_offsets: np.ndarray, keep_ptr: int, ptr_kind: int,
-                           fold=None):
+                           fold=None, asynchronous: bool = False):
         """Raw-pointer batch call (device tensors or pinned host memory); offsets are host uint64 arrays.
         The ctypes views of the offset arrays are cached per array object so that a caller streaming equally-shaped
         batches pays one foreign call per step and nothing else."""
@@ -277,16 +305,84 @@ class Handle:
             c = (key, mo, qo, mo.ctypes.data_as(POINTER(c_uint64)), qo.ctypes.data_as(POINTER(c_uint64)), len(mo) - 1)
             self._off_cache = c
         if fold is None:
-            rc = self.L.erasor_process_frames(self.h, map_ptr, c[3], query_ptr, c[4], c[5], keep_ptr, ptr_kind)
-        else:       # fold = (voi_index device ptr, global_keep device ptr, n_global): process + fold in one submission
-            rc = self.L.erasor_process_frames_fold(self.h, map_ptr, c[3], query_ptr, c[4], c[5], keep_ptr, ptr_kind, fold[0], fold[1], fold[2])
+            fn = self.L.erasor_process_frames_async if asynchronous else self.L.erasor_process_frames
+            rc = fn(self.h, map_ptr, c[3], query_ptr, c[4], c[5], keep_ptr, ptr_kind)
+        else:       # fold = (voi_index device ptr, global_keep device ptr, n_global): the fold runs in R-GPF's epilogue
+            fn = self.L.erasor_process_frames_fold_async if asynchronous else self.L.erasor_process_frames_fold
+            rc = fn(self.h, map_ptr, c[3], query_ptr, c[4], c[5], keep_ptr, ptr_kind, fold[0], fold[1], fold[2])
         if rc != OK:
             self._ck(rc)
         self.n_frames = c[5]
 
     def fold_keep_masks(self, keep_ptr: int, voi_index_ptr: int, n: int, global_keep_ptr: int, n_global: int):
-        """device pointers; asynchronous on the handle's stream"""
+        """device pointers; asynchronous on the handle's stream; accumulates (reset_keep_mask starts a job)"""
         self._ck(self.L.erasor_fold_keep_masks(self.h, c_void_p(keep_ptr), c_void_p(voi_index_ptr), n, c_void_p(global_keep_ptr), n_global))
+
+    def reset_keep_mask(self, global_keep_ptr: int, n_global: int):
+        self._ck(self.L.erasor_reset_keep_mask(self.h, c_void_p(global_keep_ptr), n_global))
+
+    def wait(self):
+        """Complete the handle's asynchronous submission (``*_async``)."""
+        rc = self.L.erasor_wait(self.h)
+        if rc != OK:
+            self._ck(rc)
+
+    # -- map-resident node mode -----------------------------------------------------------------
+    def attach_map(self, m: "Map"):
+        self._ck(self.L.erasor_attach_map(self.h, m.h if m is not None else None))
+        self._map = m
+
+    def process_nodes(self, poses7, query_xyzi, query_offsets, voi_max_range: float = 0.0, want_frame_keep: bool = False):
+        """Host-buffer node batch: returns (folded keep mask of the map after this batch, per-frame masks or None)."""
+        P = np.ascontiguousarray(poses7, dtype=np.float64).reshape(-1, 7)
+        q = _cloud(query_xyzi)
+        qo = np.ascontiguousarray(query_offsets, dtype=np.uint64)
+        F = len(qo) - 1
+        assert len(P) == F
+        n = self._map.size
+        keep = np.empty(n, dtype=np.uint8)
+        fk = np.empty((F, n), dtype=np.uint8) if want_frame_keep else None
+        self._ck(self.L.erasor_process_nodes(self.h, P.ctypes.data_as(POINTER(c_double)), q.ctypes.data, qo.ctypes.data_as(POINTER(c_uint64)), F,
+                                             float(voi_max_range), fk.ctypes.data if fk is not None else None, keep.ctypes.data, PTR_HOST))
+        self.n_frames = F
+        return keep, fk
+
+    def process_nodes_ptr(self, poses7: np.ndarray, query_ptr: int, query_offsets: np.ndarray, voi_max_range: float, frame_keep_ptr: int,
+                          keep_out_ptr: int, ptr_kind: int, asynchronous: bool = False):
+        """Raw-pointer node batch (device tensors or pinned host memory).  poses7: contiguous float64 [F,7]; offsets uint64 [F+1]."""
+        key = (id(poses7), id(query_offsets))
+        c = getattr(self, "_node_cache", None)
+        if c is None or c[0] != key:
+            assert poses7.dtype == np.float64 and poses7.flags["C_CONTIGUOUS"] and query_offsets.dtype == np.uint64
+            c = (key, poses7, query_offsets, poses7.ctypes.data_as(POINTER(c_double)), query_offsets.ctypes.data_as(POINTER(c_uint64)), len(query_offsets) - 1)
+            self._node_cache = c
+        fn = self.L.erasor_process_nodes_async if asynchronous else self.L.erasor_process_nodes
+        rc = fn(self.h, c[3], query_ptr, c[4], c[5], voi_max_range, frame_keep_ptr or None, keep_out_ptr or None, ptr_kind)
+        if rc != OK:
+            self._ck(rc)
+        self.n_frames = c[5]
+
+    def node_stats(self):
+        F = self.n_frames
+        nv, nf, nr = (np.zeros(F, dtype=np.uint32) for _ in range(3))
+        self._ck(self.L.erasor_get_node_stats(self.h, nv.ctypes.data_as(POINTER(c_uint32)), nf.ctypes.data_as(POINTER(c_uint32)),
+                                              nr.ctypes.data_as(POINTER(c_uint32))))
+        return nv, nf, nr
+
+    # -- the exchange step ------------------------------------------------------------------------
+    def comm_init(self, id128: bytes, n_ranks: int, rank: int):
+        buf = (ctypes.c_uint8 * 128).from_buffer_copy(id128)
+        self._ck(self.L.erasor_comm_init(self.h, buf, n_ranks, rank))
+
+    def comm_destroy(self):
+        self._ck(self.L.erasor_comm_destroy(self.h))
+
+    def and_keep_masks(self, masks_ptr: int, n_masks: int, n: int, out_ptr: int):
+        self._ck(self.L.erasor_and_keep_masks(self.h, c_void_p(masks_ptr), n_masks, n, c_void_p(out_ptr)))
+
+    def allgather_and_keep(self, global_keep_ptr: int, n_global: int):
+        """device pointer; asynchronous on the handle's stream; no-op without a communicator"""
+        self._ck(self.L.erasor_allgather_and_keep(self.h, c_void_p(global_keep_ptr), n_global))
 
     def frame_stats(self):
         F = self.n_frames
@@ -321,6 +417,62 @@ class Handle:
         t, n = c_double(), c_uint64()
         self._ck(self.L.erasor_get_kernel_time_ms(self.h, kernel_id, ctypes.byref(t), ctypes.byref(n)))
         return t.value, n.value
+
+
+def comm_unique_id() -> bytes:
+    """NCCL unique id for erasor_comm_init (call on rank 0, ship the bytes to the other ranks)."""
+    buf = (ctypes.c_uint8 * 128)()
+    rc = lib().erasor_comm_unique_id(buf)
+    if rc != OK:
+        raise ErasorError(rc, (lib().erasor_last_error(None) or b"").decode())
+    return bytes(buf)
+
+
+class Map:
+    """One ``erasor_map_t``: the global map resident in HBM plus its global keep mask."""
+
+    def __init__(self, map_xyzi=None, device: int = 0, device_ptr: int = 0, n: int = 0):
+        self.L = lib()
+        h = c_void_p()
+        if device_ptr:
+            rc = self.L.erasor_map_create(c_void_p(device_ptr), n, PTR_DEVICE, device, ctypes.byref(h))
+        else:
+            m = _cloud(map_xyzi)
+            rc = self.L.erasor_map_create(m.ctypes.data, len(m), PTR_HOST, device, ctypes.byref(h))
+        if rc != OK:
+            raise ErasorError(rc, (self.L.erasor_last_error(None) or b"").decode())
+        self.h = h
+
+    @property
+    def size(self) -> int:
+        return int(self.L.erasor_map_size(self.h))
+
+    @property
+    def keep_ptr(self) -> int:
+        return self.L.erasor_map_keep_device(self.h) or 0
+
+    def reset_keep(self):
+        rc = self.L.erasor_map_reset_keep(self.h)
+        if rc != OK:
+            raise ErasorError(rc, "erasor_map_reset_keep")
+
+    def get_keep(self) -> np.ndarray:
+        out = np.empty(self.size, dtype=np.uint8)
+        rc = self.L.erasor_map_get_keep(self.h, out.ctypes.data, PTR_HOST)
+        if rc != OK:
+            raise ErasorError(rc, "erasor_map_get_keep")
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.erasor_map_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Updater:

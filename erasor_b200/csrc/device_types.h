@@ -17,12 +17,24 @@ enum : uint8_t { ACT_MAP = 0, ACT_FLAG = 1, ACT_MERGE = 2, ACT_CURR = 3, ACT_NON
 
 // One contiguous run of points of one cloud of one frame, processed by one CTA of K1 / one warp of K2.
 struct ChunkDesc {
-    uint32_t begin;        // first point (index into the concatenated cloud array)
+    uint32_t begin;        // first point (index into the source cloud array: the concatenated batch clouds, or the resident global map in node mode)
     uint32_t len;          // points in this chunk
     uint32_t frame;        // frame index
     uint32_t cloud;        // 0 map, 1 query
-    uint32_t frame_begin;  // first point of this frame's cloud
-    uint32_t pad_[3];
+    uint32_t frame_begin;  // source index of the frame's first point (node mode, map cloud: 0 -- every frame scans the whole map)
+    uint32_t bin_begin;    // index of the chunk's first point in the bin-id array (batch mode: == begin; node mode: frame * n_map + begin)
+    uint32_t out_base;     // base of the frame's region in the scattered arrays and the per-frame masks (batch: frame_begin; node: frame * n_map)
+    uint32_t pad_;
+};
+
+// Node mode (map resident in HBM, erasor_process_nodes): what OfflineMapUpdater::fetch_VoI needs per frame
+// (reference OfflineMapUpdater.cpp:381-438): the radius cut around the body position, in double on float
+// differences, and the origin -> body affine (float, pcl::transformPointCloud association, no contraction).
+struct NodePose {
+    double px, py;         // tf_body2origin(0,3), (1,3) as the reference reads them (:246-247)
+    double limit;          // pow(max_range, 2)
+    float  T[12];          // rows 0..2 of tf_body2origin.inverse()
+    float  pad_[2];
 };
 
 struct SrtParams {
@@ -41,6 +53,14 @@ struct GpfParams {
     int    num_lpr;
     int    iters;
     int    cov_mode;
+};
+
+// The multi-GPU fold, done in K4's epilogue: global_keep[index ? index[frame_base + src] : src] = 0 for every rejected point.
+struct K4Fold {
+    uint8_t*        keep;      // global keep mask of the map (null: no fold)
+    const uint32_t* index;     // per-VoI-point global index (batch mode); null: the source index is the global index (node mode)
+    uint32_t        n;         // size of the global mask (writes beyond it are dropped)
+    uint32_t        pad_;
 };
 
 // R-GPF work queue.  K3 appends every flagged-bin record to the bucket of its size; K4's three size classes

@@ -2,6 +2,8 @@
 // There is no host compute path in this file: every entry point either launches the sm_100a kernels of
 // kernels.cu or fails with an error code.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>      // types only: the library is loaded with dlopen on first use (erasor_comm_*)
 
 #include <algorithm>
 #include <cmath>
@@ -16,6 +18,7 @@
 #include "binning_tables.h"
 #include "device_types.h"
 #include "kernels.h"
+#include "pose_math.h"
 
 using namespace erasor;
 
@@ -23,14 +26,13 @@ namespace {
 
 thread_local std::string g_create_error;
 
-uint64_t g_alloc_epoch = 0;   // bumped on every device (re)allocation: captured graphs hold raw pointers
-
 struct DevBuf {
-    void*  p = nullptr;
-    size_t cap = 0;
+    void*     p = nullptr;
+    size_t    cap = 0;
+    uint64_t* epoch = nullptr;   // the owning handle's allocation epoch: bumped on every (re)allocation, captured graphs hold raw pointers
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
-        ++g_alloc_epoch;
+        if (epoch) ++*epoch;
         if (p) { cudaFree(p); p = nullptr; cap = 0; }
         size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
@@ -59,6 +61,7 @@ struct PinnedBuf {
 };
 
 constexpr int kNumTimers = 6;   // 0 whole pipeline, 1..5 = K1..K5
+constexpr size_t kMaxRecords = (size_t)1 << 21;   // flagged-bin records of one submission (larger batches are split)
 
 struct Timer {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
@@ -67,6 +70,24 @@ struct Timer {
 };
 
 }  // namespace
+
+struct erasor_map_ctx {
+    int          device = 0;
+    float4*      d_pts = nullptr;
+    uint8_t*     d_keep = nullptr;
+    size_t       n = 0;
+    cudaStream_t st = nullptr;
+    std::string  err;
+};
+
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char*  (*GetErrorString)(ncclResult_t) = nullptr;
+};
 
 struct erasor_ctx {
     erasor_params_t p{};
@@ -79,6 +100,7 @@ struct erasor_ctx {
     DevBuf          d_ring, d_pos, d_neg;
     BinTablesView   view{};
     int             B = 0;
+    uint64_t        alloc_epoch = 0;           // bumped by every DevBuf (re)allocation of this handle
 
     // per-batch buffers
     DevBuf d_map_in, d_qry_in;                 // staging when the caller's clouds are host memory
@@ -91,23 +113,41 @@ struct erasor_ctx {
     DevBuf d_arranged, d_map_rej, d_curr_rej, d_jobs, d_out_sizes, d_k5tmp;
     DevBuf d_vox, d_vox_cnt, d_vox_start, d_vox_scratch;
     DevBuf d_fence;                            // 4 x u64: negzero, empty fits, ambiguous, slow-path points
-    PinnedBuf h_stage;
+    DevBuf d_poses;                            // node mode: NodePose per frame
+    DevBuf d_pack, d_gather;                   // exchange step: packed keep bits of this rank / of every rank
+    PinnedBuf h_stage, h_pose;
+    std::vector<DevBuf*> all_bufs() {
+        return {&d_ring, &d_pos, &d_neg, &d_map_in, &d_qry_in, &d_bin_map, &d_bin_qry, &d_chunks, &d_chunk_range, &d_frame_off, &d_chcnt, &d_zmin,
+                &d_zmax, &d_cnt, &d_dst_start, &d_status, &d_action, &d_flag_slot, &d_nflag, &d_recs, &d_nrecs, &d_queue, &d_bucket, &d_frame_rej,
+                &d_map_sorted, &d_map_src, &d_qry_sorted, &d_qry_src, &d_part, &d_scratch, &d_keep, &d_ground, &d_arranged, &d_map_rej, &d_curr_rej,
+                &d_jobs, &d_out_sizes, &d_k5tmp, &d_fence, &d_vox, &d_vox_cnt, &d_vox_start, &d_vox_scratch, &d_frame_rec_base, &d_poses, &d_pack,
+                &d_gather};
+    }
 
     // batch geometry of the last run
     int      F = 0;
-    size_t   NM = 0, NQ = 0;
+    size_t   NM = 0, NQ = 0;                   // points of the map-side arrays (node mode: F * n_map) / of the queries
     uint32_t n_chunks_map = 0, n_chunks_qry = 0;
     uint32_t rec_capacity = 0;
     const float4* cur_map = nullptr;
     const float4* cur_qry = nullptr;
     std::vector<uint64_t> map_off, qry_off;
-    int      desc_mode = -1;                   // mode the uploaded chunk descriptors were built for (-1: none)
+    int      desc_mode = -1;                   // mode the uploaded chunk descriptors were built for (-1: none; 0 cloud, 1 batch masks, 2 node masks)
     uint64_t desc_epoch = 0;                   // bumped whenever the descriptors are rebuilt (invalidates cached graphs)
-    struct StepGraph { const void* map; const void* qry; void* keep; int kind; uint64_t epoch, alloc; cudaGraphExec_t exec;
-                       const void* fold_index; const void* fold_global; size_t fold_n; };
+    int      stat_F = 0;                       // frames of the last batch call (all its sub-batches): extent of the per-frame counters
+    int      f0 = 0;                           // first frame of the sub-batch being submitted
+    struct StepGraph { const void* ptr[8]; size_t fold_n; int kind, mode, f0; uint64_t epoch, alloc; cudaGraphExec_t exec; };
     std::vector<StepGraph> graphs;             // captured mask-mode steps, one per (pointers, geometry)
     bool     use_graphs = true;
     uint64_t graph_kernel_nodes = 0;
+    bool     pending = false;                  // an asynchronous submission has not been waited for yet
+
+    // node mode
+    erasor_map_ctx* map = nullptr;
+
+    // exchange
+    ncclComm_t comm = nullptr;
+    int        comm_ranks = 1, comm_rank = 0;
 
     // single-frame state machine
     int      stage = 0;                        // 0: nothing, 1: inputs set, 2: compared
@@ -130,6 +170,27 @@ namespace {
             return ERASOR_E_CUDA;                                                                  \
         }                                                                                          \
     } while (0)
+
+// NCCL is bound at run time: single-GPU users need no libnccl, and inside a torch process dlopen returns the copy torch
+// already loaded (same soname), so the process keeps exactly one NCCL.
+NcclApi* nccl_api(std::string& err) {
+    static NcclApi api;
+    static bool tried = false;
+    if (api.lib) return &api;
+    if (tried) { err = "libnccl.so.2 could not be loaded"; return nullptr; }
+    tried = true;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { err = std::string("dlopen(libnccl.so.2): ") + dlerror(); return nullptr; }
+    api.GetUniqueId    = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+    api.CommInitRank   = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+    api.CommDestroy    = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+    api.AllGather      = reinterpret_cast<decltype(api.AllGather)>(dlsym(lib, "ncclAllGather"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+    if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.GetErrorString) { err = "libnccl.so.2 lacks a required symbol"; return nullptr; }
+    api.lib = lib;
+    return &api;
+}
 
 struct Scope {   // optional CUDA-event bracket around a kernel (timing == true only)
     erasor_ctx* h; int id; cudaEvent_t a = nullptr, b = nullptr;
@@ -178,6 +239,8 @@ uint32_t choose_chunk(const erasor_ctx* h, const uint64_t* map_off, const uint64
 }
 
 // Build chunk descriptors + per-frame chunk ranges + frame offsets, upload them, size every buffer.
+// mode 0: single frame, cloud outputs; 1: batch of (map_voi, query_voi) pairs, masks; 2: node mode -- map_off is
+// {0, n_map, 2 n_map, ...}: every frame scans the whole resident map (fetch_VoI fused into K1), masks on global indices.
 int prepare_batch(erasor_ctx* h, const uint64_t* map_off, const uint64_t* qry_off, int F, int mode) {
     if (F <= 0) { h->err = "n_frames must be positive"; return ERASOR_E_INVALID; }
     const size_t NM = map_off[F], NQ = qry_off[F];
@@ -185,6 +248,9 @@ int prepare_batch(erasor_ctx* h, const uint64_t* map_off, const uint64_t* qry_of
     for (int f = 0; f < F; ++f)
         if (map_off[f + 1] < map_off[f] || qry_off[f + 1] < qry_off[f]) { h->err = "offsets must be non-decreasing"; return ERASOR_E_INVALID; }
     const int B = h->B;
+    // per-frame counters span the caller's whole batch (all its sub-batches), so they are sized before the shortcut below
+    CK(h->d_nflag.ensure(sizeof(uint32_t) * (size_t)std::max(h->stat_F, h->f0 + F)));
+    CK(h->d_frame_rej.ensure(sizeof(uint32_t) * (size_t)std::max(h->stat_F, h->f0 + F)));
     // same batch geometry as the previous call (the usual case when a caller streams equally-shaped batches):
     // the chunk descriptors already on the device are still valid -- skip rebuild, upload and the staging sync
     if (h->desc_mode == mode && h->F == F && h->map_off.size() == (size_t)F + 1 && h->qry_off.size() == (size_t)F + 1 &&
@@ -195,6 +261,7 @@ int prepare_batch(erasor_ctx* h, const uint64_t* map_off, const uint64_t* qry_of
     h->map_off.assign(map_off, map_off + F + 1);
     h->qry_off.assign(qry_off, qry_off + F + 1);
     const uint32_t CH = choose_chunk(h, map_off, qry_off, F);
+    const bool node = mode == 2;
 
     std::vector<ChunkDesc> chunks;
     std::vector<uint32_t>  range(2 * (size_t)(F + 1)), foff(2 * (size_t)(F + 1));
@@ -206,8 +273,11 @@ int prepare_batch(erasor_ctx* h, const uint64_t* map_off, const uint64_t* qry_of
             foff[(size_t)c * (F + 1) + f]  = (uint32_t)off[f];
             for (uint64_t b = off[f]; b < off[f + 1]; b += CH) {
                 ChunkDesc d{};
-                d.begin = (uint32_t)b; d.len = (uint32_t)std::min<uint64_t>(CH, off[f + 1] - b);
-                d.frame = (uint32_t)f; d.cloud = (uint32_t)c; d.frame_begin = (uint32_t)off[f];
+                d.len = (uint32_t)std::min<uint64_t>(CH, off[f + 1] - b);
+                d.frame = (uint32_t)f; d.cloud = (uint32_t)c;
+                d.bin_begin = (uint32_t)b; d.out_base = (uint32_t)off[f];
+                if (node && c == 0) { d.begin = (uint32_t)(b - off[f]); d.frame_begin = 0u; }      // source = the resident map itself
+                else                { d.begin = (uint32_t)b; d.frame_begin = (uint32_t)off[f]; }
                 chunks.push_back(d);
             }
         }
@@ -233,16 +303,15 @@ int prepare_batch(erasor_ctx* h, const uint64_t* map_off, const uint64_t* qry_of
     CK(h->d_status.ensure((size_t)F * B));
     CK(h->d_action.ensure((size_t)F * B));
     CK(h->d_flag_slot.ensure(sizeof(uint32_t) * (size_t)F * B));
-    CK(h->d_nflag.ensure(sizeof(uint32_t) * (size_t)F));
-    CK(h->d_frame_rej.ensure(sizeof(uint32_t) * (size_t)F));
     CK(h->d_frame_rec_base.ensure(sizeof(uint32_t) * (size_t)F));
-    h->rec_capacity = (uint32_t)std::min<size_t>((size_t)F * B, (size_t)1 << 21);
+    h->rec_capacity = (uint32_t)std::min<size_t>((size_t)F * B, kMaxRecords);
     CK(h->d_recs.ensure(sizeof(FlagRec) * (size_t)h->rec_capacity));
     CK(h->d_nrecs.ensure(sizeof(uint32_t) * 4));
     CK(h->d_queue.ensure(sizeof(uint32_t) * kQueueWords));
     CK(h->d_bucket.ensure(sizeof(uint32_t) * (size_t)kNumBuckets * h->rec_capacity));
     CK(h->d_map_src.ensure(sizeof(uint32_t) * std::max<size_t>(NM, 1)));
     CK(h->d_scratch.ensure((size_t)24 * std::max<size_t>(NM, 1) + 64));
+    if (node) CK(h->d_poses.ensure(sizeof(NodePose) * (size_t)F));
     if (mode == 0) {
         CK(h->d_qry_sorted.ensure(sizeof(float4) * std::max<size_t>(NQ, 1)));
         CK(h->d_qry_src.ensure(sizeof(uint32_t) * std::max<size_t>(NQ, 1)));
@@ -265,22 +334,23 @@ int prepare_batch(erasor_ctx* h, const uint64_t* map_off, const uint64_t* qry_of
     return ERASOR_OK;
 }
 
-int stage_inputs(erasor_ctx* h, const float* map_xyzi, const float* qry_xyzi, int ptr_kind) {
+// one caller cloud -> device pointer (staged through `stage` when it lives in host memory)
+int stage_cloud(erasor_ctx* h, DevBuf& stage, const float* xyzi, size_t n, int ptr_kind, const float4** out) {
     if (ptr_kind == ERASOR_PTR_DEVICE) {
-        h->cur_map = reinterpret_cast<const float4*>(map_xyzi);
-        h->cur_qry = reinterpret_cast<const float4*>(qry_xyzi);
-        if ((h->NM && (reinterpret_cast<uintptr_t>(map_xyzi) & 15)) || (h->NQ && (reinterpret_cast<uintptr_t>(qry_xyzi) & 15))) {
-            h->err = "device clouds must be 16-byte aligned (float4)"; return ERASOR_E_INVALID;
-        }
+        if (n && (reinterpret_cast<uintptr_t>(xyzi) & 15)) { h->err = "device clouds must be 16-byte aligned (float4)"; return ERASOR_E_INVALID; }
+        *out = reinterpret_cast<const float4*>(xyzi);
         return ERASOR_OK;
     }
-    CK(h->d_map_in.ensure(sizeof(float4) * std::max<size_t>(h->NM, 1)));
-    CK(h->d_qry_in.ensure(sizeof(float4) * std::max<size_t>(h->NQ, 1)));
-    if (h->NM) CK(cudaMemcpyAsync(h->d_map_in.p, map_xyzi, sizeof(float4) * h->NM, cudaMemcpyHostToDevice, h->stream));
-    if (h->NQ) CK(cudaMemcpyAsync(h->d_qry_in.p, qry_xyzi, sizeof(float4) * h->NQ, cudaMemcpyHostToDevice, h->stream));
-    h->cur_map = h->d_map_in.as<float4>();
-    h->cur_qry = h->d_qry_in.as<float4>();
+    CK(stage.ensure(sizeof(float4) * std::max<size_t>(n, 1)));
+    if (n) CK(cudaMemcpyAsync(stage.p, xyzi, sizeof(float4) * n, cudaMemcpyHostToDevice, h->stream));
+    *out = stage.as<float4>();
     return ERASOR_OK;
+}
+
+int stage_inputs(erasor_ctx* h, const float* map_xyzi, const float* qry_xyzi, int ptr_kind) {
+    int rc;
+    if ((rc = stage_cloud(h, h->d_map_in, map_xyzi, h->NM, ptr_kind, &h->cur_map))) return rc;
+    return stage_cloud(h, h->d_qry_in, qry_xyzi, h->NQ, ptr_kind, &h->cur_qry);
 }
 
 int run_k1(erasor_ctx* h, int mode) {
@@ -288,7 +358,7 @@ int run_k1(erasor_ctx* h, int mode) {
     {
         h->launches++;
         CK(launch_init_tables(h->stream, h->d_zmin.as<uint32_t>(), h->d_zmax.as<uint32_t>(), 2 * (size_t)F * B,
-                              h->d_cnt.as<uint32_t>(), 2 * (size_t)F * (B + 1), h->d_nrecs.as<uint32_t>(), h->d_frame_rej.as<uint32_t>(), F,
+                              h->d_cnt.as<uint32_t>(), 2 * (size_t)F * (B + 1), h->d_nrecs.as<uint32_t>(), h->d_frame_rej.as<uint32_t>() + h->f0, F,
                               h->d_queue.as<uint32_t>()));
     }
     {
@@ -296,25 +366,28 @@ int run_k1(erasor_ctx* h, int mode) {
         if (h->n_chunks_map + h->n_chunks_qry) h->launches++;
         CK(launch_k1(h->stream, h->view, h->cur_map, h->cur_qry, h->d_chunks.as<ChunkDesc>(), (int)(h->n_chunks_map + h->n_chunks_qry),
                      h->d_bin_map.as<uint16_t>(), h->d_bin_qry.as<uint16_t>(), h->d_chcnt.as<uint32_t>(), h->d_zmin.as<uint32_t>(),
-                     h->d_zmax.as<uint32_t>(), h->d_cnt.as<uint32_t>(), B, F, true, h->d_fence.as<unsigned long long>()));
+                     h->d_zmax.as<uint32_t>(), h->d_cnt.as<uint32_t>(), B, F, h->d_fence.as<unsigned long long>(),
+                     mode == 2 ? h->d_poses.as<NodePose>() : nullptr));
     }
     return ERASOR_OK;
 }
 
-// K3 -> K2 -> K4 ; mode 0: every bin scattered + partitioned copies (cloud outputs), mode 1: flagged only + masks
-int run_compare(erasor_ctx* h, int version, int mode, uint8_t* keep_mask, uint8_t* ground_mask) {
+// K3 -> K2 -> K4 ; mode 0: every bin scattered + partitioned copies (cloud outputs), mode 1 / 2: flagged only + masks
+int run_compare(erasor_ctx* h, int version, int mode, uint8_t* keep_mask, uint8_t* ground_mask, const K4Fold& fold) {
     const int B = h->B, F = h->F;
+    const NodePose* poses = mode == 2 ? h->d_poses.as<NodePose>() : nullptr;
+    uint32_t* nflag = h->d_nflag.as<uint32_t>() + h->f0;
     SrtParams sp{};
     sp.scan_ratio_threshold = h->p.scan_ratio_threshold;
     sp.th_bin_max_h = h->p.th_bin_max_h;
     sp.minimum_num_pts = h->p.minimum_num_pts;
-    sp.version = version; sp.R = h->p.num_rings; sp.S = h->p.num_sectors; sp.B = B; sp.scatter_mode = mode;
+    sp.version = version; sp.R = h->p.num_rings; sp.S = h->p.num_sectors; sp.B = B; sp.scatter_mode = mode == 0 ? 0 : 1;
     {
         Scope s(h, 3);
         h->launches++;
         CK(launch_k3(h->stream, sp, F, h->d_chunk_range.as<uint32_t>(), h->d_chcnt.as<uint32_t>(), h->d_zmin.as<uint32_t>(),
                      h->d_zmax.as<uint32_t>(), h->d_frame_off.as<uint32_t>(), h->d_cnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>(),
-                     h->d_status.as<uint8_t>(), h->d_action.as<uint8_t>(), h->d_flag_slot.as<uint32_t>(), h->d_nflag.as<uint32_t>(),
+                     h->d_status.as<uint8_t>(), h->d_action.as<uint8_t>(), h->d_flag_slot.as<uint32_t>(), nflag,
                      h->d_frame_rec_base.as<uint32_t>(), h->d_recs.as<FlagRec>(), h->d_nrecs.as<uint32_t>(), h->rec_capacity,
                      h->d_queue.as<uint32_t>(), h->d_bucket.as<uint32_t>()));
     }
@@ -322,17 +395,18 @@ int run_compare(erasor_ctx* h, int version, int mode, uint8_t* keep_mask, uint8_
         Scope s(h, 2);
         if (mode == 0) {
             if (h->n_chunks_map) h->launches++;
-            CK(launch_k2(h->stream, h->d_chunks.as<ChunkDesc>(), 0u, h->n_chunks_map, F, h->d_bin_map.as<uint16_t>(), h->cur_map,
-                         h->d_chcnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>(), h->d_map_sorted.as<float4>(), h->d_map_src.as<uint32_t>(), B));
+            CK(launch_k2(h->stream, h->d_chunks.as<ChunkDesc>(), 0u, h->n_chunks_map, h->d_bin_map.as<uint16_t>(), h->cur_map, nullptr,
+                         h->d_chcnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>(), nullptr, nullptr, h->d_map_sorted.as<float4>(), h->d_map_src.as<uint32_t>(), B));
             if (h->n_chunks_qry) h->launches++;
-            CK(launch_k2(h->stream, h->d_chunks.as<ChunkDesc>(), h->n_chunks_map, h->n_chunks_qry, F, h->d_bin_qry.as<uint16_t>(), h->cur_qry,
-                         h->d_chcnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>() + (size_t)F * (B + 2), h->d_qry_sorted.as<float4>(),
+            CK(launch_k2(h->stream, h->d_chunks.as<ChunkDesc>(), h->n_chunks_map, h->n_chunks_qry, h->d_bin_qry.as<uint16_t>(), h->cur_qry, nullptr,
+                         h->d_chcnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>() + (size_t)F * (B + 2), nullptr, nullptr, h->d_qry_sorted.as<float4>(),
                          h->d_qry_src.as<uint32_t>(), B));
         } else {
-            // mask mode: the same stable scatter, restricted by dst_start to the flagged bins
+            // mask modes: the same stable scatter, restricted to the flagged bins (K3's dense slots)
             if (h->n_chunks_map) h->launches++;
-            CK(launch_k2(h->stream, h->d_chunks.as<ChunkDesc>(), 0u, h->n_chunks_map, F, h->d_bin_map.as<uint16_t>(), h->cur_map,
-                         h->d_chcnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>(), h->d_map_sorted.as<float4>(), h->d_map_src.as<uint32_t>(), B));
+            CK(launch_k2(h->stream, h->d_chunks.as<ChunkDesc>(), 0u, h->n_chunks_map, h->d_bin_map.as<uint16_t>(), h->cur_map, poses,
+                         h->d_chcnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>(), h->d_flag_slot.as<uint32_t>(), nflag,
+                         h->d_map_sorted.as<float4>(), h->d_map_src.as<uint32_t>(), B));
         }
     }
     {
@@ -347,7 +421,7 @@ int run_compare(erasor_ctx* h, int version, int mode, uint8_t* keep_mask, uint8_
         CK(launch_k4(h->stream, h->stream_b, h->stream_c, gp, h->d_recs.as<FlagRec>(), h->d_queue.as<uint32_t>(), h->d_bucket.as<uint32_t>(), h->rec_capacity,
                      h->d_map_sorted.as<float4>(), h->d_map_src.as<uint32_t>(), h->cur_map,
                      h->d_frame_off.as<uint32_t>(), mode == 0 ? h->d_part.as<float4>() : nullptr, keep_mask, ground_mask,
-                     h->d_frame_rej.as<uint32_t>(), h->d_scratch.as<unsigned char>(), h->sm_count, h->d_fence.as<unsigned long long>()));
+                     h->d_frame_rej.as<uint32_t>() + h->f0, h->d_scratch.as<unsigned char>(), h->sm_count, h->d_fence.as<unsigned long long>(), fold));
         CK(cudaEventRecord(h->ev_join_b, h->stream_b));
         CK(cudaEventRecord(h->ev_join_c, h->stream_c));
         CK(cudaStreamWaitEvent(h->stream, h->ev_join_b, 0));
@@ -399,6 +473,7 @@ int erasor_create(const erasor_params_t* params, int device, erasor_handle_t* ou
     if (device < 0 || device >= ndev) { g_create_error = "bad device index"; return ERASOR_E_INVALID; }
     erasor_ctx* h = new erasor_ctx();
     h->p = p; h->device = device; h->B = (int)Bll;
+    for (DevBuf* b : h->all_bufs()) b->epoch = &h->alloc_epoch;
     if (const char* ng = std::getenv("ERASOR_B200_NO_GRAPH")) h->use_graphs = !(ng[0] == '1');
     std::string terr;
     if (build_bin_tables(p, h->tables, terr) != 0) { g_create_error = terr; delete h; return ERASOR_E_INVALID; }
@@ -443,13 +518,9 @@ void erasor_destroy(erasor_handle_t h) {
     drain_timers(h);
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
     h->graphs.clear();
-    DevBuf* bufs[] = {&h->d_ring, &h->d_pos, &h->d_neg, &h->d_map_in, &h->d_qry_in, &h->d_bin_map, &h->d_bin_qry, &h->d_chunks,
-                      &h->d_chunk_range, &h->d_frame_off, &h->d_chcnt, &h->d_zmin, &h->d_zmax, &h->d_cnt, &h->d_dst_start, &h->d_status,
-                      &h->d_action, &h->d_flag_slot, &h->d_nflag, &h->d_recs, &h->d_nrecs, &h->d_queue, &h->d_bucket, &h->d_frame_rej, &h->d_map_sorted, &h->d_map_src,
-                      &h->d_qry_sorted, &h->d_qry_src, &h->d_part, &h->d_scratch, &h->d_keep, &h->d_ground, &h->d_arranged, &h->d_map_rej,
-                      &h->d_curr_rej, &h->d_jobs, &h->d_out_sizes, &h->d_k5tmp, &h->d_fence, &h->d_vox, &h->d_vox_cnt, &h->d_vox_start,
-                      &h->d_vox_scratch, &h->d_frame_rec_base};
-    for (DevBuf* b : bufs) b->release();
+    if (h->comm) { NcclApi* api = nccl_api(h->err); if (api) api->CommDestroy(h->comm); h->comm = nullptr; }
+    for (DevBuf* b : h->all_bufs()) b->release();
+    h->h_pose.release();
     h->h_stage.release();
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join_b) cudaEventDestroy(h->ev_join_b);
@@ -474,9 +545,12 @@ int erasor_set_inputs(erasor_handle_t h, const float* map_voi_xyzi, size_t n_map
     if (!h) return ERASOR_E_INVALID;
     if ((n_map && !map_voi_xyzi) || (n_query && !query_voi_xyzi)) { h->err = "null cloud"; return ERASOR_E_INVALID; }
     CK(cudaSetDevice(h->device));
+    int rc;
+    if (h->pending && (rc = erasor_wait(h))) return rc;
     h->stage = 0;
+    h->f0 = 0; h->stat_F = 1;
     const uint64_t mo[2] = {0, n_map}, qo[2] = {0, n_query};
-    int rc = prepare_batch(h, mo, qo, 1, 0);
+    rc = prepare_batch(h, mo, qo, 1, 0);
     if (rc) return rc;
     if ((rc = stage_inputs(h, map_voi_xyzi, query_voi_xyzi, ptr_kind))) return rc;
     if ((rc = run_k1(h, 0))) return rc;
@@ -497,7 +571,7 @@ int erasor_compare(erasor_handle_t h, int version, int frame) {
     CK(h->d_ground.ensure(std::max<size_t>(NM, 1)));
     CK(cudaMemsetAsync(h->d_keep.p, 1, std::max<size_t>(NM, 1), h->stream));
     CK(cudaMemsetAsync(h->d_ground.p, 0, std::max<size_t>(NM, 1), h->stream));
-    int rc = run_compare(h, version, 0, h->d_keep.as<uint8_t>(), h->d_ground.as<uint8_t>());
+    int rc = run_compare(h, version, 0, h->d_keep.as<uint8_t>(), h->d_ground.as<uint8_t>(), K4Fold{nullptr, nullptr, 0u, 0u});
     if (rc) return rc;
     const bool vox = (version == 3) && !h->p.skip_voxelize;
     if (vox) {
@@ -671,62 +745,105 @@ int erasor_get_fence_counts(erasor_handle_t h, uint64_t* negzero_points, uint64_
 }
 
 namespace {
-// erasor_process_frames, optionally followed (same stream / same graph, before the host synchronises) by the fold of the
-// fresh masks onto the global map
-int process_frames_impl(erasor_handle_t h, const float* map_xyzi, const uint64_t* map_offsets, const float* query_xyzi,
-                        const uint64_t* query_offsets, int n_frames, uint8_t* keep_mask, int ptr_kind,
-                        const uint32_t* fold_index, uint8_t* fold_global, size_t fold_n_global) {
-    if (!h || !map_offsets || !query_offsets || !keep_mask) { if (h) h->err = "null argument"; return ERASOR_E_INVALID; }
+
+// One submission of a mask mode: a batch of (map_voi, query_voi) pairs (mode 1) or of nodes against the resident map (mode 2).
+struct Submit {
+    int mode = 1;
+    const float*    map_xyzi = nullptr;     // mode 1
+    const uint64_t* map_off = nullptr;      // mode 1: caller's offsets; mode 2: {0, n_map, 2 n_map, ...}
+    const float*    qry_xyzi = nullptr;
+    const uint64_t* qry_off = nullptr;
+    int             F = 0;
+    uint8_t*        keep_mask = nullptr;    // mode 1: one byte per VoI point; mode 2: frame_keep [F][n_map] (nullable)
+    int             ptr_kind = ERASOR_PTR_HOST;
+    const uint32_t* fold_index = nullptr;   // mode 1 fold (nullable)
+    uint8_t*        fold_global = nullptr;
+    size_t          fold_n = 0;
+    const NodePose* poses = nullptr;        // mode 2: host array [F]
+    uint8_t*        keep_out = nullptr;     // mode 2 (nullable)
+    int             f0 = 0;                 // index of the first frame within the caller's batch (per-frame counters)
+};
+
+bool is_pinned_host(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// Enqueue one submission on the handle's stream (CUDA graph when possible) and return without waiting.
+// The whole step (copies, memset, K1, K3, K2, the three concurrent K4 classes with the fold in their epilogue, mask /
+// counter read-back) is a fixed launch sequence once the batch geometry and the buffers are known: it is captured into a
+// CUDA graph the first time and replayed afterwards (one launch instead of ~15 API calls).
+int submit(erasor_ctx* h, const Submit& S) {
+    int rc;
     CK(cudaSetDevice(h->device));
+    if (h->pending && (rc = erasor_wait(h))) return rc;      // one submission in flight per handle (buffers and staging are reused)
     h->stage = 0;
-    int rc = prepare_batch(h, map_offsets, query_offsets, n_frames, 1);
-    if (rc) return rc;
-    if ((h->NM && !map_xyzi) || (h->NQ && !query_xyzi)) { h->err = "null cloud"; return ERASOR_E_INVALID; }
-    // the whole step (copies, memset, K1, K3, K2, the three concurrent K4 classes, mask / counter read-back) is a fixed
-    // launch sequence once the batch geometry and the buffers are known: capture it into a CUDA graph the first time and
-    // replay it afterwards (one launch instead of ~15 API calls; the kernels' dependencies become graph edges).
+    h->f0 = S.f0;
+    if ((rc = prepare_batch(h, S.map_off, S.qry_off, S.F, S.mode))) return rc;
+    const bool host = S.ptr_kind != ERASOR_PTR_DEVICE;
+    const size_t n_keep = S.keep_mask ? h->NM : 0;          // bytes of the per-frame mask output
+    const size_t n_map_global = S.mode == 2 ? h->map->n : 0;
+    if (S.mode == 1 && ((h->NM && !S.map_xyzi) || (h->NQ && !S.qry_xyzi))) { h->err = "null cloud"; return ERASOR_E_INVALID; }
+    if (S.mode == 2 && h->NQ && !S.qry_xyzi) { h->err = "null cloud"; return ERASOR_E_INVALID; }
+    if (host) {
+        if (n_keep) CK(h->d_keep.ensure(std::max<size_t>(n_keep, 1)));
+        if (S.mode == 1) CK(h->d_map_in.ensure(sizeof(float4) * std::max<size_t>(h->NM, 1)));
+        CK(h->d_qry_in.ensure(sizeof(float4) * std::max<size_t>(h->NQ, 1)));
+    }
+    if (S.mode == 2) {
+        if (sizeof(NodePose) * (size_t)S.F > h->h_pose.cap) h->alloc_epoch++;      // captured graphs copy from this staging buffer
+        CK(h->h_pose.ensure(sizeof(NodePose) * (size_t)S.F));
+        std::memcpy(h->h_pose.p, S.poses, sizeof(NodePose) * (size_t)S.F);
+    }
     auto enqueue = [&]() -> int {
         int r;
-        if ((r = stage_inputs(h, map_xyzi, query_xyzi, ptr_kind))) return r;
-        uint8_t* d_keep = keep_mask;
-        if (ptr_kind != ERASOR_PTR_DEVICE) d_keep = h->d_keep.as<uint8_t>();
-        if (h->NM) CK(cudaMemsetAsync(d_keep, 1, h->NM, h->stream));
-        if ((r = run_k1(h, 1))) return r;
-        if ((r = run_compare(h, h->p.version, 1, d_keep, nullptr))) return r;
-        if (fold_global) {
-            h->launches++;
-            CK(launch_fold_keep(h->stream, d_keep, fold_index, h->NM, fold_global, fold_n_global));
+        if (S.mode == 1) {
+            if ((r = stage_inputs(h, S.map_xyzi, S.qry_xyzi, S.ptr_kind))) return r;
+        } else {
+            h->cur_map = reinterpret_cast<const float4*>(h->map->d_pts);
+            if ((r = stage_cloud(h, h->d_qry_in, S.qry_xyzi, h->NQ, S.ptr_kind, &h->cur_qry))) return r;
+            CK(cudaMemcpyAsync(h->d_poses.p, h->h_pose.p, sizeof(NodePose) * (size_t)S.F, cudaMemcpyHostToDevice, h->stream));
         }
-        if (ptr_kind != ERASOR_PTR_DEVICE && h->NM)
-            CK(cudaMemcpyAsync(keep_mask, d_keep, h->NM, cudaMemcpyDeviceToHost, h->stream));
+        uint8_t* d_keep = nullptr;
+        if (n_keep) {
+            d_keep = host ? h->d_keep.as<uint8_t>() : S.keep_mask;
+            CK(cudaMemsetAsync(d_keep, 1, n_keep, h->stream));
+        }
+        if ((r = run_k1(h, S.mode))) return r;
+        K4Fold fold{nullptr, nullptr, 0u, 0u};
+        if (S.mode == 2)        fold = K4Fold{h->map->d_keep, nullptr, (uint32_t)n_map_global, 0u};
+        else if (S.fold_global) fold = K4Fold{S.fold_global, S.fold_index, (uint32_t)std::min<size_t>(S.fold_n, 0xFFFFFFFFu), 0u};
+        if ((r = run_compare(h, h->p.version, S.mode, d_keep, nullptr, fold))) return r;
+        if (host && n_keep) CK(cudaMemcpyAsync(S.keep_mask, d_keep, n_keep, cudaMemcpyDeviceToHost, h->stream));
+        if (S.keep_out && n_map_global)
+            CK(cudaMemcpyAsync(S.keep_out, h->map->d_keep, n_map_global, host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, h->stream));
         CK(cudaMemcpyAsync(&h->n_recs_host, h->d_nrecs.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
         return ERASOR_OK;
     };
-    if (ptr_kind != ERASOR_PTR_DEVICE) {
-        CK(h->d_keep.ensure(std::max<size_t>(h->NM, 1)));
-        CK(h->d_map_in.ensure(sizeof(float4) * std::max<size_t>(h->NM, 1)));
-        CK(h->d_qry_in.ensure(sizeof(float4) * std::max<size_t>(h->NQ, 1)));
-    }
     bool graphable = h->use_graphs && !h->timing;
-    if (graphable && ptr_kind != ERASOR_PTR_DEVICE) {
+    if (graphable && host) {
         // host buffers must be pinned for copies to be capturable
-        cudaPointerAttributes a{};
-        const void* ptrs[3] = {map_xyzi, query_xyzi, keep_mask};
-        const size_t need[3] = {h->NM, h->NQ, h->NM};
-        for (int i = 0; i < 3 && graphable; ++i) {
-            if (!need[i]) continue;
-            if (cudaPointerGetAttributes(&a, ptrs[i]) != cudaSuccess || a.type != cudaMemoryTypeHost) { graphable = false; cudaGetLastError(); }
-        }
+        if (S.mode == 1 && h->NM && !is_pinned_host(S.map_xyzi)) graphable = false;
+        if (h->NQ && !is_pinned_host(S.qry_xyzi)) graphable = false;
+        if (n_keep && !is_pinned_host(S.keep_mask)) graphable = false;
+        if (S.keep_out && n_map_global && !is_pinned_host(S.keep_out)) graphable = false;
     }
     if (graphable) {
+        erasor_ctx::StepGraph key{};
+        key.ptr[0] = S.map_xyzi; key.ptr[1] = S.qry_xyzi; key.ptr[2] = S.keep_mask; key.ptr[3] = S.fold_index; key.ptr[4] = S.fold_global;
+        key.ptr[5] = S.keep_out; key.ptr[6] = S.mode == 2 ? (const void*)h->map : nullptr; key.ptr[7] = nullptr;
+        key.fold_n = S.fold_n; key.kind = S.ptr_kind; key.mode = S.mode; key.f0 = S.f0; key.epoch = h->desc_epoch; key.alloc = h->alloc_epoch;
+        auto same = [&](const erasor_ctx::StepGraph& g) {
+            return std::equal(g.ptr, g.ptr + 8, key.ptr) && g.fold_n == key.fold_n && g.kind == key.kind && g.mode == key.mode && g.f0 == key.f0 &&
+                   g.epoch == key.epoch && g.alloc == key.alloc;
+        };
         cudaGraphExec_t exec = nullptr;
-        for (auto& g : h->graphs)
-            if (g.map == map_xyzi && g.qry == query_xyzi && g.keep == keep_mask && g.kind == ptr_kind && g.epoch == h->desc_epoch && g.alloc == g_alloc_epoch &&
-                g.fold_index == fold_index && g.fold_global == fold_global && g.fold_n == fold_n_global) exec = g.exec;
+        for (auto& g : h->graphs) if (same(g)) exec = g.exec;
         if (!exec) {
             // drop graphs of older geometries, bound the cache
             for (size_t i = 0; i < h->graphs.size();) {
-                if (h->graphs[i].epoch != h->desc_epoch || h->graphs[i].alloc != g_alloc_epoch || h->graphs.size() > 16) { cudaGraphExecDestroy(h->graphs[i].exec); h->graphs.erase(h->graphs.begin() + i); }
+                if (h->graphs[i].epoch != h->desc_epoch || h->graphs[i].alloc != h->alloc_epoch || h->graphs.size() > 16) { cudaGraphExecDestroy(h->graphs[i].exec); h->graphs.erase(h->graphs.begin() + i); }
                 else ++i;
             }
             cudaGraph_t graph = nullptr;
@@ -736,10 +853,10 @@ int process_frames_impl(erasor_handle_t h, const float* map_xyzi, const uint64_t
             h->graph_kernel_nodes = h->launches - launches_before;
             h->launches = launches_before;                              // captured, not launched
             cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
-            if (rc == ERASOR_OK && ce == cudaSuccess && graph) {
+            if (rc == ERASOR_OK && ce == cudaSuccess && graph && h->alloc_epoch == key.alloc) {
                 ce = cudaGraphInstantiate(&exec, graph, 0);
                 cudaGraphDestroy(graph);
-                if (ce == cudaSuccess) h->graphs.push_back(erasor_ctx::StepGraph{map_xyzi, query_xyzi, keep_mask, ptr_kind, h->desc_epoch, g_alloc_epoch, exec, fold_index, fold_global, fold_n_global});
+                if (ce == cudaSuccess) { key.exec = exec; h->graphs.push_back(key); }
                 else exec = nullptr;
             } else {
                 if (graph) cudaGraphDestroy(graph);
@@ -757,15 +874,115 @@ int process_frames_impl(erasor_handle_t h, const float* map_xyzi, const uint64_t
         Scope whole(h, 0);
         if ((rc = enqueue())) return rc;
     }
-    CK(cudaStreamSynchronize(h->stream));
-    if (h->n_recs_host > h->rec_capacity) { h->err = "flagged-bin records overflowed; split the batch"; return ERASOR_E_CAPACITY; }
+    h->pending = true;
     return ERASOR_OK;
+}
+
+// frames [f0, f1) that fit one submission: < 2^32 points per side and at most kMaxRecords flagged-bin records
+int sub_batch_end(const erasor_ctx* h, const uint64_t* map_off, const uint64_t* qry_off, int f0, int F) {
+    const uint64_t lim = 0xFFFFFFF0ull;
+    const int max_frames = (int)std::max<size_t>(1, kMaxRecords / (size_t)h->B);
+    int f1 = f0;
+    while (f1 < F && f1 - f0 < max_frames && map_off[f1 + 1] - map_off[f0] < lim && qry_off[f1 + 1] - qry_off[f0] < lim) ++f1;
+    return f1;
+}
+
+int process_frames_impl(erasor_handle_t h, const float* map_xyzi, const uint64_t* map_offsets, const float* query_xyzi,
+                        const uint64_t* query_offsets, int n_frames, uint8_t* keep_mask, int ptr_kind,
+                        const uint32_t* fold_index, uint8_t* fold_global, size_t fold_n_global, bool async) {
+    if (!h || !map_offsets || !query_offsets || !keep_mask) { if (h) h->err = "null argument"; return ERASOR_E_INVALID; }
+    if (n_frames <= 0) { h->err = "n_frames must be positive"; return ERASOR_E_INVALID; }
+    int rc;
+    if (h->pending && (rc = erasor_wait(h))) return rc;
+    h->stat_F = n_frames;
+    std::vector<uint64_t> mo, qo;
+    for (int f0 = 0; f0 < n_frames;) {
+        const int f1 = sub_batch_end(h, map_offsets, query_offsets, f0, n_frames);
+        if (f1 == f0) { h->err = "a single frame exceeds 2^32 points"; return ERASOR_E_INVALID; }
+        Submit S;
+        S.mode = 1; S.F = f1 - f0; S.ptr_kind = ptr_kind; S.f0 = f0;
+        const uint64_t m0 = map_offsets[f0], q0 = query_offsets[f0];
+        if (f0 == 0 && f1 == n_frames) { S.map_off = map_offsets; S.qry_off = query_offsets; }
+        else {
+            mo.assign(map_offsets + f0, map_offsets + f1 + 1); qo.assign(query_offsets + f0, query_offsets + f1 + 1);
+            for (auto& v : mo) v -= m0;
+            for (auto& v : qo) v -= q0;
+            S.map_off = mo.data(); S.qry_off = qo.data();
+        }
+        S.map_xyzi = map_xyzi ? map_xyzi + 4 * m0 : nullptr;
+        S.qry_xyzi = query_xyzi ? query_xyzi + 4 * q0 : nullptr;
+        S.keep_mask = keep_mask + m0;
+        S.fold_index = fold_index ? fold_index + m0 : nullptr; S.fold_global = fold_global; S.fold_n = fold_n_global;
+        if ((rc = submit(h, S))) return rc;
+        f0 = f1;
+        if (f0 < n_frames && (rc = erasor_wait(h))) return rc;      // the next sub-batch reuses the handle's buffers
+    }
+    return async ? ERASOR_OK : erasor_wait(h);
+}
+
+int process_nodes_impl(erasor_handle_t h, const double* poses7, const float* query_xyzi, const uint64_t* query_offsets, int n_frames,
+                       double voi_max_range, uint8_t* frame_keep, uint8_t* keep_out, int ptr_kind, bool async) {
+    if (!h || !poses7 || !query_offsets) { if (h) h->err = "null argument"; return ERASOR_E_INVALID; }
+    if (!h->map) { h->err = "erasor_process_nodes: no map attached (erasor_attach_map)"; return ERASOR_E_STATE; }
+    if (n_frames <= 0) { h->err = "n_frames must be positive"; return ERASOR_E_INVALID; }
+    int rc;
+    if (h->pending && (rc = erasor_wait(h))) return rc;
+    const size_t N = h->map->n;
+    const double range = voi_max_range > 0.0 ? voi_max_range : h->p.max_range;
+    h->stat_F = n_frames;
+    // scratch per (frame, map point): bin id 2 + scattered point 16 + source index 4 + class-C scratch 24 bytes
+    size_t budget = (size_t)16 << 30;
+    if (const char* e = std::getenv("ERASOR_B200_NODE_SCRATCH_GB")) budget = (size_t)std::max(1.0, std::atof(e)) << 30;
+    const size_t by_mem = std::max<size_t>(1, budget / (46 * std::max<size_t>(N, 1)));
+    const size_t by_idx = std::max<size_t>(1, (size_t)0xFFFFFFF0ull / std::max<size_t>(N, 1) - 1);
+    const int max_frames = (int)std::min<size_t>({by_mem, by_idx, std::max<size_t>(1, kMaxRecords / (size_t)h->B), (size_t)n_frames});
+    std::vector<uint64_t> mo, qo;
+    std::vector<NodePose> poses;
+    for (int f0 = 0; f0 < n_frames;) {
+        int f1 = f0;
+        while (f1 < n_frames && f1 - f0 < max_frames && query_offsets[f1 + 1] - query_offsets[f0] < 0xFFFFFFF0ull) ++f1;
+        if (f1 == f0) { h->err = "a single query exceeds 2^32 points"; return ERASOR_E_INVALID; }
+        const int F = f1 - f0;
+        mo.resize((size_t)F + 1);
+        for (int f = 0; f <= F; ++f) mo[f] = (uint64_t)f * N;
+        const uint64_t q0 = query_offsets[f0];
+        qo.assign(query_offsets + f0, query_offsets + f1 + 1);
+        for (auto& v : qo) v -= q0;
+        poses.resize(F);
+        for (int f = 0; f < F; ++f) node_pose_of(poses7 + 7 * (size_t)(f0 + f), range, poses[f]);
+        Submit S;
+        S.mode = 2; S.F = F; S.ptr_kind = ptr_kind; S.f0 = f0;
+        S.map_off = mo.data(); S.qry_off = qo.data();
+        S.qry_xyzi = query_xyzi ? query_xyzi + 4 * q0 : nullptr;
+        S.keep_mask = frame_keep ? frame_keep + (size_t)f0 * N : nullptr;
+        S.poses = poses.data();
+        S.keep_out = (f1 == n_frames) ? keep_out : nullptr;
+        if ((rc = submit(h, S))) return rc;
+        f0 = f1;
+        if (f0 < n_frames && (rc = erasor_wait(h))) return rc;
+    }
+    return async ? ERASOR_OK : erasor_wait(h);
 }
 }  // namespace
 
+int erasor_wait(erasor_handle_t h) {
+    if (!h) return ERASOR_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->pending) {
+        h->pending = false;
+        if (h->n_recs_host > h->rec_capacity) { h->err = "internal: flagged-bin records overflowed the work queue"; return ERASOR_E_CAPACITY; }
+    }
+    return ERASOR_OK;
+}
+
 int erasor_process_frames(erasor_handle_t h, const float* map_xyzi, const uint64_t* map_offsets, const float* query_xyzi,
                           const uint64_t* query_offsets, int n_frames, uint8_t* keep_mask, int ptr_kind) {
-    return process_frames_impl(h, map_xyzi, map_offsets, query_xyzi, query_offsets, n_frames, keep_mask, ptr_kind, nullptr, nullptr, 0);
+    return process_frames_impl(h, map_xyzi, map_offsets, query_xyzi, query_offsets, n_frames, keep_mask, ptr_kind, nullptr, nullptr, 0, false);
+}
+int erasor_process_frames_async(erasor_handle_t h, const float* map_xyzi, const uint64_t* map_offsets, const float* query_xyzi,
+                                const uint64_t* query_offsets, int n_frames, uint8_t* keep_mask, int ptr_kind) {
+    return process_frames_impl(h, map_xyzi, map_offsets, query_xyzi, query_offsets, n_frames, keep_mask, ptr_kind, nullptr, nullptr, 0, true);
 }
 
 int erasor_process_frames_fold(erasor_handle_t h, const float* map_xyzi, const uint64_t* map_offsets, const float* query_xyzi,
@@ -773,17 +990,202 @@ int erasor_process_frames_fold(erasor_handle_t h, const float* map_xyzi, const u
                                const uint32_t* voi_index, uint8_t* global_keep, size_t n_global) {
     if (!h) return ERASOR_E_INVALID;
     if (!voi_index || !global_keep) { h->err = "null fold argument"; return ERASOR_E_INVALID; }
-    return process_frames_impl(h, map_xyzi, map_offsets, query_xyzi, query_offsets, n_frames, keep_mask, ptr_kind, voi_index, global_keep, n_global);
+    return process_frames_impl(h, map_xyzi, map_offsets, query_xyzi, query_offsets, n_frames, keep_mask, ptr_kind, voi_index, global_keep, n_global, false);
+}
+int erasor_process_frames_fold_async(erasor_handle_t h, const float* map_xyzi, const uint64_t* map_offsets, const float* query_xyzi,
+                                     const uint64_t* query_offsets, int n_frames, uint8_t* keep_mask, int ptr_kind,
+                                     const uint32_t* voi_index, uint8_t* global_keep, size_t n_global) {
+    if (!h) return ERASOR_E_INVALID;
+    if (!voi_index || !global_keep) { h->err = "null fold argument"; return ERASOR_E_INVALID; }
+    return process_frames_impl(h, map_xyzi, map_offsets, query_xyzi, query_offsets, n_frames, keep_mask, ptr_kind, voi_index, global_keep, n_global, true);
 }
 
-// Multi-GPU exchange helper: fold the per-frame keep masks of erasor_process_frames onto the global
-// map (global_keep[voi_index[i]] = 0 where keep[i] == 0, everything else 1).  All pointers are DEVICE pointers; runs on
-// the handle's stream, asynchronously -- order your collective after erasor_stream(h).
+// Multi-GPU exchange helper: fold per-frame keep masks onto the global map
+// (global_keep[voi_index[i]] = 0 where keep[i] == 0).  Accumulates; all pointers are DEVICE pointers; asynchronous on the
+// handle's stream.  (erasor_process_frames_fold / erasor_process_nodes do this inside R-GPF's epilogue instead.)
 int erasor_fold_keep_masks(erasor_handle_t h, const uint8_t* keep_mask, const uint32_t* voi_index, size_t n, uint8_t* global_keep, size_t n_global) {
     if (!h || !global_keep || (n && (!keep_mask || !voi_index))) { if (h) h->err = "null argument"; return ERASOR_E_INVALID; }
+    if (n_global > 0xFFFFFFFFull) { h->err = "global map beyond 2^32 points"; return ERASOR_E_INVALID; }
     CK(cudaSetDevice(h->device));
-    h->launches++;
+    if (n) h->launches++;
     CK(launch_fold_keep(h->stream, keep_mask, voi_index, n, global_keep, n_global));
+    return ERASOR_OK;
+}
+
+int erasor_reset_keep_mask(erasor_handle_t h, uint8_t* global_keep, size_t n_global) {
+    if (!h || (n_global && !global_keep)) { if (h) h->err = "null argument"; return ERASOR_E_INVALID; }
+    CK(cudaSetDevice(h->device));
+    if (n_global) h->launches++;
+    CK(launch_fill_u8(h->stream, global_keep, n_global, 1));
+    return ERASOR_OK;
+}
+
+// ---- map-resident mode -------------------------------------------------------------------------------------------
+int erasor_map_create(const float* map_xyzi, size_t n_map, int ptr_kind, int device, erasor_map_t* out) {
+    if (!out || (n_map && !map_xyzi)) { g_create_error = "null argument"; return ERASOR_E_INVALID; }
+    *out = nullptr;
+    if (n_map >= 0xFFFFFFF0ull) { g_create_error = "map beyond 2^32 points"; return ERASOR_E_INVALID; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { g_create_error = "no CUDA device (this library has no CPU path)"; return ERASOR_E_CUDA; }
+    if (device < 0 || device >= ndev) { g_create_error = "bad device index"; return ERASOR_E_INVALID; }
+    erasor_map_ctx* m = new erasor_map_ctx();
+    m->device = device; m->n = n_map;
+    auto fail = [&](const char* what, cudaError_t ce) { g_create_error = std::string(what) + ": " + cudaGetErrorString(ce); erasor_map_destroy(m); return ERASOR_E_CUDA; };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    if ((e = cudaMalloc(&m->d_pts, sizeof(float4) * std::max<size_t>(n_map, 1))) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = cudaMalloc(&m->d_keep, std::max<size_t>(n_map, 1))) != cudaSuccess) return fail("cudaMalloc", e);
+    if (n_map) {
+        const cudaMemcpyKind k = ptr_kind == ERASOR_PTR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        if ((e = cudaMemcpyAsync(m->d_pts, map_xyzi, sizeof(float4) * n_map, k, m->st)) != cudaSuccess) return fail("cudaMemcpy", e);
+        if ((e = cudaMemsetAsync(m->d_keep, 1, n_map, m->st)) != cudaSuccess) return fail("cudaMemset", e);
+    }
+    if ((e = cudaStreamSynchronize(m->st)) != cudaSuccess) return fail("cudaStreamSynchronize", e);
+    *out = m;
+    return ERASOR_OK;
+}
+
+void erasor_map_destroy(erasor_map_t m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->st) { cudaStreamSynchronize(m->st); cudaStreamDestroy(m->st); }
+    if (m->d_pts) cudaFree(m->d_pts);
+    if (m->d_keep) cudaFree(m->d_keep);
+    delete m;
+}
+
+size_t erasor_map_size(erasor_map_t m) { return m ? m->n : 0; }
+uint8_t* erasor_map_keep_device(erasor_map_t m) { return m ? m->d_keep : nullptr; }
+const float* erasor_map_points_device(erasor_map_t m) { return m ? reinterpret_cast<const float*>(m->d_pts) : nullptr; }
+
+int erasor_map_reset_keep(erasor_map_t m) {
+    if (!m) return ERASOR_E_INVALID;
+    if (cudaSetDevice(m->device) != cudaSuccess) return ERASOR_E_CUDA;
+    if (m->n && cudaMemsetAsync(m->d_keep, 1, m->n, m->st) != cudaSuccess) return ERASOR_E_CUDA;
+    return cudaStreamSynchronize(m->st) == cudaSuccess ? ERASOR_OK : ERASOR_E_CUDA;
+}
+
+int erasor_map_get_keep(erasor_map_t m, uint8_t* keep, int ptr_kind) {
+    if (!m || (m->n && !keep)) return ERASOR_E_INVALID;
+    if (cudaSetDevice(m->device) != cudaSuccess) return ERASOR_E_CUDA;
+    const cudaMemcpyKind k = ptr_kind == ERASOR_PTR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (m->n && cudaMemcpyAsync(keep, m->d_keep, m->n, k, m->st) != cudaSuccess) return ERASOR_E_CUDA;
+    return cudaStreamSynchronize(m->st) == cudaSuccess ? ERASOR_OK : ERASOR_E_CUDA;
+}
+
+int erasor_attach_map(erasor_handle_t h, erasor_map_t m) {
+    if (!h) return ERASOR_E_INVALID;
+    if (m && m->device != h->device) { h->err = "map and handle live on different devices"; return ERASOR_E_INVALID; }
+    int rc;
+    if (h->pending && (rc = erasor_wait(h))) return rc;
+    h->map = m;
+    h->desc_mode = -1;
+    return ERASOR_OK;
+}
+
+int erasor_process_nodes(erasor_handle_t h, const double* poses7, const float* query_xyzi, const uint64_t* query_offsets, int n_frames,
+                         double voi_max_range, uint8_t* frame_keep, uint8_t* keep_out, int ptr_kind) {
+    return process_nodes_impl(h, poses7, query_xyzi, query_offsets, n_frames, voi_max_range, frame_keep, keep_out, ptr_kind, false);
+}
+int erasor_process_nodes_async(erasor_handle_t h, const double* poses7, const float* query_xyzi, const uint64_t* query_offsets, int n_frames,
+                               double voi_max_range, uint8_t* frame_keep, uint8_t* keep_out, int ptr_kind) {
+    return process_nodes_impl(h, poses7, query_xyzi, query_offsets, n_frames, voi_max_range, frame_keep, keep_out, ptr_kind, true);
+}
+
+int erasor_get_node_stats(erasor_handle_t h, uint32_t* n_voi_points, uint32_t* n_flagged_bins, uint32_t* n_rejected_points) {
+    if (!h) return ERASOR_E_INVALID;
+    if (h->F <= 0 || h->desc_mode != 2) { h->err = "no node batch has run"; return ERASOR_E_STATE; }
+    int rc;
+    if ((rc = erasor_wait(h))) return rc;
+    if (n_voi_points) {
+        // |map_voi_| of every node of the LAST submission = binned + complement counts of the map cloud (K1's tables)
+        const size_t row = (size_t)h->B + 1;
+        std::vector<uint32_t> c((size_t)h->F * row);
+        CK(cudaMemcpy(c.data(), h->d_cnt.p, sizeof(uint32_t) * c.size(), cudaMemcpyDeviceToHost));
+        for (int f = 0; f < h->F; ++f) {
+            uint64_t t = 0;
+            for (size_t b = 0; b < row; ++b) t += c[(size_t)f * row + b];
+            n_voi_points[h->f0 + f] = (uint32_t)t;
+        }
+    }
+    if (n_flagged_bins) CK(cudaMemcpy(n_flagged_bins, h->d_nflag.p, sizeof(uint32_t) * h->stat_F, cudaMemcpyDeviceToHost));
+    if (n_rejected_points) CK(cudaMemcpy(n_rejected_points, h->d_frame_rej.p, sizeof(uint32_t) * h->stat_F, cudaMemcpyDeviceToHost));
+    return ERASOR_OK;
+}
+
+// ---- the path's single collective ---------------------------------------------------------------------------------
+int erasor_comm_unique_id(uint8_t* id128) {
+    if (!id128) return ERASOR_E_INVALID;
+    NcclApi* api = nccl_api(g_create_error);
+    if (!api) return ERASOR_E_UNSUPPORTED;
+    static_assert(sizeof(ncclUniqueId) == ERASOR_COMM_ID_BYTES, "NCCL unique id size");
+    ncclUniqueId id;
+    const ncclResult_t r = api->GetUniqueId(&id);
+    if (r != ncclSuccess) { g_create_error = std::string("ncclGetUniqueId: ") + api->GetErrorString(r); return ERASOR_E_CUDA; }
+    std::memcpy(id128, &id, sizeof(id));
+    return ERASOR_OK;
+}
+
+int erasor_comm_init(erasor_handle_t h, const uint8_t* id128, int n_ranks, int rank) {
+    if (!h || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) { if (h) h->err = "bad communicator arguments"; return ERASOR_E_INVALID; }
+    NcclApi* api = nccl_api(h->err);
+    if (!api) return ERASOR_E_UNSUPPORTED;
+    CK(cudaSetDevice(h->device));
+    if (h->comm) { api->CommDestroy(h->comm); h->comm = nullptr; }
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    const ncclResult_t r = api->CommInitRank(&h->comm, n_ranks, id, rank);
+    if (r != ncclSuccess) { h->comm = nullptr; h->err = std::string("ncclCommInitRank: ") + api->GetErrorString(r); return ERASOR_E_CUDA; }
+    h->comm_ranks = n_ranks; h->comm_rank = rank;
+    return ERASOR_OK;
+}
+
+int erasor_comm_destroy(erasor_handle_t h) {
+    if (!h) return ERASOR_E_INVALID;
+    if (h->comm) {
+        NcclApi* api = nccl_api(h->err);
+        if (!api) return ERASOR_E_UNSUPPORTED;
+        CK(cudaSetDevice(h->device));
+        CK(cudaStreamSynchronize(h->stream));
+        api->CommDestroy(h->comm);
+        h->comm = nullptr; h->comm_ranks = 1; h->comm_rank = 0;
+    }
+    return ERASOR_OK;
+}
+
+// The local half of the exchange on its own (what runs after the all-gather): AND n_masks byte masks of n points each
+// (DEVICE, contiguous [n_masks][n]) through the bit-packed form into out (DEVICE, n bytes).  Lets a single-GPU test and
+// a caller with its own transport use the library's pack / AND kernels.
+int erasor_and_keep_masks(erasor_handle_t h, const uint8_t* masks, int n_masks, size_t n, uint8_t* out) {
+    if (!h || n_masks < 1 || (n && (!masks || !out))) { if (h) h->err = "bad argument"; return ERASOR_E_INVALID; }
+    if (n == 0) return ERASOR_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t words = (n + 31) / 32;
+    CK(h->d_gather.ensure(sizeof(uint32_t) * words * (size_t)n_masks));
+    for (int r = 0; r < n_masks; ++r) {
+        h->launches++;
+        CK(launch_pack_keep_bits(h->stream, masks + (size_t)r * n, n, h->d_gather.as<uint32_t>() + (size_t)r * words));
+    }
+    h->launches++;
+    CK(launch_and_unpack_keep(h->stream, h->d_gather.as<uint32_t>(), n_masks, n, out));
+    return ERASOR_OK;
+}
+
+int erasor_allgather_and_keep(erasor_handle_t h, uint8_t* global_keep, size_t n_global) {
+    if (!h || (n_global && !global_keep)) { if (h) h->err = "null argument"; return ERASOR_E_INVALID; }
+    if (!h->comm || h->comm_ranks <= 1 || n_global == 0) return ERASOR_OK;      // one rank: the folded mask is already the answer
+    NcclApi* api = nccl_api(h->err);
+    if (!api) return ERASOR_E_UNSUPPORTED;
+    CK(cudaSetDevice(h->device));
+    const size_t words = (n_global + 31) / 32;
+    CK(h->d_pack.ensure(sizeof(uint32_t) * words));
+    CK(h->d_gather.ensure(sizeof(uint32_t) * words * (size_t)h->comm_ranks));
+    h->launches += 2;
+    CK(launch_pack_keep_bits(h->stream, global_keep, n_global, h->d_pack.as<uint32_t>()));
+    const ncclResult_t r = api->AllGather(h->d_pack.p, h->d_gather.p, words, ncclUint32, h->comm, h->stream);
+    if (r != ncclSuccess) { h->err = std::string("ncclAllGather: ") + api->GetErrorString(r); return ERASOR_E_CUDA; }
+    CK(launch_and_unpack_keep(h->stream, h->d_gather.as<uint32_t>(), h->comm_ranks, n_global, global_keep));
     return ERASOR_OK;
 }
 
@@ -792,8 +1194,9 @@ int erasor_get_frame_stats(erasor_handle_t h, uint32_t* n_flagged_bins, uint32_t
     if (h->F <= 0) { h->err = "no batch has run"; return ERASOR_E_STATE; }
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
-    if (n_flagged_bins) CK(cudaMemcpy(n_flagged_bins, h->d_nflag.p, sizeof(uint32_t) * h->F, cudaMemcpyDeviceToHost));
-    if (n_rejected_points) CK(cudaMemcpy(n_rejected_points, h->d_frame_rej.p, sizeof(uint32_t) * h->F, cudaMemcpyDeviceToHost));
+    const int nf = std::max(h->stat_F, h->F);
+    if (n_flagged_bins) CK(cudaMemcpy(n_flagged_bins, h->d_nflag.p, sizeof(uint32_t) * nf, cudaMemcpyDeviceToHost));
+    if (n_rejected_points) CK(cudaMemcpy(n_rejected_points, h->d_frame_rej.p, sizeof(uint32_t) * nf, cudaMemcpyDeviceToHost));
     return ERASOR_OK;
 }
 

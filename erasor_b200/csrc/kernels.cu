@@ -21,6 +21,7 @@
 #include "device_types.h"
 #include "kernels.h"
 
+#include <algorithm>
 #include <mutex>
 #include <unordered_map>
 
@@ -150,12 +151,31 @@ __device__ __forceinline__ int bin_fast(float x, float y, float z, float z_lo, f
     return min(k, S - 1) * R + g;
 }
 
-template <int THREADS, int UNROLL, bool ROWS>
+// pcl::transformPointCloud, PCL 1.8 scalar path: ((m0*x + m1*y) + m2*z) + m3 in float, no contraction -- the same
+// association as updater_kernels.cu::affine and oracle transform_point_cloud (OfflineMapUpdater.cpp:436)
+__device__ __forceinline__ float4 affine12(const float* __restrict__ T, float4 p) {
+    float4 o;
+    o.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[0], p.x), __fmul_rn(T[1], p.y)), __fmul_rn(T[2], p.z)), T[3]);
+    o.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[4], p.x), __fmul_rn(T[5], p.y)), __fmul_rn(T[6], p.z)), T[7]);
+    o.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[8], p.x), __fmul_rn(T[9], p.y)), __fmul_rn(T[10], p.z)), T[11]);
+    o.w = p.w;
+    return o;
+}
+// OfflineMapUpdater::fetch_VoI's cut (OfflineMapUpdater.cpp:394-396): pow(pt.x - x, 2) + pow(pt.y - y, 2) < max_dist_square in double
+__device__ __forceinline__ bool in_voi_radius(const NodePose& P, float x, float y) {
+    const double dx = __dsub_rn((double)x, P.px), dy = __dsub_rn((double)y, P.py);
+    return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < P.limit;
+}
+
+// NODE: the map cloud is the resident global map in the origin frame; every frame's chunks scan it, keep the points
+// inside the frame's radius (fetch_VoI) and bin their origin -> body transforms.  Points outside the VoI get no bin id
+// and are not counted anywhere (they are the reference's map_outskirts_, which never reach ERASOR).
+template <int THREADS, int UNROLL, bool ROWS, bool NODE>
 __global__ void __launch_bounds__(THREADS)
 k1_rpod_bin(BinTablesView T, const float4* __restrict__ map_pts, const float4* __restrict__ qry_pts,
             const ChunkDesc* __restrict__ chunks, uint16_t* __restrict__ bin_map, uint16_t* __restrict__ bin_qry,
             uint32_t* __restrict__ ch_cnt, uint32_t* __restrict__ zmin, uint32_t* __restrict__ zmax, uint32_t* __restrict__ cnt_tab,
-            int B, int F, unsigned long long* __restrict__ fence) {
+            int B, int F, unsigned long long* __restrict__ fence, const NodePose* __restrict__ poses) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double*   s_ring = reinterpret_cast<double*>(smem_raw);
     uint32_t* s_cnt  = reinterpret_cast<uint32_t*>(s_ring + ((T.R + 2) & ~1));
@@ -165,14 +185,17 @@ k1_rpod_bin(BinTablesView T, const float4* __restrict__ map_pts, const float4* _
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = THREADS / 32;
     const ChunkDesc cd = chunks[blockIdx.x];
+    __shared__ NodePose s_pose;
+    const bool node_map = NODE && cd.cloud == 0;          // CTA-uniform
 
     for (int i = tid; i <= T.R; i += THREADS) s_ring[i] = T.ring_thr[i];
     for (int i = tid; i <= B; i += THREADS) s_cnt[i] = 0u;
     for (int i = tid; i < B; i += THREADS) { s_mn[i] = 0xFFFFFFFFu; s_mx[i] = 0u; }
+    if (NODE && tid == 0) s_pose = poses[cd.frame];
     __syncthreads();
 
     const float4* __restrict__ src = (cd.cloud == 0 ? map_pts : qry_pts) + cd.begin;
-    uint16_t* __restrict__     dst = (cd.cloud == 0 ? bin_map : bin_qry) + cd.begin;
+    uint16_t* __restrict__     dst = (cd.cloud == 0 ? bin_map : bin_qry) + cd.bin_begin;
     BinFenceCounters fc{0u, 0u, 0u};
     const float  z_lo = T.z_lo, z_hi = T.z_hi, inv_ring = T.inv_ring, inv_ss = T.inv_ss, eps_q = T.eps_q;
     const double s_max = T.s_max;
@@ -190,16 +213,23 @@ k1_rpod_bin(BinTablesView T, const float4* __restrict__ map_pts, const float4* _
         for (int u = 0; u < UNROLL; ++u) {
             const uint32_t i = base + u * 32u + lane;
             const bool ok = full || i < cd.len;
-            int b = bin_fast(p[u].x, p[u].y, p[u].z, z_lo, z_hi, s_max, inv_ring, inv_ss, eps_q, R, S, s_ring);
+            bool inside = true;                                  // inside the frame's VoI (always, outside node mode)
+            float4 pp = p[u];
+            if (node_map) {
+                inside = in_voi_radius(s_pose, pp.x, pp.y);
+                pp = affine12(s_pose.T, pp);
+            }
+            int b = bin_fast(pp.x, pp.y, pp.z, z_lo, z_hi, s_max, inv_ring, inv_ss, eps_q, R, S, s_ring);
+            if (NODE && !inside) b = -1;
             if (__any_sync(FULL_MASK, ok && b == -3)) {
-                if (ok && b == -3) b = bin_exact(T, s_ring, p[u].x, p[u].y, p[u].z, &fc);   // exact path (rare)
+                if (ok && b == -3) b = bin_exact(T, s_ring, pp.x, pp.y, pp.z, &fc);   // exact path (rare)
             }
             int key = -2;
             if (ok) {
                 dst[i] = (b < 0) ? kNoBin16 : (uint16_t)b;
-                key    = (b < 0) ? B : b;
+                if (inside) key = (b < 0) ? B : b;
             }
-            k1_aggregate(key, float_to_ordered(p[u].z), lane, s_cnt, s_mn, s_mx, B);
+            k1_aggregate(key, float_to_ordered(pp.z), lane, s_cnt, s_mn, s_mx, B);
         }
     }
     __syncthreads();
@@ -231,19 +261,19 @@ size_t k1_smem_bytes(int R, int B) {
 
 cudaError_t launch_k1(cudaStream_t st, const BinTablesView& T, const float4* map_pts, const float4* qry_pts,
                       const ChunkDesc* chunks, int n_chunks, uint16_t* bin_map, uint16_t* bin_qry, uint32_t* ch_cnt,
-                      uint32_t* zmin, uint32_t* zmax, uint32_t* cnt_tab, int B, int F, bool rows, unsigned long long* fence) {
+                      uint32_t* zmin, uint32_t* zmax, uint32_t* cnt_tab, int B, int F, unsigned long long* fence, const NodePose* poses) {
     if (n_chunks == 0) return cudaSuccess;
     constexpr int THREADS = 256, UNROLL = 4;
     const size_t smem = k1_smem_bytes(T.R, B);
     cudaError_t e;
-    if (rows) {
-        auto kern = k1_rpod_bin<THREADS, UNROLL, true>;
+    if (poses) {
+        auto kern = k1_rpod_bin<THREADS, UNROLL, true, true>;
         if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
-        kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence);
+        kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, poses);
     } else {
-        auto kern = k1_rpod_bin<THREADS, UNROLL, false>;
+        auto kern = k1_rpod_bin<THREADS, UNROLL, true, false>;
         if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
-        kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence);
+        kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, nullptr);
     }
     return cudaGetLastError();
 }
@@ -508,170 +538,159 @@ cudaError_t launch_k3(cudaStream_t st, const SrtParams& P, int F, const uint32_t
 // ============================================================================================
 // K2
 // ============================================================================================
-// One warp per chunk.  Stable: a point's slot is  dst_start[bin] + (points of the bin in earlier chunks of the
-// frame) + (points of the bin earlier in this chunk), the last term kept as a running offset in shared memory
-// and advanced 32 points at a time with match_any ranks.
-__global__ void __launch_bounds__(32)
-k2_scatter(const ChunkDesc* __restrict__ chunks, uint32_t chunk_base, int F, const uint16_t* __restrict__ bin_ids,
-           const float4* __restrict__ pts, const uint32_t* __restrict__ ch_cnt, const uint32_t* __restrict__ dst_start /*[F][B+2] of this cloud*/,
-           float4* __restrict__ out_pts, uint32_t* __restrict__ out_src, int B) {
-    extern __shared__ uint32_t s_off[];   // B+1
-    const int lane = threadIdx.x;
-    const uint32_t row = chunk_base + blockIdx.x;
-    const ChunkDesc cd = chunks[row];
-    const uint32_t* ds   = dst_start + (size_t)cd.frame * (B + 2);
-    const uint32_t* pref = ch_cnt + (size_t)row * (B + 1);
-    for (int b = lane; b <= B; b += 32) {
-        const uint32_t d = ds[b];
-        const uint32_t v = (d == kSkip) ? kSkip : d + pref[b];
-        s_off[b] = v;
-    }
-    __syncwarp();
-    const uint32_t local0 = cd.begin - cd.frame_begin;
-    for (uint32_t i0 = 0; i0 < cd.len; i0 += 32) {
-        const uint32_t i = i0 + lane;
-        const bool valid = i < cd.len;
-        const unsigned vmask = __ballot_sync(FULL_MASK, valid);
-        if (valid) {
-            const uint16_t id  = bin_ids[cd.begin + i];
-            const int      key = (id == kNoBin16) ? B : (int)id;
-            const unsigned peers = __match_any_sync(vmask, key);
-            const uint32_t base  = s_off[key];
-            __syncwarp(vmask);
-            const int leader = __ffs(peers) - 1;
-            if (base != kSkip) {
-                const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-                if (lane == leader) s_off[key] = base + __popc(peers);
-                const float4 p = pts[cd.begin + i];
-                const size_t o = (size_t)cd.frame_begin + base + rank;
-                out_pts[o] = p;
-                out_src[o] = local0 + i;
-            }
-        }
-        __syncwarp();
-    }
-}
-
-// Multi-warp variant: the CTA's W warps split the chunk into W contiguous sub-ranges.  Pass A counts each sub-range per
-// bin into the warp's own shared-memory row (match_any dedups a 32-point step, so no atomics); a column scan turns the
-// rows into absolute destinations (dst_start + earlier chunks + earlier warps); pass B re-walks the sub-range in order.
-// W x more parallelism per chunk than the one-warp kernel; needs W*(B+1)*4 bytes of shared memory.
-template <int W>
+// Stable counting-sort scatter of the points of the "scattered" bins into bin-contiguous storage, source order kept
+// inside every bin (the per-bin pcl::PointCloud push_back of erasor.cpp:89).  Scattered bins are numbered by dense
+// SLOTS in bin order: every bin plus the complement (cloud mode: slot == bin, B + 1 slots) or the flagged bins only
+// (mask mode: K3's flag_slot, n_flagged[frame] slots -- a few per cent of the bins).
+//
+// One CTA of W warps per chunk; the warps split the chunk into W contiguous sub-ranges.  Pass A counts each sub-range
+// per slot into the warp's own shared-memory row (match_any dedups a 32-point step, so no atomics); a column scan
+// turns the rows into absolute destinations (dst_start + earlier chunks of the frame + earlier warps); pass B re-walks
+// the sub-range in order.  The rows cover a WINDOW of SW slots; a frame with more slots than fit in shared memory
+// (40 x 360 bins in cloud mode) takes several window passes over the chunk's bin ids, so there is no bin-count limit
+// and no slow fallback.  NODE: points are read from the resident map and moved origin -> body on the way (fetch_VoI's
+// transform, OfflineMapUpdater.cpp:436), the source index is the global map index.
+template <int W, bool NODE>
 __global__ void __launch_bounds__(W * 32, 4)      // 4 CTAs per SM: the chunking aims at one wave of sm_count * 4 CTAs
-k2_scatter_mw(const ChunkDesc* __restrict__ chunks, uint32_t chunk_base, const uint16_t* __restrict__ bin_ids,
-              const float4* __restrict__ pts, const uint32_t* __restrict__ ch_cnt, const uint32_t* __restrict__ dst_start,
-              float4* __restrict__ out_pts, uint32_t* __restrict__ out_src, int B) {
-    extern __shared__ uint32_t s_tab[];   // [W][B+1] per-warp counters / destinations, then [B+1] the frame's dst_start row
+k2_scatter_win(const ChunkDesc* __restrict__ chunks, uint32_t chunk_base, const uint16_t* __restrict__ bin_ids,
+               const float4* __restrict__ pts, const NodePose* __restrict__ poses, const uint32_t* __restrict__ ch_cnt,
+               const uint32_t* __restrict__ dst_start /*[F][B+2] of this cloud*/, const uint32_t* __restrict__ flag_slot /*[F][B]; null: every bin + complement*/,
+               const uint32_t* __restrict__ n_flagged /*[F]*/, float4* __restrict__ out_pts, uint32_t* __restrict__ out_src, int B, uint32_t SW) {
+    extern __shared__ uint32_t s_tab[];   // [W][ns] per-warp counters / destinations | [SW] bases | u16 slot of every bin [B+1]
+    __shared__ float s_T[12];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t row = chunk_base + blockIdx.x;
     const ChunkDesc cd = chunks[row];
     const uint32_t* ds   = dst_start + (size_t)cd.frame * (B + 2);
     const uint32_t* pref = ch_cnt + (size_t)row * (B + 1);
-    uint32_t* mine = s_tab + (size_t)warp * (B + 1);
-    uint32_t* s_ds = s_tab + (size_t)W * (B + 1);
-    for (int i = tid; i < W * (B + 1); i += W * 32) s_tab[i] = 0u;
-    for (int b = tid; b <= B; b += W * 32) s_ds[b] = ds[b];
-    __syncthreads();
+    uint32_t* s_base = s_tab + (size_t)W * SW;
+    uint16_t* s_slot = reinterpret_cast<uint16_t*>(s_base + SW);
+    const uint32_t n_slots = flag_slot ? n_flagged[cd.frame] : (uint32_t)(B + 1);
+    if (flag_slot) {
+        const uint32_t* fs = flag_slot + (size_t)cd.frame * B;
+        for (int b = tid; b <= B; b += W * 32) { const uint32_t v = (b < B) ? fs[b] : kSkip; s_slot[b] = (v == kSkip) ? (uint16_t)0xFFFFu : (uint16_t)v; }
+    } else {
+        for (int b = tid; b <= B; b += W * 32) s_slot[b] = (ds[b] == kSkip) ? (uint16_t)0xFFFFu : (uint16_t)b;   // (the query cloud's complement is not scattered)
+    }
+    if (NODE && tid < 12) s_T[tid] = poses[cd.frame].T[tid];
     const uint32_t sub = (((cd.len + W - 1) / W) + 31u) & ~31u;
     const uint32_t s0 = min(cd.len, (uint32_t)warp * sub), s1 = min(cd.len, s0 + sub);
-    const uint16_t* ids = bin_ids + cd.begin;
-    // Both passes walk the sub-range 256 points (8 steps of 32) at a time; the bin ids of the next block are loaded while
-    // the current one is processed, so that no step waits on global memory.  Only points of scattered bins (dst_start !=
-    // kSkip: every bin in cloud mode, the flagged ~10 % in mask mode) take part in the match_any ranking.
-    uint16_t cur[8], nxt[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) { const uint32_t i = s0 + (uint32_t)u * 32u + lane; cur[u] = (i < s1) ? ids[i] : kNoBin16; }
-    for (uint32_t i0 = s0; i0 < s1; i0 += 256u) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { const uint32_t i = i0 + 256u + (uint32_t)u * 32u + lane; nxt[u] = (i < s1) ? ids[i] : kNoBin16; }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const uint32_t i = i0 + (uint32_t)u * 32u + lane;
-            const int  key  = (cur[u] == kNoBin16) ? B : (int)cur[u];
-            const bool take = (i < s1) && (s_ds[key] != kSkip);
-            const unsigned tmask = __ballot_sync(FULL_MASK, take);
-            if (take) {
-                const unsigned peers = __match_any_sync(tmask, key);
-                if (lane == __ffs(peers) - 1) mine[key] += __popc(peers);
-            }
-            __syncwarp();
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
-    }
-    __syncthreads();
-    for (int b = tid; b <= B; b += W * 32) {
-        const uint32_t d = s_ds[b];
-        uint32_t run = (d == kSkip) ? 0u : d + pref[b];
-#pragma unroll
-        for (int w = 0; w < W; ++w) {
-            const uint32_t c = s_tab[(size_t)w * (B + 1) + b];
-            s_tab[(size_t)w * (B + 1) + b] = (d == kSkip) ? kSkip : run;
-            run += c;
-        }
-    }
-    __syncthreads();
+    const uint16_t* ids = bin_ids + cd.bin_begin;
     const uint32_t local0 = cd.begin - cd.frame_begin;
     const float4* src = pts + cd.begin;
+
+    for (uint32_t win0 = 0; win0 < n_slots; win0 += SW) {
+        const uint32_t ns = min(SW, n_slots - win0);          // row stride of this window
+        uint32_t* mine = s_tab + (size_t)warp * ns;
+        __syncthreads();                                      // slot table ready / previous window's rows consumed
+        for (uint32_t i = tid; i < (uint32_t)W * ns; i += W * 32) s_tab[i] = 0u;
+        __syncthreads();
+        // Both passes walk the sub-range 256 points (8 steps of 32) at a time; the bin ids of the next block are loaded while
+        // the current one is processed, so that no step waits on global memory.  Only points of the window's slots take part
+        // in the match_any ranking.
+        uint16_t cur[8], nxt[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) { const uint32_t i = s0 + (uint32_t)u * 32u + lane; cur[u] = (i < s1) ? ids[i] : kNoBin16; }
-    for (uint32_t i0 = s0; i0 < s1; i0 += 256u) {
+        for (int u = 0; u < 8; ++u) { const uint32_t i = s0 + (uint32_t)u * 32u + lane; cur[u] = (i < s1) ? ids[i] : kNoBin16; }
+        for (uint32_t i0 = s0; i0 < s1; i0 += 256u) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { const uint32_t i = i0 + 256u + (uint32_t)u * 32u + lane; nxt[u] = (i < s1) ? ids[i] : kNoBin16; }
-        uint32_t dst[8];
+            for (int u = 0; u < 8; ++u) { const uint32_t i = i0 + 256u + (uint32_t)u * 32u + lane; nxt[u] = (i < s1) ? ids[i] : kNoBin16; }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const uint32_t i = i0 + (uint32_t)u * 32u + lane;
-            const int      key  = (cur[u] == kNoBin16) ? B : (int)cur[u];
-            const uint32_t base = (i < s1) ? mine[key] : kSkip;
-            const bool     take = base != kSkip;
-            const unsigned tmask = __ballot_sync(FULL_MASK, take);      // also orders the reads of mine[] before the updates below
-            dst[u] = kSkip;
-            if (take) {
-                const unsigned peers = __match_any_sync(tmask, key);
-                if (lane == __ffs(peers) - 1) mine[key] = base + __popc(peers);
-                dst[u] = base + __popc(peers & ((1u << lane) - 1u));
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t i = i0 + (uint32_t)u * 32u + lane;
+                const int      key  = (cur[u] == kNoBin16) ? B : (int)cur[u];
+                const uint32_t sl   = (uint32_t)s_slot[key] - win0;                 // 0xFFFF (not scattered) and other windows: >= ns
+                const bool     take = (i < s1) && (sl < ns);
+                const unsigned tmask = __ballot_sync(FULL_MASK, take);
+                if (take) {
+                    const unsigned peers = __match_any_sync(tmask, sl);
+                    if (lane == __ffs(peers) - 1) mine[sl] += __popc(peers);
+                }
+                __syncwarp();
             }
-            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
         }
-        // the copies of the block, four at a time: all loads of a group in flight before its first store
+        // bases of the window's slots: dst_start + points of the bin in earlier chunks of the frame
+        for (int b = tid; b <= B; b += W * 32) {
+            const uint32_t sl = (uint32_t)s_slot[b] - win0;
+            if (sl < ns) s_base[sl] = ds[b] + pref[b];
+        }
+        __syncthreads();
+        for (uint32_t j = tid; j < ns; j += W * 32) {
+            uint32_t run = s_base[j];
 #pragma unroll
-        for (int g = 0; g < 8; g += 4) {
-            float4 pv[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (dst[g + u] != kSkip) pv[u] = src[i0 + (uint32_t)(g + u) * 32u + lane];
+            for (int w = 0; w < W; ++w) {
+                const uint32_t c = s_tab[(size_t)w * ns + j];
+                s_tab[(size_t)w * ns + j] = run;
+                run += c;
             }
+        }
+        __syncthreads();
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (dst[g + u] != kSkip) {
-                    const size_t o = (size_t)cd.frame_begin + dst[g + u];
-                    out_pts[o] = pv[u];
-                    out_src[o] = local0 + i0 + (uint32_t)(g + u) * 32u + lane;
+        for (int u = 0; u < 8; ++u) { const uint32_t i = s0 + (uint32_t)u * 32u + lane; cur[u] = (i < s1) ? ids[i] : kNoBin16; }
+        for (uint32_t i0 = s0; i0 < s1; i0 += 256u) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const uint32_t i = i0 + 256u + (uint32_t)u * 32u + lane; nxt[u] = (i < s1) ? ids[i] : kNoBin16; }
+            uint32_t dst[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t i = i0 + (uint32_t)u * 32u + lane;
+                const int      key  = (cur[u] == kNoBin16) ? B : (int)cur[u];
+                const uint32_t sl   = (uint32_t)s_slot[key] - win0;
+                const bool     take = (i < s1) && (sl < ns);
+                const uint32_t base = take ? mine[sl] : 0u;
+                const unsigned tmask = __ballot_sync(FULL_MASK, take);      // also orders the reads of mine[] before the updates below
+                dst[u] = kSkip;
+                if (take) {
+                    const unsigned peers = __match_any_sync(tmask, sl);
+                    if (lane == __ffs(peers) - 1) mine[sl] = base + __popc(peers);
+                    dst[u] = base + __popc(peers & ((1u << lane) - 1u));
+                }
+                __syncwarp();
+            }
+            // the copies of the block, four at a time: all loads of a group in flight before its first store
+#pragma unroll
+            for (int g = 0; g < 8; g += 4) {
+                float4 pv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (dst[g + u] != kSkip) pv[u] = src[i0 + (uint32_t)(g + u) * 32u + lane];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (dst[g + u] != kSkip) {
+                        const size_t o = (size_t)cd.out_base + dst[g + u];
+                        out_pts[o] = NODE ? affine12(s_T, pv[u]) : pv[u];
+                        out_src[o] = local0 + i0 + (uint32_t)(g + u) * 32u + lane;
+                    }
                 }
             }
-        }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
+            for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
+        }
     }
 }
 
-cudaError_t launch_k2(cudaStream_t st, const ChunkDesc* chunks, uint32_t chunk_base, uint32_t n_chunks, int F,
-                      const uint16_t* bin_ids, const float4* pts, const uint32_t* ch_cnt, const uint32_t* dst_start,
-                      float4* out_pts, uint32_t* out_src, int B) {
+cudaError_t launch_k2(cudaStream_t st, const ChunkDesc* chunks, uint32_t chunk_base, uint32_t n_chunks,
+                      const uint16_t* bin_ids, const float4* pts, const NodePose* poses, const uint32_t* ch_cnt, const uint32_t* dst_start,
+                      const uint32_t* flag_slot, const uint32_t* n_flagged, float4* out_pts, uint32_t* out_src, int B) {
     if (n_chunks == 0) return cudaSuccess;
     constexpr int W = 8;
-    const size_t smem_mw = sizeof(uint32_t) * (size_t)(W + 1) * (B + 1);
+    const size_t fixed  = ((sizeof(uint16_t) * ((size_t)B + 2)) + 15) & ~(size_t)15;
+    const size_t budget = 200 * 1024;
+    const uint32_t n_slots_max = flag_slot ? (uint32_t)B : (uint32_t)B + 1u;
+    const uint32_t SW = (uint32_t)std::min<size_t>(n_slots_max, (budget - fixed) / (sizeof(uint32_t) * (W + 1)));
+    const size_t smem = sizeof(uint32_t) * (size_t)(W + 1) * SW + fixed;
     cudaError_t e;
-    if (smem_mw <= 200 * 1024) {
-        auto kern = k2_scatter_mw<W>;
-        if ((e = ensure_dyn_smem(kern, smem_mw)) != cudaSuccess) return e;
-        kern<<<n_chunks, W * 32, smem_mw, st>>>(chunks, chunk_base, bin_ids, pts, ch_cnt, dst_start, out_pts, out_src, B);
-        return cudaGetLastError();
+    if (poses) {
+        auto kern = k2_scatter_win<W, true>;
+        if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
+        kern<<<n_chunks, W * 32, smem, st>>>(chunks, chunk_base, bin_ids, pts, poses, ch_cnt, dst_start, flag_slot, n_flagged, out_pts, out_src, B, SW);
+    } else {
+        auto kern = k2_scatter_win<W, false>;
+        if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
+        kern<<<n_chunks, W * 32, smem, st>>>(chunks, chunk_base, bin_ids, pts, nullptr, ch_cnt, dst_start, flag_slot, n_flagged, out_pts, out_src, B, SW);
     }
-    const size_t smem = sizeof(uint32_t) * ((size_t)B + 1);
-    if ((e = ensure_dyn_smem(k2_scatter, smem)) != cudaSuccess) return e;
-    k2_scatter<<<n_chunks, 32, smem, st>>>(chunks, chunk_base, F, bin_ids, pts, ch_cnt, dst_start, out_pts, out_src, B);
     return cudaGetLastError();
 }
 
@@ -1202,7 +1221,7 @@ __device__ __forceinline__ void k4_process_bin(const GpfParams& P, FlagRec& rc, 
                                                const float4* __restrict__ in_pts, const uint32_t* __restrict__ frame_off,
                                                float4* __restrict__ part_pts, uint8_t* __restrict__ keep_mask,
                                                uint8_t* __restrict__ ground_mask, uint32_t* __restrict__ frame_rejected,
-                                               unsigned long long* __restrict__ fence) {
+                                               unsigned long long* __restrict__ fence, const K4Fold& fold) {
     const int tid = group_tid<G>(), lane = tid & 31, warp = tid >> 5;
     const uint32_t n = rc.n_points, src_begin = rc.src_begin;
     const uint32_t fbase = frame_off[rc.frame];
@@ -1432,7 +1451,7 @@ __device__ __forceinline__ void k4_process_bin(const GpfParams& P, FlagRec& rc, 
     }
 
     // ---- outputs ----
-    if (keep_mask || ground_mask) {
+    if (keep_mask || ground_mask || fold.keep) {
         for (uint32_t i0 = tid; i0 < n; i0 += 4u * G) {
             uint32_t s[4];
 #pragma unroll
@@ -1446,6 +1465,12 @@ __device__ __forceinline__ void k4_process_bin(const GpfParams& P, FlagRec& rc, 
                 if (i < n) {
                     if (keep_mask && !FLG[i]) keep_mask[fbase + s[u]] = 0;      // not in the selected bin any more (gf_iter == 0: dropped silently)
                     if (ground_mask && FLG[i]) ground_mask[fbase + s[u]] = 1;
+                    if (fold.keep && !FLG[i]) {
+                        // the multi-GPU fold, in the epilogue: a global map point survives unless some frame rejected it.
+                        // Only zeros are ever written, so concurrent bins / frames / handles need no atomics.
+                        const uint32_t g = fold.index ? fold.index[fbase + s[u]] : s[u];
+                        if (g < fold.n) fold.keep[g] = 0;
+                    }
                 }
             }
         }
@@ -1478,7 +1503,7 @@ k4_rgpf(GpfParams P, FlagRec* __restrict__ recs, uint32_t* __restrict__ queue, c
         float4* __restrict__ part_pts /*nullable*/, uint8_t* __restrict__ keep_mask /*nullable*/,
         uint8_t* __restrict__ ground_mask /*nullable*/, uint32_t* __restrict__ frame_rejected /*[F] nullable*/,
         unsigned char* __restrict__ gscratch, uint32_t smem_cap_points, uint32_t slice_bytes,
-        unsigned long long* __restrict__ fence) {
+        unsigned long long* __restrict__ fence, K4Fold fold) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NG = THREADS / G;
     constexpr int HT = (G == 32) ? 32 : 128;
@@ -1517,13 +1542,13 @@ k4_rgpf(GpfParams P, FlagRec* __restrict__ recs, uint32_t* __restrict__ queue, c
         if constexpr (G <= 256) {
             // classes A and B: the launch sizes the slices for the class maximum (kClassAMax / kClassBMax), so the bin always fits
             k4_process_bin<G, true>(P, rc, smem_raw + (size_t)grp * slice_bytes, s_prd[grp], s_cnt[grp], sh[grp], sorted_pts, sorted_src, in_pts,
-                                    frame_off, part_pts, keep_mask, ground_mask, frame_rejected, fence);
+                                    frame_off, part_pts, keep_mask, ground_mask, frame_rejected, fence, fold);
         } else if (n <= smem_cap_points) {
             k4_process_bin<G, true>(P, rc, smem_raw + (size_t)grp * slice_bytes, s_prd[grp], s_cnt[grp], sh[grp], sorted_pts, sorted_src, in_pts,
-                                    frame_off, part_pts, keep_mask, ground_mask, frame_rejected, fence);
+                                    frame_off, part_pts, keep_mask, ground_mask, frame_rejected, fence, fold);
         } else {
             k4_process_bin<G, false>(P, rc, gscratch + (size_t)rc.src_begin * 24u, s_prd[grp], s_cnt[grp], sh[grp], sorted_pts, sorted_src, in_pts,
-                                     frame_off, part_pts, keep_mask, ground_mask, frame_rejected, fence);
+                                     frame_off, part_pts, keep_mask, ground_mask, frame_rejected, fence, fold);
         }
     }
 }
@@ -1533,7 +1558,7 @@ static cudaError_t launch_k4_class(cudaStream_t st, const GpfParams& P, FlagRec*
                                    uint32_t rec_capacity, int bk0, int bk1, int cls, uint32_t smem_bytes, const float4* sorted_pts,
                                    uint32_t* sorted_src, const float4* in_pts, const uint32_t* frame_off, float4* part_pts,
                                    uint8_t* keep_mask, uint8_t* ground_mask, uint32_t* frame_rejected, unsigned char* gscratch, int grid,
-                                   unsigned long long* fence) {
+                                   unsigned long long* fence, const K4Fold& fold) {
     // per bin: 12 n (xyz) + 4 n (order) + n (flags) = 17 n for warp groups, + 4 n (second half of the order / exchange area) = 21 n
     constexpr int NG = THREADS / G;
     constexpr uint32_t per_pt = (G == 32) ? 17u : 21u;
@@ -1544,7 +1569,7 @@ static cudaError_t launch_k4_class(cudaStream_t st, const GpfParams& P, FlagRec*
     cudaError_t e = ensure_dyn_smem(kern, smem_bytes);
     if (e != cudaSuccess) return e;
     kern<<<grid, THREADS, smem_bytes, st>>>(P, recs, queue, bucket_list, rec_capacity, bk0, bk1, cls, sorted_pts, sorted_src, in_pts, frame_off,
-                                            part_pts, keep_mask, ground_mask, frame_rejected, gscratch, cap, slice, fence);
+                                            part_pts, keep_mask, ground_mask, frame_rejected, gscratch, cap, slice, fence, fold);
     return cudaGetLastError();
 }
 
@@ -1553,7 +1578,7 @@ int k4_num_launches() { return 3; }
 cudaError_t launch_k4(cudaStream_t st, cudaStream_t st_b, cudaStream_t st_c, const GpfParams& P, FlagRec* recs, uint32_t* queue,
                       const uint32_t* bucket_list, uint32_t rec_capacity, const float4* sorted_pts, uint32_t* sorted_src, const float4* in_pts,
                       const uint32_t* frame_off, float4* part_pts, uint8_t* keep_mask, uint8_t* ground_mask, uint32_t* frame_rejected,
-                      unsigned char* gscratch, int sm_count, unsigned long long* fence) {
+                      unsigned char* gscratch, int sm_count, unsigned long long* fence, const K4Fold& fold) {
     // The three size classes touch disjoint bins, so they run concurrently on three streams (the caller forks / joins).
     // Shared memory is sized so that one class-A CTA (8 bins) and two class-B CTAs are resident per SM at the same time:
     //   A  8 x 8.75 KB slices + 18.7 KB products  ~ 90 KB      B  52.6 KB + 9.3 KB products ~ 62 KB each   (A + 2B ~ 214 KB of 227 KB)
@@ -1563,15 +1588,15 @@ cudaError_t launch_k4(cudaStream_t st, cudaStream_t st_b, cudaStream_t st_c, con
     cudaError_t e;
     // class C: n > 2560, one 1024-thread CTA with most of an SM's shared memory; beyond ~8.7 k points global scratch
     e = launch_k4_class<1024, 1024>(st_c, P, recs, queue, bucket_list, rec_capacity, kBucketC0, kBucketB0, 2, 180 * 1024, sorted_pts, sorted_src,
-                                    in_pts, frame_off, part_pts, keep_mask, ground_mask, frame_rejected, gscratch, sm_count, fence);
+                                    in_pts, frame_off, part_pts, keep_mask, ground_mask, frame_rejected, gscratch, sm_count, fence, fold);
     if (e != cudaSuccess) return e;
     // class B: 512 < n <= 2560, one 256-thread CTA per bin
     e = launch_k4_class<256, 256>(st_b, P, recs, queue, bucket_list, rec_capacity, kBucketB0, kBucketA0, 1, 21 * kClassBMax + 64, sorted_pts,
-                                  sorted_src, in_pts, frame_off, part_pts, keep_mask, ground_mask, frame_rejected, gscratch, sm_count * 2, fence);
+                                  sorted_src, in_pts, frame_off, part_pts, keep_mask, ground_mask, frame_rejected, gscratch, sm_count * 2, fence, fold);
     if (e != cudaSuccess) return e;
     // class A: n <= 512, one warp per bin, 8 warps per CTA
     return launch_k4_class<256, 32>(st, P, recs, queue, bucket_list, rec_capacity, kBucketA0, kNumBuckets, 0, 8 * (17 * kClassAMax + 48), sorted_pts,
-                                    sorted_src, in_pts, frame_off, part_pts, keep_mask, ground_mask, frame_rejected, gscratch, sm_count, fence);
+                                    sorted_src, in_pts, frame_off, part_pts, keep_mask, ground_mask, frame_rejected, gscratch, sm_count, fence, fold);
 }
 
 // ============================================================================================
@@ -1858,15 +1883,69 @@ cudaError_t launch_init_tables(cudaStream_t st, uint32_t* zmin, uint32_t* zmax, 
 }
 
 // fold per-frame keep masks onto the global map: a map point survives unless some frame rejected it.
-// Only zeros are written, so concurrent writers need no atomics.
-__global__ void k_fold_keep(const uint8_t* __restrict__ keep, const uint32_t* __restrict__ voi_index, size_t n, uint8_t* __restrict__ global_keep) {
+// Only zeros are written, so concurrent writers need no atomics; the mask ACCUMULATES over calls (reset it with
+// launch_fill_u8 / erasor_reset_keep_mask at the start of a job).  Indices beyond the mask are dropped.
+__global__ void k_fold_keep(const uint8_t* __restrict__ keep, const uint32_t* __restrict__ voi_index, size_t n, uint8_t* __restrict__ global_keep, uint32_t n_global) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && keep[i] == 0) global_keep[voi_index[i]] = 0;
+    if (i < n && keep[i] == 0) {
+        const uint32_t g = voi_index[i];
+        if (g < n_global) global_keep[g] = 0;
+    }
 }
 cudaError_t launch_fold_keep(cudaStream_t st, const uint8_t* keep, const uint32_t* voi_index, size_t n, uint8_t* global_keep, size_t n_global) {
-    cudaError_t e = cudaMemsetAsync(global_keep, 1, n_global, st);
-    if (e != cudaSuccess || n == 0) return e;
-    k_fold_keep<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keep, voi_index, n, global_keep);
+    if (n == 0) return cudaSuccess;
+    k_fold_keep<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keep, voi_index, n, global_keep, (uint32_t)n_global);
+    return cudaGetLastError();
+}
+
+// ---- the exchange step of the frame-sharded job: bit-packed masks (8x fewer bytes over NVLink), AND over the ranks -----
+// keep[0..n) bytes (0 / non-0) -> bits, one 32-bit word per warp step (ballot); the tail word is padded with ones.
+__global__ void __launch_bounds__(256) k_pack_keep_bits(const uint8_t* __restrict__ keep, size_t n, uint32_t* __restrict__ words, size_t n_words) {
+    const size_t w0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const size_t stride = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t w = w0; w < n_words; w += stride) {
+        const size_t i = w * 32 + lane;
+        const bool k = (i < n) ? (keep[i] != 0) : true;
+        const unsigned bal = __ballot_sync(FULL_MASK, k);
+        if (lane == 0) words[w] = bal;
+    }
+}
+// gathered[r][w], r < n_ranks: AND over the ranks, unpacked back into one byte per map point
+__global__ void __launch_bounds__(256) k_and_unpack_keep(const uint32_t* __restrict__ gathered, int n_ranks, size_t n_words, size_t n, uint8_t* __restrict__ keep) {
+    const size_t w0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const size_t stride = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t w = w0; w < n_words; w += stride) {
+        uint32_t v = 0xFFFFFFFFu;
+        for (int r = lane; r < n_ranks; r += 32) v &= gathered[(size_t)r * n_words + w];
+        v = __reduce_and_sync(FULL_MASK, v);
+        const size_t i = w * 32 + lane;
+        if (i < n) keep[i] = (uint8_t)((v >> lane) & 1u);
+    }
+}
+cudaError_t launch_pack_keep_bits(cudaStream_t st, const uint8_t* keep, size_t n, uint32_t* words) {
+    const size_t n_words = (n + 31) / 32;
+    if (n_words == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)std::min<size_t>((n_words + 7) / 8, 148 * 8);
+    k_pack_keep_bits<<<blocks, 256, 0, st>>>(keep, n, words, n_words);
+    return cudaGetLastError();
+}
+cudaError_t launch_and_unpack_keep(cudaStream_t st, const uint32_t* gathered, int n_ranks, size_t n, uint8_t* keep) {
+    const size_t n_words = (n + 31) / 32;
+    if (n_words == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)std::min<size_t>((n_words + 7) / 8, 148 * 8);
+    k_and_unpack_keep<<<blocks, 256, 0, st>>>(gathered, n_ranks, n_words, n, keep);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) k_fill_u8(uint8_t* __restrict__ p, size_t n, uint8_t v) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+cudaError_t launch_fill_u8(cudaStream_t st, uint8_t* p, size_t n, uint8_t v) {
+    if (n == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 8);
+    k_fill_u8<<<blocks, 256, 0, st>>>(p, n, v);
     return cudaGetLastError();
 }
 

@@ -22,18 +22,20 @@ size_t k3_smem_bytes(int B);
 cudaError_t launch_init_tables(cudaStream_t st, uint32_t* zmin, uint32_t* zmax, size_t n, uint32_t* cnt, size_t n_cnt, uint32_t* n_recs,
                                uint32_t* frame_rejected, int F, uint32_t* queue);
 
+// poses != null: node mode (the map cloud is the resident global map; fetch_VoI's cut + transform fused into the binning)
 cudaError_t launch_k1(cudaStream_t st, const BinTablesView& T, const float4* map_pts, const float4* qry_pts,
                       const ChunkDesc* chunks, int n_chunks, uint16_t* bin_map, uint16_t* bin_qry, uint32_t* ch_cnt,
-                      uint32_t* zmin, uint32_t* zmax, uint32_t* cnt_tab, int B, int F, bool rows, unsigned long long* fence);
+                      uint32_t* zmin, uint32_t* zmax, uint32_t* cnt_tab, int B, int F, unsigned long long* fence, const NodePose* poses);
 
 cudaError_t launch_k3(cudaStream_t st, const SrtParams& P, int F, const uint32_t* chunk_range, uint32_t* ch_cnt,
                       const uint32_t* zmin, const uint32_t* zmax, const uint32_t* frame_off, const uint32_t* cnt, uint32_t* dst_start,
                       uint8_t* status, uint8_t* action, uint32_t* flag_slot, uint32_t* n_flagged, uint32_t* frame_rec_base,
                       FlagRec* recs, uint32_t* n_recs, uint32_t rec_capacity, uint32_t* queue, uint32_t* bucket_list);
 
-cudaError_t launch_k2(cudaStream_t st, const ChunkDesc* chunks, uint32_t chunk_base, uint32_t n_chunks, int F,
-                      const uint16_t* bin_ids, const float4* pts, const uint32_t* ch_cnt, const uint32_t* dst_start,
-                      float4* out_pts, uint32_t* out_src, int B);
+// flag_slot == null: every bin of dst_start's cloud that has an offset is scattered (cloud mode); otherwise the flagged bins only
+cudaError_t launch_k2(cudaStream_t st, const ChunkDesc* chunks, uint32_t chunk_base, uint32_t n_chunks,
+                      const uint16_t* bin_ids, const float4* pts, const NodePose* poses, const uint32_t* ch_cnt, const uint32_t* dst_start,
+                      const uint32_t* flag_slot, const uint32_t* n_flagged, float4* out_pts, uint32_t* out_src, int B);
 
 int k4_num_launches();
 // sorted_pts / sorted_src: K2's output (bins contiguous in source order + source index of every slot); in_pts is unused
@@ -42,7 +44,7 @@ int k4_num_launches();
 cudaError_t launch_k4(cudaStream_t st, cudaStream_t st_b, cudaStream_t st_c, const GpfParams& P, FlagRec* recs, uint32_t* queue,
                       const uint32_t* bucket_list, uint32_t rec_capacity, const float4* sorted_pts, uint32_t* sorted_src, const float4* in_pts, const uint32_t* frame_off,
                       float4* part_pts, uint8_t* keep_mask, uint8_t* ground_mask, uint32_t* frame_rejected, unsigned char* gscratch,
-                      int sm_count, unsigned long long* fence);
+                      int sm_count, unsigned long long* fence, const K4Fold& fold);
 
 cudaError_t launch_k4b(cudaStream_t st, float leaf, int B, const FlagRec* recs, const uint32_t* n_recs, uint32_t rec_capacity,
                        const uint32_t* cnt, const uint32_t* dst_start, const float4* qry_sorted, const float4* part_pts,
@@ -55,5 +57,9 @@ cudaError_t launch_k5(cudaStream_t st, int B, int version, int skip_voxelize, co
                       CopyJob* jobs, uint32_t* out_sizes, uint32_t* tmp, int copy_grid);
 
 cudaError_t launch_fold_keep(cudaStream_t st, const uint8_t* keep, const uint32_t* voi_index, size_t n, uint8_t* global_keep, size_t n_global);
+cudaError_t launch_fill_u8(cudaStream_t st, uint8_t* p, size_t n, uint8_t v);
+// exchange step of the frame-sharded job: pack the keep bytes into bits, AND the all-gathered words of every rank, unpack
+cudaError_t launch_pack_keep_bits(cudaStream_t st, const uint8_t* keep, size_t n, uint32_t* words);
+cudaError_t launch_and_unpack_keep(cudaStream_t st, const uint32_t* gathered, int n_ranks, size_t n, uint8_t* keep);
 
 }  // namespace erasor

@@ -12,7 +12,8 @@
  *     four used floats; on the device this is one float4 per point, 16-byte aligned);
  *   - every function returns 0 (ERASOR_OK) or a negative error code and never throws;
  *     erasor_last_error() gives the text;
- *   - one handle <-> one CUDA device + one stream; a handle is not thread-safe;
+ *   - one handle <-> one CUDA device + one stream; a handle is not thread-safe, but distinct handles may be driven from
+ *     distinct host threads, and several handles on one device overlap on the GPU (the *_async entry points);
  *   - device buffers are owned by the handle, caller buffers by the caller;
  *     `ptr_kind` says whether caller buffers are host (pageable or pinned) or device memory;
  *   - bins are indexed  bin = sector * num_rings + ring  (theta outer, r inner: the order
@@ -29,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ERASOR_B200_ABI_VERSION 1
+#define ERASOR_B200_ABI_VERSION 2
 
 typedef struct erasor_ctx* erasor_handle_t;
 
@@ -131,22 +132,85 @@ int erasor_get_fence_counts(erasor_handle_t h, uint64_t* negzero_points, uint64_
 /* Runs the whole path on n_frames independent (map_voi, query_voi) pairs and writes, for every map point of
  * every frame, keep = 0 where the frame rejects it.  Frame f's map points are
  * map_xyzi[map_offsets[f] .. map_offsets[f+1]) (offsets in points, n_frames+1 entries, host memory);
- * likewise the queries.  keep_mask has map_offsets[n_frames] bytes.  Clouds / mask: host or device (ptr_kind). */
+ * likewise the queries.  keep_mask has map_offsets[n_frames] bytes.  Clouds / mask: host or device (ptr_kind).
+ * A batch too large for one submission (more than 2^32 points, or more flagged-bin records than the work queue holds)
+ * is split into consecutive sub-batches internally. */
 int erasor_process_frames(erasor_handle_t h, const float* map_xyzi, const uint64_t* map_offsets,
                           const float* query_xyzi, const uint64_t* query_offsets, int n_frames,
                           uint8_t* keep_mask, int ptr_kind);
-/* Multi-GPU exchange helper: fold the per-frame keep masks onto the global map (a point survives unless some frame
- * rejected it): global_keep[] = 1, then global_keep[voi_index[i]] = 0 where keep_mask[i] == 0.  DEVICE pointers; asynchronous
- * on the handle's stream (erasor_stream).  The all-gather of the folded masks is the path's single collective. */
+/* Same, returning as soon as the work is enqueued on the handle's stream; erasor_wait(h) completes it (and reports its
+ * error, if any).  Host buffers must stay valid and -- to actually be asynchronous -- be pinned.  Two or three handles
+ * fed round-robin overlap consecutive batches on the GPU (one batch's R-GPF runs under the next one's binning). */
+int erasor_process_frames_async(erasor_handle_t h, const float* map_xyzi, const uint64_t* map_offsets,
+                                const float* query_xyzi, const uint64_t* query_offsets, int n_frames,
+                                uint8_t* keep_mask, int ptr_kind);
+int erasor_wait(erasor_handle_t h);
+/* Multi-GPU exchange helper: fold per-frame keep masks onto the global map (a point survives unless some frame
+ * rejected it): global_keep[voi_index[i]] = 0 where keep_mask[i] == 0.  The mask ACCUMULATES over calls -- start a job
+ * with erasor_reset_keep_mask.  Indices >= n_global are ignored.  DEVICE pointers; asynchronous on the handle's stream. */
 int erasor_fold_keep_masks(erasor_handle_t h, const uint8_t* keep_mask, const uint32_t* voi_index, size_t n, uint8_t* global_keep, size_t n_global);
-/* erasor_process_frames followed by erasor_fold_keep_masks of the fresh masks in the same submission (same stream, same CUDA
- * graph, before the host synchronises): what a rank of the frame-sharded job runs per batch.  voi_index / global_keep: DEVICE. */
+int erasor_reset_keep_mask(erasor_handle_t h, uint8_t* global_keep, size_t n_global);   /* global_keep[] = 1; DEVICE pointer, asynchronous */
+/* erasor_process_frames with the fold done in R-GPF's epilogue (no extra pass over the masks): what a rank of the
+ * frame-sharded job runs per batch.  voi_index (global index of every VoI point, map_offsets[n_frames] entries) and
+ * global_keep: DEVICE.  global_keep accumulates (see erasor_reset_keep_mask). */
 int erasor_process_frames_fold(erasor_handle_t h, const float* map_xyzi, const uint64_t* map_offsets,
                                const float* query_xyzi, const uint64_t* query_offsets, int n_frames,
                                uint8_t* keep_mask, int ptr_kind,
                                const uint32_t* voi_index, uint8_t* global_keep, size_t n_global);
-/* per-frame counters of the last erasor_process_frames: flagged bins and rejected points (host arrays of n_frames) */
+int erasor_process_frames_fold_async(erasor_handle_t h, const float* map_xyzi, const uint64_t* map_offsets,
+                                     const float* query_xyzi, const uint64_t* query_offsets, int n_frames,
+                                     uint8_t* keep_mask, int ptr_kind,
+                                     const uint32_t* voi_index, uint8_t* global_keep, size_t n_global);
+/* per-frame counters of the last erasor_process_frames / erasor_process_nodes: flagged bins and rejected points (host arrays of n_frames) */
 int erasor_get_frame_stats(erasor_handle_t h, uint32_t* n_flagged_bins, uint32_t* n_rejected_points);
+
+/* ---- map-resident frame-independent mode: the global map is uploaded once, per node only pose + query cross PCIe ---- */
+/* The initial map of OfflineMapUpdater::load_global_map (OfflineMapUpdater.cpp:107-167), origin frame, resident in HBM,
+ * together with its global keep mask (one byte per map point, 1 = static so far).  One map may be attached to any
+ * number of handles on the same device. */
+typedef struct erasor_map_ctx* erasor_map_t;
+int    erasor_map_create(const float* map_xyzi, size_t n_map, int ptr_kind, int device, erasor_map_t* out);
+void   erasor_map_destroy(erasor_map_t m);
+size_t erasor_map_size(erasor_map_t m);
+int    erasor_map_reset_keep(erasor_map_t m);                              /* keep[] = 1 (synchronous) */
+int    erasor_map_get_keep(erasor_map_t m, uint8_t* keep, int ptr_kind);   /* synchronous copy; wait for the handles first */
+uint8_t*     erasor_map_keep_device(erasor_map_t m);                       /* the mask in HBM (n_map bytes) */
+const float* erasor_map_points_device(erasor_map_t m);
+int    erasor_attach_map(erasor_handle_t h, erasor_map_t m);
+/* n_frames nodes against the attached map, every one tested against the same (initial) map.  For node f:
+ *   poses7[7 f .. 7 f + 7) = msg->odom, body -> origin, x y z qx qy qz qw (HOST memory; OfflineMapUpdater.cpp:219);
+ *   query cloud = query_xyzi[query_offsets[f] .. query_offsets[f+1]): the scan as callback_node hands it to
+ *   ERASOR::set_inputs, i.e. voxelised and in the body frame (OfflineMapUpdater.cpp:237-241).
+ * On the device, per node: fetch_VoI (OfflineMapUpdater.cpp:381-438: radius cut at voi_max_range around the body position
+ * in double, origin -> body transform; <= 0 selects /erasor/max_range) fused into the polar binning, then SRT and R-GPF
+ * as in erasor_process_frames.  Results:
+ *   - the map's keep mask &= this batch's verdicts (always; written by R-GPF's epilogue);
+ *   - frame_keep (nullable): n_frames x n_map bytes, frame f's keep mask over the GLOBAL map indices
+ *     (1 also for points outside the node's VoI);
+ *   - keep_out (nullable): copy of the map's keep mask after this batch (n_map bytes).
+ * query_xyzi / frame_keep / keep_out: host or device (ptr_kind); host buffers should be pinned. */
+int erasor_process_nodes(erasor_handle_t h, const double* poses7, const float* query_xyzi, const uint64_t* query_offsets, int n_frames,
+                         double voi_max_range, uint8_t* frame_keep, uint8_t* keep_out, int ptr_kind);
+int erasor_process_nodes_async(erasor_handle_t h, const double* poses7, const float* query_xyzi, const uint64_t* query_offsets, int n_frames,
+                               double voi_max_range, uint8_t* frame_keep, uint8_t* keep_out, int ptr_kind);
+/* per-node counters of the last erasor_process_nodes: points inside the VoI (|map_voi_|), flagged bins, rejected points */
+int erasor_get_node_stats(erasor_handle_t h, uint32_t* n_voi_points, uint32_t* n_flagged_bins, uint32_t* n_rejected_points);
+
+/* ---- the path's single collective, behind the C ABI (north_star: one NCCL all-gather of the static masks) ------------ */
+/* A communicator owned by the handle (NCCL is loaded with dlopen("libnccl.so.2") on first use).  Rank 0 calls
+ * erasor_comm_unique_id and ships the 128 bytes to the other ranks by whatever means the host program has
+ * (MPI, torch.distributed, a file); every rank then calls erasor_comm_init (collective). */
+#define ERASOR_COMM_ID_BYTES 128
+int erasor_comm_unique_id(uint8_t* id128);
+int erasor_comm_init(erasor_handle_t h, const uint8_t* id128, int n_ranks, int rank);
+int erasor_comm_destroy(erasor_handle_t h);
+/* global_keep (DEVICE, n_global bytes, this rank's folded mask) <- AND over all ranks: the bytes are packed to bits
+ * (8x less traffic), all-gathered with ONE ncclAllGather over NVLink and AND-ed + unpacked by a library kernel.
+ * Asynchronous on the handle's stream.  Without a communicator (single GPU) it is a no-op. */
+int erasor_allgather_and_keep(erasor_handle_t h, uint8_t* global_keep, size_t n_global);
+/* The local half of that exchange on its own: out[i] = AND over r of masks[r][i] (DEVICE, contiguous [n_masks][n] bytes),
+ * through the same bit-pack / AND / unpack kernels.  For callers with their own transport, and for single-GPU tests. */
+int erasor_and_keep_masks(erasor_handle_t h, const uint8_t* masks, int n_masks, size_t n, uint8_t* out);
 
 /* ---- instrumentation ---------------------------------------------------------------------- */
 /* per flagged bin of the last run: point count and SM cycles per R-GPF phase (load + index sort, z sort, seeds,

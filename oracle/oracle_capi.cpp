@@ -6,6 +6,7 @@
 #include "erasor_oracle.hpp"
 
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <memory>
 
@@ -145,6 +146,27 @@ void oracle_transform(const float* xyzi, size_t n, const float* T16, float* out_
     from_cloud(d, out_xyzi, nullptr, n);
 }
 void oracle_pose_to_matrix(const double* pose7, float* T16) { geo_pose_to_matrix(pose7, T16); }
+// OfflineMapUpdater::fetch_VoI as a free function (OfflineMapUpdater.cpp:381-438 with the pose handling of :219,246-247):
+// 2-D radius cut around the body position in double on float differences, then origin -> body with the float inverse.
+// Writes the VoI (body frame) and the map index of every VoI point; returns the VoI size (outputs truncated at cap).
+size_t oracle_fetch_voi(const float* map_xyzi, size_t n_map, const double* pose7, double max_range, float* voi_xyzi, uint32_t* voi_index, size_t cap) {
+    float T[16], Tinv[16];
+    geo_pose_to_matrix(pose7, T);
+    const double x_criterion = T[3], y_criterion = T[7];
+    const double max_dist_square = std::pow(max_range + 0.0, 2);
+    Cloud sel;
+    for (size_t i = 0; i < n_map; ++i) {
+        PointXYZI p{};
+        p.x = map_xyzi[4 * i + 0]; p.y = map_xyzi[4 * i + 1]; p.z = map_xyzi[4 * i + 2]; p.intensity = map_xyzi[4 * i + 3];
+        p.src = static_cast<uint32_t>(i);
+        const double dist_square = std::pow(p.x - x_criterion, 2) + std::pow(p.y - y_criterion, 2);
+        if (dist_square < max_dist_square) sel.push_back(p);
+    }
+    invert_4x4(T, Tinv);
+    Cloud out;
+    transform_point_cloud(sel, out, Tinv);
+    return from_cloud(out, voi_xyzi, voi_index, cap);
+}
 void oracle_invert4(const float* T16, float* out16) { invert_4x4(T16, out16); }
 // extract_ground on a free-standing cloud (R-GPF unit test): returns ground flags per src point
 void oracle_extract_ground(void* h, const float* xyzi, size_t n, uint8_t* is_ground) {

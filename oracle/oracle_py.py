@@ -92,6 +92,8 @@ def _bind(L):
     L.oracle_transform.argtypes = [fp, c_size_t, fp, fp]
     L.oracle_pose_to_matrix.argtypes = [POINTER(c_double), fp]
     L.oracle_invert4.argtypes = [fp, fp]
+    L.oracle_fetch_voi.restype = c_size_t
+    L.oracle_fetch_voi.argtypes = [fp, c_size_t, POINTER(c_double), c_double, fp, POINTER(c_uint32), c_size_t]
     L.oracle_extract_ground.argtypes = [c_void_p, fp, c_size_t, POINTER(c_uint8)]
     L.oracle_updater_create.restype = c_void_p
     L.oracle_updater_create.argtypes = [POINTER(OracleUpdaterParamsC), POINTER(OracleParamsC), fp, c_size_t]
@@ -254,6 +256,17 @@ def invert4(T) -> np.ndarray:
     out = np.zeros(16, dtype=np.float32)
     lib().oracle_invert4(_fptr(T), _fptr(out))
     return out.reshape(4, 4)
+
+
+def fetch_voi(map_cloud, pose7, max_range: float):
+    """OfflineMapUpdater::fetch_VoI restated as a free function: (voi in the body frame, index of every VoI point in the map)."""
+    m = _as_cloud(map_cloud)
+    p = np.ascontiguousarray(pose7, dtype=np.float64)
+    voi = np.empty((max(len(m), 1), 4), dtype=np.float32)
+    idx = np.empty(max(len(m), 1), dtype=np.uint32)
+    n = lib().oracle_fetch_voi(_fptr(m), len(m), p.ctypes.data_as(POINTER(c_double)), float(max_range), _fptr(voi),
+                               idx.ctypes.data_as(POINTER(c_uint32)), len(m))
+    return voi[:n].copy(), idx[:n].copy()
 
 
 class OracleUpdater:

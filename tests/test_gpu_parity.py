@@ -188,6 +188,7 @@ def test_fold_keep_masks(capi):
     d_keep = keep.cuda()
     d_out = torch.zeros(n_global, dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
+    h.reset_keep_mask(d_out.data_ptr(), n_global)          # the fold accumulates: a job starts with an explicit reset
     h.fold_keep_masks(d_keep.data_ptr(), d_idx.data_ptr(), n, d_out.data_ptr(), n_global)
     h.synchronize()
     assert np.array_equal(d_out.cpu().numpy(), expect)
@@ -369,10 +370,11 @@ def test_process_frames_fold_matches_separate_calls(capi, small_workload):
     keep_a = torch.empty(len(M), dtype=torch.uint8, device="cuda"); keep_b = torch.empty_like(keep_a)
     g_a = torch.zeros(n_global, dtype=torch.uint8, device="cuda"); g_b = torch.zeros_like(g_a)
     h.process_frames_ptr(dM.data_ptr(), mo, dQ.data_ptr(), qo, keep_a.data_ptr(), capi.PTR_DEVICE)
+    g_a.fill_(1)
     h.fold_keep_masks(keep_a.data_ptr(), dI.data_ptr(), len(M), g_a.data_ptr(), n_global)
     torch.cuda.synchronize()
     for _ in range(3):
-        g_b.zero_()
+        g_b.fill_(1)
         h.process_frames_ptr(dM.data_ptr(), mo, dQ.data_ptr(), qo, keep_b.data_ptr(), capi.PTR_DEVICE, (dI.data_ptr(), g_b.data_ptr(), n_global))
         torch.cuda.synchronize()
         assert torch.equal(keep_a, keep_b) and torch.equal(g_a, g_b)
@@ -380,7 +382,7 @@ def test_process_frames_fold_matches_separate_calls(capi, small_workload):
     hM, hQ = torch.from_numpy(M).pin_memory(), torch.from_numpy(Q).pin_memory()
     hK = torch.empty(len(M), dtype=torch.uint8).pin_memory()
     for _ in range(2):
-        g_b.zero_()
+        g_b.fill_(1)
         h.process_frames_ptr(hM.data_ptr(), mo, hQ.data_ptr(), qo, hK.data_ptr(), capi.PTR_HOST, (dI.data_ptr(), g_b.data_ptr(), n_global))
         torch.cuda.synchronize()
         assert torch.equal(keep_a.cpu(), hK) and torch.equal(g_a, g_b)

@@ -69,7 +69,7 @@ def test_capi_exports_every_declared_symbol():
     L = ctypes.CDLL(capi.LIB_PATH)          # loads without a GPU (no compute call is made)
     for s in sorted(declared):
         assert hasattr(L, s), s
-    assert L.erasor_abi_version() == 1
+    assert L.erasor_abi_version() == 2
 
 
 def test_create_fails_loudly_without_cuda():
