@@ -57,7 +57,9 @@ struct BinTablesView {
     int    R, S;
     int    sec_of_pi;        // sector of theta = atan2(+0, -1)
     double s_max;            // r <= max_r  <=>  s <= s_max
+    float  smax_lo, smax_hi; // float guard band around s_max: sf <= smax_lo => s <= s_max for sure; sf > smax_hi => s > s_max for sure
     const double*         ring_thr;   // [R+1]: [0] = -inf, [k] = min s with ring >= k, [R] = +inf
+    const float*          ring_guard; // [2(R+1)]: {up_k, dn_k}: sf >= up_k => s >= ring_thr[k] for sure; sf < dn_k => s < ring_thr[k] for sure
     const SectorBoundary* sec_pos;    // [S+1], entries 1..S-1 used, y > 0 branch (A in (0, pi])
     const SectorBoundary* sec_neg;    // [S+1], y < 0 branch (A in [-pi, 0))
 };

@@ -99,6 +99,23 @@ int build_bin_tables(const erasor_params_t& p, HostBinTables& out, std::string& 
     for (int k = 1; k <= R - 1; ++k)
         out.ring_thr[k] = first_true(0.0, s_hi_bound, [&](double s) { return ring_of_s(s, ring_size) >= k; });
 
+    // float guard bands for the device's fast path: sf = fmaf(y, y, x * x) in float differs from the exact s by at most
+    // 2^-23 relative (x * x rounded, then the fused add rounded; all terms non-negative).  With delta = 2^-22:
+    //   sf >= up(T) = T (1 + 2 delta), rounded up    =>  s >= T        sf < dn(T) = T (1 - 2 delta), rounded down  =>  s < T
+    // Points inside a band (a few in 10^6) take the exact double path.
+    {
+        const double delta2 = 2.0 * 0x1p-22;
+        const float finf = std::numeric_limits<float>::infinity();
+        auto up_of = [&](double T) { float f = (float)(T * (1.0 + delta2)); if ((double)f < T * (1.0 + delta2)) f = std::nextafterf(f, finf); return std::nextafterf(f, finf); };
+        auto dn_of = [&](double T) { float f = (float)(T * (1.0 - delta2)); if ((double)f > T * (1.0 - delta2)) f = std::nextafterf(f, -finf); return std::nextafterf(f, -finf); };
+        out.ring_guard.assign(2 * (size_t)(R + 1), 0.0f);
+        out.ring_guard[0] = -finf; out.ring_guard[1] = -finf;                       // T_0 = -inf: every s is >= it
+        for (int k = 1; k <= R - 1; ++k) { out.ring_guard[2 * k] = up_of(out.ring_thr[k]); out.ring_guard[2 * k + 1] = dn_of(out.ring_thr[k]); }
+        out.ring_guard[2 * R] = finf; out.ring_guard[2 * R + 1] = finf;             // T_R = +inf: every finite s is below it
+        out.smax_lo = dn_of(out.s_max);        // sf <= smax_lo  =>  s <= s_max   (dn is strictly below s_max (1 - 2 delta))
+        out.smax_hi = up_of(out.s_max);        // sf >  smax_hi  =>  s >  s_max
+    }
+
     // sectors
     const double A_MAX = std::atan2(0.0, -1.0);        // largest value atan2 can return
     out.sec_of_pi = std::min(sector_of_theta(A_MAX, sector_size), S - 1);

@@ -34,7 +34,8 @@ struct NodePose {
     double px, py;         // tf_body2origin(0,3), (1,3) as the reference reads them (:246-247)
     double limit;          // pow(max_range, 2)
     float  T[12];          // rows 0..2 of tf_body2origin.inverse()
-    float  pad_[2];
+    float  pxf, pyf;       // px, py as floats (they are floats widened to double, so this is exact)
+    float  lim_lo, lim_hi; // float guard band around limit: d2f < lim_lo => inside for sure, d2f > lim_hi => outside for sure
 };
 
 struct SrtParams {

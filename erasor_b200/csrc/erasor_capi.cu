@@ -97,7 +97,7 @@ struct erasor_ctx {
     int             sm_count = 148;
     std::string     err;
     HostBinTables   tables;
-    DevBuf          d_ring, d_pos, d_neg;
+    DevBuf          d_ring, d_pos, d_neg, d_guard;
     BinTablesView   view{};
     int             B = 0;
     uint64_t        alloc_epoch = 0;           // bumped by every DevBuf (re)allocation of this handle
@@ -117,7 +117,7 @@ struct erasor_ctx {
     DevBuf d_pack, d_gather;                   // exchange step: packed keep bits of this rank / of every rank
     PinnedBuf h_stage, h_pose;
     std::vector<DevBuf*> all_bufs() {
-        return {&d_ring, &d_pos, &d_neg, &d_map_in, &d_qry_in, &d_bin_map, &d_bin_qry, &d_chunks, &d_chunk_range, &d_frame_off, &d_chcnt, &d_zmin,
+        return {&d_ring, &d_pos, &d_neg, &d_guard, &d_map_in, &d_qry_in, &d_bin_map, &d_bin_qry, &d_chunks, &d_chunk_range, &d_frame_off, &d_chcnt, &d_zmin,
                 &d_zmax, &d_cnt, &d_dst_start, &d_status, &d_action, &d_flag_slot, &d_nflag, &d_recs, &d_nrecs, &d_queue, &d_bucket, &d_frame_rej,
                 &d_map_sorted, &d_map_src, &d_qry_sorted, &d_qry_src, &d_part, &d_scratch, &d_keep, &d_ground, &d_arranged, &d_map_rej, &d_curr_rej,
                 &d_jobs, &d_out_sizes, &d_k5tmp, &d_fence, &d_vox, &d_vox_cnt, &d_vox_start, &d_vox_scratch, &d_frame_rec_base, &d_poses, &d_pack,
@@ -139,6 +139,8 @@ struct erasor_ctx {
     struct StepGraph { const void* ptr[8]; size_t fold_n; int kind, mode, f0; uint64_t epoch, alloc; cudaGraphExec_t exec; };
     std::vector<StepGraph> graphs;             // captured mask-mode steps, one per (pointers, geometry)
     bool     use_graphs = true;
+    int      ctas_per_sm = 4;                  // K1 / K2 grid target: one wave of sm_count * ctas_per_sm CTAs (ERASOR_B200_CTAS_PER_SM)
+    bool     fused_srt = true;                 // mask modes: Scan Ratio Test inside the scatter kernel (ERASOR_B200_UNFUSED_SRT=1: separate k3_srt)
     uint64_t graph_kernel_nodes = 0;
     bool     pending = false;                  // an asynchronous submission has not been waited for yet
 
@@ -221,7 +223,7 @@ uint32_t choose_chunk(const erasor_ctx* h, const uint64_t* map_off, const uint64
     // wave costs a whole CTA latency.  Frames are chunked separately, so the count is taken over the real frame sizes.
     // The dense per-chunk count rows cost 4*(B+1) bytes each: keep the chunk at >= 5*B points (<= 5 % extra traffic).
     const size_t total = (size_t)(map_off[F] + qry_off[F]);
-    const size_t slots = (size_t)h->sm_count * 4;
+    const size_t slots = (size_t)h->sm_count * h->ctas_per_sm;
     auto count = [&](size_t ch) {
         size_t n = 0;
         for (int f = 0; f < F; ++f) n += (size_t)((map_off[f + 1] - map_off[f] + ch - 1) / ch) + (size_t)((qry_off[f + 1] - qry_off[f] + ch - 1) / ch);
@@ -358,8 +360,8 @@ int run_k1(erasor_ctx* h, int mode) {
     {
         h->launches++;
         CK(launch_init_tables(h->stream, h->d_zmin.as<uint32_t>(), h->d_zmax.as<uint32_t>(), 2 * (size_t)F * B,
-                              h->d_cnt.as<uint32_t>(), 2 * (size_t)F * (B + 1), h->d_nrecs.as<uint32_t>(), h->d_frame_rej.as<uint32_t>() + h->f0, F,
-                              h->d_queue.as<uint32_t>()));
+                              h->d_cnt.as<uint32_t>(), 2 * (size_t)F * (B + 1), h->d_nrecs.as<uint32_t>(), h->d_frame_rej.as<uint32_t>() + h->f0,
+                              h->d_nflag.as<uint32_t>() + h->f0, F, h->d_queue.as<uint32_t>()));
     }
     {
         Scope s(h, 1);
@@ -382,7 +384,8 @@ int run_compare(erasor_ctx* h, int version, int mode, uint8_t* keep_mask, uint8_
     sp.th_bin_max_h = h->p.th_bin_max_h;
     sp.minimum_num_pts = h->p.minimum_num_pts;
     sp.version = version; sp.R = h->p.num_rings; sp.S = h->p.num_sectors; sp.B = B; sp.scatter_mode = mode == 0 ? 0 : 1;
-    {
+    const bool fused = mode != 0 && h->fused_srt;      // mask modes: SRT inside the scatter kernel
+    if (!fused) {
         Scope s(h, 3);
         h->launches++;
         CK(launch_k3(h->stream, sp, F, h->d_chunk_range.as<uint32_t>(), h->d_chcnt.as<uint32_t>(), h->d_zmin.as<uint32_t>(),
@@ -401,8 +404,14 @@ int run_compare(erasor_ctx* h, int version, int mode, uint8_t* keep_mask, uint8_
             CK(launch_k2(h->stream, h->d_chunks.as<ChunkDesc>(), h->n_chunks_map, h->n_chunks_qry, h->d_bin_qry.as<uint16_t>(), h->cur_qry, nullptr,
                          h->d_chcnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>() + (size_t)F * (B + 2), nullptr, nullptr, h->d_qry_sorted.as<float4>(),
                          h->d_qry_src.as<uint32_t>(), B));
+        } else if (fused) {
+            if (h->n_chunks_map) h->launches++;
+            CK(launch_k2_srt(h->stream, sp, F, h->d_chunks.as<ChunkDesc>(), h->d_chunk_range.as<uint32_t>(), h->n_chunks_map, h->d_bin_map.as<uint16_t>(),
+                             h->cur_map, poses, h->d_chcnt.as<uint32_t>(), h->d_zmin.as<uint32_t>(), h->d_zmax.as<uint32_t>(), h->d_cnt.as<uint32_t>(),
+                             h->d_frame_off.as<uint32_t>(), nflag, h->d_recs.as<FlagRec>(), h->d_nrecs.as<uint32_t>(), h->rec_capacity,
+                             h->d_queue.as<uint32_t>(), h->d_bucket.as<uint32_t>(), h->d_map_sorted.as<float4>(), h->d_map_src.as<uint32_t>()));
         } else {
-            // mask modes: the same stable scatter, restricted to the flagged bins (K3's dense slots)
+            // mask modes, unfused (ERASOR_B200_UNFUSED_SRT=1): the same stable scatter, restricted to the flagged bins (K3's dense slots)
             if (h->n_chunks_map) h->launches++;
             CK(launch_k2(h->stream, h->d_chunks.as<ChunkDesc>(), 0u, h->n_chunks_map, h->d_bin_map.as<uint16_t>(), h->cur_map, poses,
                          h->d_chcnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>(), h->d_flag_slot.as<uint32_t>(), nflag,
@@ -475,6 +484,8 @@ int erasor_create(const erasor_params_t* params, int device, erasor_handle_t* ou
     h->p = p; h->device = device; h->B = (int)Bll;
     for (DevBuf* b : h->all_bufs()) b->epoch = &h->alloc_epoch;
     if (const char* ng = std::getenv("ERASOR_B200_NO_GRAPH")) h->use_graphs = !(ng[0] == '1');
+    if (const char* uf = std::getenv("ERASOR_B200_UNFUSED_SRT")) h->fused_srt = !(uf[0] == '1');
+    if (const char* cs = std::getenv("ERASOR_B200_CTAS_PER_SM")) h->ctas_per_sm = std::max(1, std::min(8, std::atoi(cs)));
     std::string terr;
     if (build_bin_tables(p, h->tables, terr) != 0) { g_create_error = terr; delete h; return ERASOR_E_INVALID; }
     auto fail = [&](const char* what, cudaError_t ce) {
@@ -499,6 +510,9 @@ int erasor_create(const erasor_params_t* params, int device, erasor_handle_t* ou
     if ((e = cudaEventCreateWithFlags(&h->ev_join_b, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&h->ev_join_c, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     const size_t rb = sizeof(double) * h->tables.ring_thr.size(), sb = sizeof(SectorBoundary) * h->tables.sec_pos.size();
+    const size_t gb = sizeof(float) * h->tables.ring_guard.size();
+    if ((e = h->d_guard.ensure(gb)) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = cudaMemcpy(h->d_guard.p, h->tables.ring_guard.data(), gb, cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy", e);
     if ((e = h->d_ring.ensure(rb)) != cudaSuccess || (e = h->d_pos.ensure(sb)) != cudaSuccess || (e = h->d_neg.ensure(sb)) != cudaSuccess ||
         (e = h->d_fence.ensure(sizeof(unsigned long long) * 4)) != cudaSuccess)
         return fail("cudaMalloc", e);
@@ -506,7 +520,7 @@ int erasor_create(const erasor_params_t* params, int device, erasor_handle_t* ou
     if ((e = cudaMemcpy(h->d_pos.p, h->tables.sec_pos.data(), sb, cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy", e);
     if ((e = cudaMemcpy(h->d_neg.p, h->tables.sec_neg.data(), sb, cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy", e);
     if ((e = cudaMemset(h->d_fence.p, 0, sizeof(unsigned long long) * 4)) != cudaSuccess) return fail("cudaMemset", e);
-    h->view = h->tables.view(h->d_ring.as<double>(), h->d_pos.as<SectorBoundary>(), h->d_neg.as<SectorBoundary>());
+    h->view = h->tables.view(h->d_ring.as<double>(), h->d_pos.as<SectorBoundary>(), h->d_neg.as<SectorBoundary>(), h->d_guard.as<float>());
     *out = h;
     return ERASOR_OK;
 }

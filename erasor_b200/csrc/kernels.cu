@@ -120,22 +120,25 @@ __device__ __forceinline__ float rsqrt_ftz(float v) { float r; asm("rsqrt.approx
 __device__ __forceinline__ float div_ftz(float a, float b) { float r; asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
 
 // the exact path of binning.h, kept out of line: it is taken by ~1e-4 of the points
-__device__ __noinline__ int bin_exact(const BinTablesView& T, const double* ring_thr, float x, float y, float z, BinFenceCounters* fc) {
-    return bin_of_point(T, ring_thr, x, y, z, fc);
+__device__ __noinline__ int bin_exact(const BinTablesView& T, float x, float y, float z, BinFenceCounters* fc) {
+    return bin_of_point(T, T.ring_thr, x, y, z, fc);
 }
 
-// Branch-free fast path of binning.h's bin_of_point for the device: returns the bin, -1 (not binned) or -3 when the
-// point needs the exact path (ring guess off, sector coordinate inside the guard band, y == 0).  The decisions are the
-// same threshold comparisons as in binning.h; only the guesses use approximate float ops (MUFU rcp / rsqrt).
-__device__ __forceinline__ int bin_fast(float x, float y, float z, float z_lo, float z_hi, double s_max, float inv_ring, float inv_ss,
-                                        float eps_q, int R, int S, const double* __restrict__ s_ring) {
-    const double xd = (double)x, yd = (double)y;
-    const double s  = fma(yd, yd, xd * xd);
-    const bool inr  = (z < z_hi) && (z > z_lo) && (s <= s_max);
-    const float sf  = fmaxf((float)s, 1e-30f);
-    int g = (int)(sf * rsqrt_ftz(sf) * inv_ring);
+// Branch-free fast path of binning.h's bin_of_point for the device, float arithmetic only: returns the bin, -1 (not
+// binned) or -3 when the point needs the exact path (r^2 inside the guard band of s_max or of a ring threshold, ring guess
+// off, sector coordinate inside its guard band, y == 0).  Every decision taken here is one the exact path would take too:
+// the float r^2 is compared against thresholds widened by its own worst-case error (binning_tables.cpp).
+__device__ __forceinline__ int bin_fast(float x, float y, float z, float z_lo, float z_hi, float smax_lo, float smax_hi, float inv_ring, float inv_ss,
+                                        float eps_q, int R, int S, const float2* __restrict__ s_ringf) {
+    const float sf   = fmaf(y, y, x * x);
+    const bool  zin  = (z < z_hi) && (z > z_lo);
+    const bool  in_sure  = sf <= smax_lo;
+    const bool  out_sure = !(sf <= smax_hi);                  // also NaN
+    const float sfc = fmaxf(sf, 1e-30f);
+    int g = (int)(sfc * rsqrt_ftz(sfc) * inv_ring);
     g = min(g, R - 1);
-    const bool ring_ok = (s_ring[g] <= s) && (s < s_ring[g + 1]);
+    const float2 t0 = s_ringf[g], t1 = s_ringf[g + 1];         // {up, dn} of thresholds g and g + 1
+    const bool ring_ok = (sf >= t0.x) && (sf < t1.y);
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
     float a = atan_unit(div_ftz(mn, mx));
@@ -146,8 +149,8 @@ __device__ __forceinline__ int bin_fast(float x, float y, float z, float z_lo, f
     const int   k  = (int)q;
     const float fr = q - (float)k;
     const bool sec_ok = (fr >= eps_q) && (fr <= 1.0f - eps_q) && (ay != 0.0f);
-    if (!inr) return -1;
-    if (!(ring_ok && sec_ok)) return -3;
+    if (!zin || out_sure) return -1;
+    if (!(in_sure && ring_ok && sec_ok)) return -3;
     return min(k, S - 1) * R + g;
 }
 
@@ -161,8 +164,14 @@ __device__ __forceinline__ float4 affine12(const float* __restrict__ T, float4 p
     o.w = p.w;
     return o;
 }
-// OfflineMapUpdater::fetch_VoI's cut (OfflineMapUpdater.cpp:394-396): pow(pt.x - x, 2) + pow(pt.y - y, 2) < max_dist_square in double
+// OfflineMapUpdater::fetch_VoI's cut (OfflineMapUpdater.cpp:394-396): pow(pt.x - x, 2) + pow(pt.y - y, 2) < max_dist_square in
+// double on float differences.  A float evaluation decides every point outside a 1e-6 band around the limit (its error is
+// below 2.4e-7 relative); points inside the band get the reference's double expression.
 __device__ __forceinline__ bool in_voi_radius(const NodePose& P, float x, float y) {
+    const float dxf = x - P.pxf, dyf = y - P.pyf;
+    const float d2f = fmaf(dyf, dyf, dxf * dxf);
+    if (d2f < P.lim_lo) return true;
+    if (d2f > P.lim_hi) return false;
     const double dx = __dsub_rn((double)x, P.px), dy = __dsub_rn((double)y, P.py);
     return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < P.limit;
 }
@@ -177,7 +186,7 @@ k1_rpod_bin(BinTablesView T, const float4* __restrict__ map_pts, const float4* _
             uint32_t* __restrict__ ch_cnt, uint32_t* __restrict__ zmin, uint32_t* __restrict__ zmax, uint32_t* __restrict__ cnt_tab,
             int B, int F, unsigned long long* __restrict__ fence, const NodePose* __restrict__ poses) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double*   s_ring = reinterpret_cast<double*>(smem_raw);
+    float2*   s_ring = reinterpret_cast<float2*>(smem_raw);               // {up, dn} guard thresholds of r^2 per ring boundary
     uint32_t* s_cnt  = reinterpret_cast<uint32_t*>(s_ring + ((T.R + 2) & ~1));
     uint32_t* s_mn   = s_cnt + (B + 1);
     uint32_t* s_mx   = s_mn + B;
@@ -188,7 +197,7 @@ k1_rpod_bin(BinTablesView T, const float4* __restrict__ map_pts, const float4* _
     __shared__ NodePose s_pose;
     const bool node_map = NODE && cd.cloud == 0;          // CTA-uniform
 
-    for (int i = tid; i <= T.R; i += THREADS) s_ring[i] = T.ring_thr[i];
+    for (int i = tid; i <= T.R; i += THREADS) s_ring[i] = make_float2(T.ring_guard[2 * i], T.ring_guard[2 * i + 1]);
     for (int i = tid; i <= B; i += THREADS) s_cnt[i] = 0u;
     for (int i = tid; i < B; i += THREADS) { s_mn[i] = 0xFFFFFFFFu; s_mx[i] = 0u; }
     if (NODE && tid == 0) s_pose = poses[cd.frame];
@@ -198,7 +207,7 @@ k1_rpod_bin(BinTablesView T, const float4* __restrict__ map_pts, const float4* _
     uint16_t* __restrict__     dst = (cd.cloud == 0 ? bin_map : bin_qry) + cd.bin_begin;
     BinFenceCounters fc{0u, 0u, 0u};
     const float  z_lo = T.z_lo, z_hi = T.z_hi, inv_ring = T.inv_ring, inv_ss = T.inv_ss, eps_q = T.eps_q;
-    const double s_max = T.s_max;
+    const float  smax_lo = T.smax_lo, smax_hi = T.smax_hi;
     const int    R = T.R, S = T.S;
 
     for (uint32_t base = warp * (32u * UNROLL); base < cd.len; base += NW * (32u * UNROLL)) {
@@ -217,12 +226,17 @@ k1_rpod_bin(BinTablesView T, const float4* __restrict__ map_pts, const float4* _
             float4 pp = p[u];
             if (node_map) {
                 inside = in_voi_radius(s_pose, pp.x, pp.y);
+                // the map is scanned in its own order, so whole warps fall outside the node's radius: they only clear their bin ids
+                if (!__any_sync(FULL_MASK, ok && inside)) {
+                    if (ok) dst[i] = kNoBin16;
+                    continue;
+                }
                 pp = affine12(s_pose.T, pp);
             }
-            int b = bin_fast(pp.x, pp.y, pp.z, z_lo, z_hi, s_max, inv_ring, inv_ss, eps_q, R, S, s_ring);
+            int b = bin_fast(pp.x, pp.y, pp.z, z_lo, z_hi, smax_lo, smax_hi, inv_ring, inv_ss, eps_q, R, S, s_ring);
             if (NODE && !inside) b = -1;
             if (__any_sync(FULL_MASK, ok && b == -3)) {
-                if (ok && b == -3) b = bin_exact(T, s_ring, pp.x, pp.y, pp.z, &fc);   // exact path (rare)
+                if (ok && b == -3) b = bin_exact(T, pp.x, pp.y, pp.z, &fc);   // exact path (rare)
             }
             int key = -2;
             if (ok) {
@@ -256,7 +270,7 @@ k1_rpod_bin(BinTablesView T, const float4* __restrict__ map_pts, const float4* _
 }
 
 size_t k1_smem_bytes(int R, int B) {
-    return sizeof(double) * ((R + 2) & ~1) + sizeof(uint32_t) * ((size_t)(B + 1) + 2 * (size_t)B);
+    return sizeof(float2) * ((R + 2) & ~1) + sizeof(uint32_t) * ((size_t)(B + 1) + 2 * (size_t)B);
 }
 
 cudaError_t launch_k1(cudaStream_t st, const BinTablesView& T, const float4* map_pts, const float4* qry_pts,
@@ -321,6 +335,20 @@ __device__ uint32_t block_excl_scan(const uint32_t* in, uint32_t* out, int n, ui
 }
 
 __device__ __forceinline__ double std_min_d(double a, double b) { return (b < a) ? b : a; }   // std::min, NaN-faithful (App. B-4)
+
+// Does the Scan Ratio Test hand this bin to R-GPF?  The same decisions as k3_srt's status passes, reduced to the one bit
+// the scatter needs: version 3 -- MAP_IS_HIGHER in pass 1 and map_dh > 0.5 in pass 2 (erasor.cpp:448-486, 507-511; the
+// neighbour test of pass 2 only relabels MERGE_BINS as BLOCKED); version 2 -- MAP_IS_HIGHER and map.max_h > th_bin_max_h
+// (erasor.cpp:346-389).
+__device__ __forceinline__ bool srt_is_flagged(const SrtParams& P, uint32_t mc, uint32_t qc, uint32_t zmx_m, uint32_t zmn_m, uint32_t zmx_q, uint32_t zmn_q) {
+    if (mc == 0u || qc == 0u || P.minimum_num_pts < 0 || qc < (uint32_t)P.minimum_num_pts) return false;
+    const double map_max = (double)ordered_to_float(zmx_m);
+    const double map_dh  = map_max - (double)ordered_to_float(zmn_m);
+    const double curr_dh = (double)ordered_to_float(zmx_q) - (double)ordered_to_float(zmn_q);
+    const double ratio   = std_min_d(map_dh / curr_dh, curr_dh / map_dh);
+    if (!(ratio < P.scan_ratio_threshold) || !(map_dh >= curr_dh)) return false;
+    return (P.version == 3) ? (map_dh > 0.5) : (map_max > P.th_bin_max_h);
+}
 
 __global__ void __launch_bounds__(1024)
 k3_srt(SrtParams P, int F, const uint32_t* __restrict__ chunk_range /*[2][F+1]*/, uint32_t* __restrict__ ch_cnt,
@@ -550,6 +578,87 @@ cudaError_t launch_k3(cudaStream_t st, const SrtParams& P, int F, const uint32_t
 // (40 x 360 bins in cloud mode) takes several window passes over the chunk's bin ids, so there is no bin-count limit
 // and no slow fallback.  NODE: points are read from the resident map and moved origin -> body on the way (fetch_VoI's
 // transform, OfflineMapUpdater.cpp:436), the source index is the global map index.
+// pass A of one window: per-slot counts of the warp's sub-range [s0, s1) into its own row
+__device__ __forceinline__ void k2_count_pass(const uint16_t* __restrict__ ids, uint32_t s0, uint32_t s1, const uint16_t* __restrict__ s_slot,
+                                              uint32_t win0, uint32_t ns, uint32_t* __restrict__ mine, int B, int lane) {
+    // Both passes walk the sub-range 256 points (8 steps of 32) at a time; the bin ids of the next block are loaded while
+    // the current one is processed, so that no step waits on global memory.  Only points of the window's slots take part
+    // in the match_any ranking.
+    uint16_t cur[8], nxt[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const uint32_t i = s0 + (uint32_t)u * 32u + lane; cur[u] = (i < s1) ? ids[i] : kNoBin16; }
+    for (uint32_t i0 = s0; i0 < s1; i0 += 256u) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const uint32_t i = i0 + 256u + (uint32_t)u * 32u + lane; nxt[u] = (i < s1) ? ids[i] : kNoBin16; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const uint32_t i = i0 + (uint32_t)u * 32u + lane;
+            const int      key  = (cur[u] == kNoBin16) ? B : (int)cur[u];
+            const uint32_t sl   = (uint32_t)s_slot[key] - win0;                 // 0xFFFF (not scattered) and other windows: >= ns
+            const bool     take = (i < s1) && (sl < ns);
+            const unsigned tmask = __ballot_sync(FULL_MASK, take);
+            if (take) {
+                const unsigned peers = __match_any_sync(tmask, sl);
+                if (lane == __ffs(peers) - 1) mine[sl] += __popc(peers);
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
+    }
+}
+
+// pass B of one window: re-walk the sub-range in order; mine[] holds the absolute destination of the next point per slot
+template <bool NODE>
+__device__ __forceinline__ void k2_scatter_pass(const uint16_t* __restrict__ ids, uint32_t s0, uint32_t s1, const uint16_t* __restrict__ s_slot,
+                                                uint32_t win0, uint32_t ns, uint32_t* __restrict__ mine, int B, int lane,
+                                                const float4* __restrict__ src, const float* __restrict__ s_T, uint32_t out_base, uint32_t local0,
+                                                float4* __restrict__ out_pts, uint32_t* __restrict__ out_src) {
+    uint16_t cur[8], nxt[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const uint32_t i = s0 + (uint32_t)u * 32u + lane; cur[u] = (i < s1) ? ids[i] : kNoBin16; }
+    for (uint32_t i0 = s0; i0 < s1; i0 += 256u) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const uint32_t i = i0 + 256u + (uint32_t)u * 32u + lane; nxt[u] = (i < s1) ? ids[i] : kNoBin16; }
+        uint32_t dst[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const uint32_t i = i0 + (uint32_t)u * 32u + lane;
+            const int      key  = (cur[u] == kNoBin16) ? B : (int)cur[u];
+            const uint32_t sl   = (uint32_t)s_slot[key] - win0;
+            const bool     take = (i < s1) && (sl < ns);
+            const uint32_t base = take ? mine[sl] : 0u;
+            const unsigned tmask = __ballot_sync(FULL_MASK, take);      // also orders the reads of mine[] before the updates below
+            dst[u] = kSkip;
+            if (take) {
+                const unsigned peers = __match_any_sync(tmask, sl);
+                if (lane == __ffs(peers) - 1) mine[sl] = base + __popc(peers);
+                dst[u] = base + __popc(peers & ((1u << lane) - 1u));
+            }
+            __syncwarp();
+        }
+        // the copies of the block, four at a time: all loads of a group in flight before its first store
+#pragma unroll
+        for (int g = 0; g < 8; g += 4) {
+            float4 pv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (dst[g + u] != kSkip) pv[u] = src[i0 + (uint32_t)(g + u) * 32u + lane];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (dst[g + u] != kSkip) {
+                    const size_t o = (size_t)out_base + dst[g + u];
+                    out_pts[o] = NODE ? affine12(s_T, pv[u]) : pv[u];
+                    out_src[o] = local0 + i0 + (uint32_t)(g + u) * 32u + lane;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
+    }
+}
+
 template <int W, bool NODE>
 __global__ void __launch_bounds__(W * 32, 4)      // 4 CTAs per SM: the chunking aims at one wave of sm_count * 4 CTAs
 k2_scatter_win(const ChunkDesc* __restrict__ chunks, uint32_t chunk_base, const uint16_t* __restrict__ bin_ids,
@@ -585,31 +694,7 @@ k2_scatter_win(const ChunkDesc* __restrict__ chunks, uint32_t chunk_base, const 
         __syncthreads();                                      // slot table ready / previous window's rows consumed
         for (uint32_t i = tid; i < (uint32_t)W * ns; i += W * 32) s_tab[i] = 0u;
         __syncthreads();
-        // Both passes walk the sub-range 256 points (8 steps of 32) at a time; the bin ids of the next block are loaded while
-        // the current one is processed, so that no step waits on global memory.  Only points of the window's slots take part
-        // in the match_any ranking.
-        uint16_t cur[8], nxt[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { const uint32_t i = s0 + (uint32_t)u * 32u + lane; cur[u] = (i < s1) ? ids[i] : kNoBin16; }
-        for (uint32_t i0 = s0; i0 < s1; i0 += 256u) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) { const uint32_t i = i0 + 256u + (uint32_t)u * 32u + lane; nxt[u] = (i < s1) ? ids[i] : kNoBin16; }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const uint32_t i = i0 + (uint32_t)u * 32u + lane;
-                const int      key  = (cur[u] == kNoBin16) ? B : (int)cur[u];
-                const uint32_t sl   = (uint32_t)s_slot[key] - win0;                 // 0xFFFF (not scattered) and other windows: >= ns
-                const bool     take = (i < s1) && (sl < ns);
-                const unsigned tmask = __ballot_sync(FULL_MASK, take);
-                if (take) {
-                    const unsigned peers = __match_any_sync(tmask, sl);
-                    if (lane == __ffs(peers) - 1) mine[sl] += __popc(peers);
-                }
-                __syncwarp();
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
-        }
+        k2_count_pass(ids, s0, s1, s_slot, win0, ns, mine, B, lane);
         // bases of the window's slots: dst_start + points of the bin in earlier chunks of the frame
         for (int b = tid; b <= B; b += W * 32) {
             const uint32_t sl = (uint32_t)s_slot[b] - win0;
@@ -626,49 +711,190 @@ k2_scatter_win(const ChunkDesc* __restrict__ chunks, uint32_t chunk_base, const 
             }
         }
         __syncthreads();
+        k2_scatter_pass<NODE>(ids, s0, s1, s_slot, win0, ns, mine, B, lane, src, s_T, cd.out_base, local0, out_pts, out_src);
+    }
+}
+
+// Mask modes: the Scan Ratio Test folded into the scatter (no k3_srt launch, no dependent round trip between them).
+// Every CTA (one per map chunk) recomputes its frame's flagged set from K1's R-POD tables -- B cheap FP64 decisions, the
+// tables sit in L2 -- numbers the flagged bins (slots, bin order), and per window of slots derives
+//   destination = (points of earlier flagged bins of the frame) + (points of the bin in earlier chunks of the frame) + earlier warps.
+// The first chunk of each frame is its LEADER: it also publishes n_flagged[frame] and the flagged-bin records + size
+// buckets R-GPF consumes (what k3_srt does in cloud mode).
+template <int W, bool NODE>
+__global__ void __launch_bounds__(W * 32, 4)
+k2_srt_scatter(SrtParams P, int F, const ChunkDesc* __restrict__ chunks, const uint32_t* __restrict__ chunk_range /*[2][F+1]*/,
+               const uint16_t* __restrict__ bin_ids, const float4* __restrict__ pts, const NodePose* __restrict__ poses,
+               const uint32_t* __restrict__ ch_cnt /*raw per-chunk counts*/, const uint32_t* __restrict__ zmin, const uint32_t* __restrict__ zmax,
+               const uint32_t* __restrict__ cnt /*[2][F][B+1]*/, const uint32_t* __restrict__ frame_off /*[2][F+1]*/,
+               uint32_t* __restrict__ n_flagged /*[F]*/, FlagRec* __restrict__ recs, uint32_t* __restrict__ n_recs, uint32_t rec_capacity,
+               uint32_t* __restrict__ queue, uint32_t* __restrict__ bucket_list,
+               float4* __restrict__ out_pts, uint32_t* __restrict__ out_src, uint32_t SW) {
+    extern __shared__ uint32_t s_tab[];   // [W][ns] rows | [SW] bases | u16 slot of every bin [B+1]
+    __shared__ float    s_T[12];
+    __shared__ uint32_t s_part[34];
+    __shared__ uint32_t s_bcast[2];
+    constexpr int NT = W * 32;
+    const int B = P.B;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t row = blockIdx.x;
+    const ChunkDesc cd = chunks[row];
+    const int f = (int)cd.frame;
+    const uint32_t row0 = chunk_range[f];                    // first chunk of the frame's map cloud
+    const bool leader = row == row0;
+    uint32_t* s_base = s_tab + (size_t)W * SW;
+    uint16_t* s_slot = reinterpret_cast<uint16_t*>(s_base + SW);
+    const uint32_t* cm = cnt + ((size_t)0 * F + f) * (B + 1);
+    const uint32_t* cq = cnt + ((size_t)1 * F + f) * (B + 1);
+    const uint32_t* mnm = zmin + ((size_t)0 * F + f) * B; const uint32_t* mxm = zmax + ((size_t)0 * F + f) * B;
+    const uint32_t* mnq = zmin + ((size_t)1 * F + f) * B; const uint32_t* mxq = zmax + ((size_t)1 * F + f) * B;
+
+    // ---- Scan Ratio Test: flagged bit per bin (coalesced over the tables) ----
+    for (int b = tid; b <= B; b += NT) {
+        bool fl = false;
+        if (b < B) {
+            const uint32_t mc = cm[b], qc = cq[b];
+            if (mc != 0u && qc != 0u) fl = srt_is_flagged(P, mc, qc, mxm[b], mnm[b], mxq[b], mnq[b]);
+        }
+        s_slot[b] = fl ? (uint16_t)0u : (uint16_t)0xFFFFu;
+    }
+    if (NODE && tid < 12) s_T[tid] = poses[f].T[tid];
+    __syncthreads();
+    // ---- slots: rank of every flagged bin, in bin order (each thread numbers a contiguous range of bins) ----
+    const int seg = (B + NT - 1) / NT;
+    const int b0 = min(B, tid * seg), b1 = min(B, b0 + seg);
+    uint32_t mycnt = 0;
+    for (int b = b0; b < b1; ++b) mycnt += (s_slot[b] == 0u) ? 1u : 0u;
+    uint32_t incl = mycnt;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { const uint32_t i = s0 + (uint32_t)u * 32u + lane; cur[u] = (i < s1) ? ids[i] : kNoBin16; }
-        for (uint32_t i0 = s0; i0 < s1; i0 += 256u) {
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_part[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = lane < W ? s_part[lane] : 0u;
+        uint32_t wi = w;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) { const uint32_t i = i0 + 256u + (uint32_t)u * 32u + lane; nxt[u] = (i < s1) ? ids[i] : kNoBin16; }
-            uint32_t dst[8];
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL_MASK, wi, o); if (lane >= o) wi += v; }
+        if (lane < W) s_part[lane] = wi - w;
+        if (lane == 31) s_part[33] = wi;
+    }
+    __syncthreads();
+    const uint32_t n_slots = s_part[33];
+    {
+        uint32_t run = s_part[warp] + incl - mycnt;
+        for (int b = b0; b < b1; ++b) if (s_slot[b] == 0u) s_slot[b] = (uint16_t)(run++);
+    }
+    if (leader && tid == 0) {
+        n_flagged[f] = n_slots;
+        s_bcast[0] = n_slots ? atomicAdd(n_recs, n_slots) : 0u;
+    }
+    __syncthreads();
+    const uint32_t rec_base = leader ? s_bcast[0] : 0u;
+
+    const uint32_t sub = (((cd.len + W - 1) / W) + 31u) & ~31u;
+    const uint32_t s0 = min(cd.len, (uint32_t)warp * sub), s1 = min(cd.len, s0 + sub);
+    const uint16_t* ids = bin_ids + cd.bin_begin;
+    const uint32_t local0 = cd.begin - cd.frame_begin;
+    const float4* src = pts + cd.begin;
+    const uint32_t fbase = frame_off[f];
+    uint32_t win_carry = 0u;                                  // points of the flagged bins of earlier windows
+
+    for (uint32_t win0 = 0; win0 < n_slots; win0 += SW) {
+        const uint32_t ns = min(SW, n_slots - win0);
+        uint32_t* mine = s_tab + (size_t)warp * ns;
+        uint32_t* s_bin = s_tab;                              // [ns] bin of every slot of the window   (rows are not in use yet)
+        uint32_t* s_pf  = s_tab + ns;                         // [ns] points of the bin in earlier chunks of the frame
+        __syncthreads();
+        for (int b = tid; b < B; b += NT) {
+            const uint32_t sl = (uint32_t)s_slot[b] - win0;
+            if (sl < ns) s_bin[sl] = (uint32_t)b;
+        }
+        __syncthreads();
+        // sizes -> s_base, earlier-chunk prefixes -> s_pf
+        for (uint32_t j = tid; j < ns; j += NT) {
+            const uint32_t b = s_bin[j];
+            s_base[j] = cm[b];
+            uint32_t pf = 0u;
+            for (uint32_t k0 = row0; k0 < row; k0 += 8u) {    // eight rows per round trip
+                uint32_t v[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const uint32_t i = i0 + (uint32_t)u * 32u + lane;
-                const int      key  = (cur[u] == kNoBin16) ? B : (int)cur[u];
-                const uint32_t sl   = (uint32_t)s_slot[key] - win0;
-                const bool     take = (i < s1) && (sl < ns);
-                const uint32_t base = take ? mine[sl] : 0u;
-                const unsigned tmask = __ballot_sync(FULL_MASK, take);      // also orders the reads of mine[] before the updates below
-                dst[u] = kSkip;
-                if (take) {
-                    const unsigned peers = __match_any_sync(tmask, sl);
-                    if (lane == __ffs(peers) - 1) mine[sl] = base + __popc(peers);
-                    dst[u] = base + __popc(peers & ((1u << lane) - 1u));
-                }
-                __syncwarp();
+                for (uint32_t u = 0; u < 8u; ++u) v[u] = (k0 + u < row) ? ch_cnt[(size_t)(k0 + u) * (B + 1) + b] : 0u;
+#pragma unroll
+                for (uint32_t u = 0; u < 8u; ++u) pf += v[u];
             }
-            // the copies of the block, four at a time: all loads of a group in flight before its first store
-#pragma unroll
-            for (int g = 0; g < 8; g += 4) {
-                float4 pv[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (dst[g + u] != kSkip) pv[u] = src[i0 + (uint32_t)(g + u) * 32u + lane];
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (dst[g + u] != kSkip) {
-                        const size_t o = (size_t)cd.out_base + dst[g + u];
-                        out_pts[o] = NODE ? affine12(s_T, pv[u]) : pv[u];
-                        out_src[o] = local0 + i0 + (uint32_t)(g + u) * 32u + lane;
+            s_pf[j] = pf;
+        }
+        __syncthreads();
+        const uint32_t win_total = block_excl_scan(s_base, s_base, (int)ns, s_part);     // offsets of the window's bins inside the frame's region
+        if (leader) {
+            // flagged-bin records for K4 (slot order == bin order) and their size buckets
+            for (uint32_t j = tid; j < ns; j += NT) {
+                const uint32_t b = s_bin[j], slot = win0 + j, ri = rec_base + slot, sz = cm[b];
+                if (ri < rec_capacity) {
+                    FlagRec& rc = recs[ri];
+                    rc.frame = (uint32_t)f; rc.bin = b; rc.slot = slot; rc.n_points = sz;
+                    rc.src_begin = fbase + win_carry + s_base[j];
+                    rc.n_seeds = 0; rc.n_empty_fits = 0; rc.n_ground_final = 0; rc.lpr_height = 0.0; rc.cursor = 0u; rc.n_rejected = 0u;
+                    if (sz != 0u) {
+                        const int bk = rgpf_bucket_of(sz);
+                        bucket_list[(size_t)bk * rec_capacity + atomicAdd(&queue[bk], 1u)] = ri;
                     }
                 }
             }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
         }
+        __syncthreads();
+        // absolute base per slot, then the rows can be zeroed (s_bin / s_pf live in them)
+        for (uint32_t j = tid; j < ns; j += NT) s_base[j] = win_carry + s_base[j] + s_pf[j];
+        __syncthreads();
+        for (uint32_t i = tid; i < (uint32_t)W * ns; i += NT) s_tab[i] = 0u;
+        __syncthreads();
+        k2_count_pass(ids, s0, s1, s_slot, win0, ns, mine, B, lane);
+        __syncthreads();
+        for (uint32_t j = tid; j < ns; j += NT) {
+            uint32_t run = s_base[j];
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                const uint32_t c = s_tab[(size_t)w * ns + j];
+                s_tab[(size_t)w * ns + j] = run;
+                run += c;
+            }
+        }
+        __syncthreads();
+        k2_scatter_pass<NODE>(ids, s0, s1, s_slot, win0, ns, mine, B, lane, src, s_T, cd.out_base, local0, out_pts, out_src);
+        win_carry += win_total;
     }
+}
+
+static void k2_smem_plan(int B, bool with_complement, uint32_t& SW, size_t& smem) {
+    constexpr int W = 8;
+    const size_t fixed  = ((sizeof(uint16_t) * ((size_t)B + 2)) + 15) & ~(size_t)15;
+    const size_t budget = 200 * 1024;
+    const uint32_t n_slots_max = with_complement ? (uint32_t)B + 1u : (uint32_t)B;
+    SW   = (uint32_t)std::min<size_t>(std::max<uint32_t>(n_slots_max, 1u), (budget - fixed) / (sizeof(uint32_t) * (W + 1)));
+    smem = sizeof(uint32_t) * (size_t)(W + 1) * SW + fixed;
+}
+
+cudaError_t launch_k2_srt(cudaStream_t st, const SrtParams& P, int F, const ChunkDesc* chunks, const uint32_t* chunk_range, uint32_t n_chunks_map,
+                          const uint16_t* bin_ids, const float4* pts, const NodePose* poses, const uint32_t* ch_cnt, const uint32_t* zmin,
+                          const uint32_t* zmax, const uint32_t* cnt, const uint32_t* frame_off, uint32_t* n_flagged, FlagRec* recs, uint32_t* n_recs,
+                          uint32_t rec_capacity, uint32_t* queue, uint32_t* bucket_list, float4* out_pts, uint32_t* out_src) {
+    if (n_chunks_map == 0) return cudaSuccess;
+    constexpr int W = 8;
+    uint32_t SW; size_t smem;
+    k2_smem_plan(P.B, false, SW, smem);
+    cudaError_t e;
+    if (poses) {
+        auto kern = k2_srt_scatter<W, true>;
+        if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
+        kern<<<n_chunks_map, W * 32, smem, st>>>(P, F, chunks, chunk_range, bin_ids, pts, poses, ch_cnt, zmin, zmax, cnt, frame_off, n_flagged, recs, n_recs,
+                                                 rec_capacity, queue, bucket_list, out_pts, out_src, SW);
+    } else {
+        auto kern = k2_srt_scatter<W, false>;
+        if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
+        kern<<<n_chunks_map, W * 32, smem, st>>>(P, F, chunks, chunk_range, bin_ids, pts, nullptr, ch_cnt, zmin, zmax, cnt, frame_off, n_flagged, recs, n_recs,
+                                                 rec_capacity, queue, bucket_list, out_pts, out_src, SW);
+    }
+    return cudaGetLastError();
 }
 
 cudaError_t launch_k2(cudaStream_t st, const ChunkDesc* chunks, uint32_t chunk_base, uint32_t n_chunks,
@@ -676,11 +902,8 @@ cudaError_t launch_k2(cudaStream_t st, const ChunkDesc* chunks, uint32_t chunk_b
                       const uint32_t* flag_slot, const uint32_t* n_flagged, float4* out_pts, uint32_t* out_src, int B) {
     if (n_chunks == 0) return cudaSuccess;
     constexpr int W = 8;
-    const size_t fixed  = ((sizeof(uint16_t) * ((size_t)B + 2)) + 15) & ~(size_t)15;
-    const size_t budget = 200 * 1024;
-    const uint32_t n_slots_max = flag_slot ? (uint32_t)B : (uint32_t)B + 1u;
-    const uint32_t SW = (uint32_t)std::min<size_t>(n_slots_max, (budget - fixed) / (sizeof(uint32_t) * (W + 1)));
-    const size_t smem = sizeof(uint32_t) * (size_t)(W + 1) * SW + fixed;
+    uint32_t SW; size_t smem;
+    k2_smem_plan(B, flag_slot == nullptr, SW, smem);
     cudaError_t e;
     if (poses) {
         auto kern = k2_scatter_win<W, true>;
@@ -1865,20 +2088,21 @@ cudaError_t launch_k5(cudaStream_t st, int B, int version, int skip_voxelize, co
 // small utilities
 // ============================================================================================
 __global__ void k_init_tables(uint32_t* zmin, uint32_t* zmax, size_t n, uint32_t* cnt, size_t n_cnt, uint32_t* n_recs,
-                              uint32_t* frame_rejected, int F, uint32_t* queue) {
+                              uint32_t* frame_rejected, uint32_t* n_flagged, int F, uint32_t* queue) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < (size_t)kQueueWords) queue[i] = 0u;
     if (i < n) { zmin[i] = 0xFFFFFFFFu; zmax[i] = 0u; }
     if (i < n_cnt) cnt[i] = 0u;
     if (i == 0) *n_recs = 0u;
     if (frame_rejected && i < (size_t)F) frame_rejected[i] = 0u;
+    if (n_flagged && i < (size_t)F) n_flagged[i] = 0u;      // (a frame without map points has no chunk, hence no leader CTA to write it)
 }
 cudaError_t launch_init_tables(cudaStream_t st, uint32_t* zmin, uint32_t* zmax, size_t n, uint32_t* cnt, size_t n_cnt, uint32_t* n_recs,
-                               uint32_t* frame_rejected, int F, uint32_t* queue) {
+                               uint32_t* frame_rejected, uint32_t* n_flagged, int F, uint32_t* queue) {
     size_t m = n > (size_t)F ? n : (size_t)F;
     m = m > n_cnt ? m : n_cnt;
     const int blocks = (int)((m + 255) / 256);
-    k_init_tables<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(zmin, zmax, n, cnt, n_cnt, n_recs, frame_rejected, F, queue);
+    k_init_tables<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(zmin, zmax, n, cnt, n_cnt, n_recs, frame_rejected, n_flagged, F, queue);
     return cudaGetLastError();
 }
 

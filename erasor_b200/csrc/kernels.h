@@ -20,7 +20,7 @@ size_t k1_smem_bytes(int R, int B);
 size_t k3_smem_bytes(int B);
 
 cudaError_t launch_init_tables(cudaStream_t st, uint32_t* zmin, uint32_t* zmax, size_t n, uint32_t* cnt, size_t n_cnt, uint32_t* n_recs,
-                               uint32_t* frame_rejected, int F, uint32_t* queue);
+                               uint32_t* frame_rejected, uint32_t* n_flagged, int F, uint32_t* queue);
 
 // poses != null: node mode (the map cloud is the resident global map; fetch_VoI's cut + transform fused into the binning)
 cudaError_t launch_k1(cudaStream_t st, const BinTablesView& T, const float4* map_pts, const float4* qry_pts,
@@ -31,6 +31,13 @@ cudaError_t launch_k3(cudaStream_t st, const SrtParams& P, int F, const uint32_t
                       const uint32_t* zmin, const uint32_t* zmax, const uint32_t* frame_off, const uint32_t* cnt, uint32_t* dst_start,
                       uint8_t* status, uint8_t* action, uint32_t* flag_slot, uint32_t* n_flagged, uint32_t* frame_rec_base,
                       FlagRec* recs, uint32_t* n_recs, uint32_t rec_capacity, uint32_t* queue, uint32_t* bucket_list);
+
+// mask modes: Scan Ratio Test + stable scatter of the flagged bins + R-GPF records / queue in one kernel (no k3_srt launch);
+// ch_cnt holds K1's raw per-chunk counts
+cudaError_t launch_k2_srt(cudaStream_t st, const SrtParams& P, int F, const ChunkDesc* chunks, const uint32_t* chunk_range, uint32_t n_chunks_map,
+                          const uint16_t* bin_ids, const float4* pts, const NodePose* poses, const uint32_t* ch_cnt, const uint32_t* zmin,
+                          const uint32_t* zmax, const uint32_t* cnt, const uint32_t* frame_off, uint32_t* n_flagged, FlagRec* recs, uint32_t* n_recs,
+                          uint32_t rec_capacity, uint32_t* queue, uint32_t* bucket_list, float4* out_pts, uint32_t* out_src);
 
 // flag_slot == null: every bin of dst_start's cloud that has an offset is scattered (cloud mode); otherwise the flagged bins only
 cudaError_t launch_k2(cudaStream_t st, const ChunkDesc* chunks, uint32_t chunk_base, uint32_t n_chunks,

@@ -172,7 +172,7 @@ def test_fold_accumulates_and_checks_bounds(capi, oracle_mod, small_workload):
 def test_sub_batch_split_many_small_frames(capi, oracle_mod):
     """More frames than one submission's work queue holds (40 x 360 bins: 2^21 / 14400 = 145 frames): the batch is split
     internally; every frame still equals the oracle and the per-frame counters cover the whole batch."""
-    from tests.test_gpu_parity import _crafted_bin_frame
+    from test_gpu_parity import _crafted_bin_frame
     p = P.preset("synthetic_40x360").replace(skip_voxelize=1)
     rng = np.random.default_rng(77)
     frames = [_crafted_bin_frame(rng, int(rng.integers(30, 120)), "rough") for _ in range(150)]
