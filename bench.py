@@ -407,6 +407,9 @@ def run_ours(args):
             h.wait()
 
     def timed(submit, steps, warmup, n_lanes):
+        # every (lane, input copy) pair is seen once before the clock starts: the library captures one CUDA graph per distinct
+        # set of buffer pointers, and a first use must not land inside the timed region
+        warmup = max(warmup, n_copies * n_lanes if submit is submit_resident else n_lanes)
         for i in range(warmup):
             lanes[i % n_lanes].wait()
             submit(i, i % n_lanes)

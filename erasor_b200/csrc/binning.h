@@ -78,7 +78,7 @@ ERASOR_HD bool sign_bit(float f) {
 #endif
 }
 
-// atan(t) for t in [0,1], |error| < 1.1e-7 in float arithmetic (tests/test_binning_host.py)
+// atan(t) for t in [0,1], |error| < 1.1e-7 in float arithmetic (tests/test_host_logic.py)
 ERASOR_HD float atan_unit(float t) {
     const float u = t * t;
     float p = 0.0028340641874819994f;

@@ -146,7 +146,7 @@ int build_bin_tables(const erasor_params_t& p, HostBinTables& out, std::string& 
     // guard band of the float sector coordinate q = theta_f * inv_ss (binning.h):
     //   |theta_f - theta| <= 1e-6 rad (polynomial 1.1e-7, division 3e-8, three float "C - a" steps with
     //   rounded constants 8.4e-7 worst case) and q carries two more float roundings (<= 1.2e-7 * S).
-    //   Doubled for margin; verified empirically by tests/test_binning_host.py.
+    //   Doubled for margin; verified empirically by tests/test_host_logic.py.
     out.eps_q = (float)(2.0 * (1.0e-6 / sector_size + 1.5e-7 * S));
     if (!(out.eps_q < 0.25f)) { err = "num_sectors too large for the float sector guess"; return -1; }
     return 0;

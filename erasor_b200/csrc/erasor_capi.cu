@@ -294,8 +294,8 @@ int prepare_batch(erasor_ctx* h, const uint64_t* map_off, const uint64_t* qry_of
     CK(h->d_chunks.ensure(sizeof(ChunkDesc) * std::max<size_t>(n_chunks, 1)));
     CK(h->d_chunk_range.ensure(sizeof(uint32_t) * range.size()));
     CK(h->d_frame_off.ensure(sizeof(uint32_t) * foff.size()));
-    CK(h->d_bin_map.ensure(sizeof(uint16_t) * std::max<size_t>(NM, 1)));
-    CK(h->d_bin_qry.ensure(sizeof(uint16_t) * std::max<size_t>(NQ, 1)));
+    CK(h->d_bin_map.ensure(sizeof(uint16_t) * (NM + kIdPad)));      // + slack: K2 prefetches ids past a chunk's end unchecked
+    CK(h->d_bin_qry.ensure(sizeof(uint16_t) * (NQ + kIdPad)));
     CK(h->d_chcnt.ensure(sizeof(uint32_t) * std::max<size_t>(n_chunks, 1) * (B + 1)));
     CK(h->d_map_sorted.ensure(sizeof(float4) * std::max<size_t>(NM, 1)));
     CK(h->d_zmin.ensure(sizeof(uint32_t) * 2 * (size_t)F * B));
@@ -857,7 +857,7 @@ int submit(erasor_ctx* h, const Submit& S) {
         if (!exec) {
             // drop graphs of older geometries, bound the cache
             for (size_t i = 0; i < h->graphs.size();) {
-                if (h->graphs[i].epoch != h->desc_epoch || h->graphs[i].alloc != h->alloc_epoch || h->graphs.size() > 16) { cudaGraphExecDestroy(h->graphs[i].exec); h->graphs.erase(h->graphs.begin() + i); }
+                if (h->graphs[i].epoch != h->desc_epoch || h->graphs[i].alloc != h->alloc_epoch || h->graphs.size() > 64) { cudaGraphExecDestroy(h->graphs[i].exec); h->graphs.erase(h->graphs.begin() + i); }
                 else ++i;
             }
             cudaGraph_t graph = nullptr;

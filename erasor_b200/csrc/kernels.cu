@@ -76,43 +76,16 @@ __device__ __forceinline__ void k1_aggregate(int key, uint32_t zenc, int lane, u
         }
         return;
     }
-    // runs of equal keys in lane order.  (Partial-mask __reduce_*_sync compiles to a per-lane software loop on sm_100a
-    // -- measured at 60 % of this kernel's instructions, also when the mask is full but the call sits in control flow the
-    // compiler cannot prove uniform -- so runs are reduced with a segmented shuffle scan.)
-    const int      prev  = __shfl_up_sync(FULL_MASK, key, 1);
-    const bool     head  = (lane == 0) || (key != prev);
-    const unsigned heads = __ballot_sync(FULL_MASK, head);
-    if (__popc(heads) >= 8) {
-        // incoherent input (a VoI cropped from an arbitrarily ordered map): runs are too short for the scan to pay --
-        // three shared-memory atomics per lane, at most a few lanes per address
-        if (key >= 0) {
-            if (key < B) {
-                atomicMin(&s_mn[key], zenc);
-                atomicMax(&s_mx[key], zenc);
-                atomicAdd(&s_cnt[key], 1u);
-            } else {
-                atomicAdd(&s_cnt[B], 1u);
-            }
-        }
-        return;
-    }
-    const unsigned above = heads & ~((2u << lane) - 1u);      // run heads at lanes > lane (lane 31: mask 0)
-    const int      e     = above ? (__ffs(above) - 1) : 32;   // my run is [.., e)
-    uint32_t mn = zenc, mx = zenc;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t omn = __shfl_down_sync(FULL_MASK, mn, d);
-        const uint32_t omx = __shfl_down_sync(FULL_MASK, mx, d);
-        if (lane + d < e) { mn = min(mn, omn); mx = max(mx, omx); }
-    }
-    if (head && key >= 0) {
+    // Mixed warp (in node mode a third of the lanes of a typical row lie outside the VoI, so runs of equal bins are short):
+    // per-lane shared-memory atomics, but only where they can change something -- a bin's min / max settle after its
+    // first few points, and a plain (possibly stale) read is a safe filter because the values only move one way.
+    // (A segmented shuffle scan over the runs was measured at 68 instructions per row here, ncu r02; this is ~14.)
+    if (key >= 0) {
         if (key < B) {
-            atomicMin(&s_mn[key], mn);
-            atomicMax(&s_mx[key], mx);
-            atomicAdd(&s_cnt[key], (uint32_t)(e - lane));
-        } else {
-            atomicAdd(&s_cnt[B], (uint32_t)(e - lane));
+            if (zenc < s_mn[key]) atomicMin(&s_mn[key], zenc);
+            if (zenc > s_mx[key]) atomicMax(&s_mx[key], zenc);
         }
+        atomicAdd(&s_cnt[key], 1u);          // key == B: the complement's count
     }
 }
 
@@ -584,16 +557,18 @@ __device__ __forceinline__ void k2_count_pass(const uint16_t* __restrict__ ids, 
     // Both passes walk the sub-range 256 points (8 steps of 32) at a time; the bin ids of the next block are loaded while
     // the current one is processed, so that no step waits on global memory.  Only points of the window's slots take part
     // in the match_any ranking.
-    uint16_t cur[8], nxt[8];
+    // (the id arrays carry kIdPad entries of slack, so the loads need no bounds checks: positions >= s1 are masked by `take`)
+    uint32_t cur[8], nxt[8];
+    const uint16_t* __restrict__ pb = ids + (size_t)s0 + lane;      // one 64-bit base per block, constant offsets per load
 #pragma unroll
-    for (int u = 0; u < 8; ++u) { const uint32_t i = s0 + (uint32_t)u * 32u + lane; cur[u] = (i < s1) ? ids[i] : kNoBin16; }
-    for (uint32_t i0 = s0; i0 < s1; i0 += 256u) {
+    for (int u = 0; u < 8; ++u) cur[u] = pb[u * 32];
+    for (uint32_t i0 = s0; i0 < s1; i0 += 256u, pb += 256) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { const uint32_t i = i0 + 256u + (uint32_t)u * 32u + lane; nxt[u] = (i < s1) ? ids[i] : kNoBin16; }
+        for (int u = 0; u < 8; ++u) nxt[u] = pb[256 + u * 32];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const uint32_t i = i0 + (uint32_t)u * 32u + lane;
-            const int      key  = (cur[u] == kNoBin16) ? B : (int)cur[u];
+            const int      key  = (cur[u] == (uint32_t)kNoBin16) ? B : (int)cur[u];
             const uint32_t sl   = (uint32_t)s_slot[key] - win0;                 // 0xFFFF (not scattered) and other windows: >= ns
             const bool     take = (i < s1) && (sl < ns);
             const unsigned tmask = __ballot_sync(FULL_MASK, take);
@@ -614,17 +589,18 @@ __device__ __forceinline__ void k2_scatter_pass(const uint16_t* __restrict__ ids
                                                 uint32_t win0, uint32_t ns, uint32_t* __restrict__ mine, int B, int lane,
                                                 const float4* __restrict__ src, const float* __restrict__ s_T, uint32_t out_base, uint32_t local0,
                                                 float4* __restrict__ out_pts, uint32_t* __restrict__ out_src) {
-    uint16_t cur[8], nxt[8];
+    uint32_t cur[8], nxt[8];
+    const uint16_t* __restrict__ pb = ids + (size_t)s0 + lane;      // one 64-bit base per block, constant offsets per load
 #pragma unroll
-    for (int u = 0; u < 8; ++u) { const uint32_t i = s0 + (uint32_t)u * 32u + lane; cur[u] = (i < s1) ? ids[i] : kNoBin16; }
-    for (uint32_t i0 = s0; i0 < s1; i0 += 256u) {
+    for (int u = 0; u < 8; ++u) cur[u] = pb[u * 32];
+    for (uint32_t i0 = s0; i0 < s1; i0 += 256u, pb += 256) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { const uint32_t i = i0 + 256u + (uint32_t)u * 32u + lane; nxt[u] = (i < s1) ? ids[i] : kNoBin16; }
+        for (int u = 0; u < 8; ++u) nxt[u] = pb[256 + u * 32];
         uint32_t dst[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const uint32_t i = i0 + (uint32_t)u * 32u + lane;
-            const int      key  = (cur[u] == kNoBin16) ? B : (int)cur[u];
+            const int      key  = (cur[u] == (uint32_t)kNoBin16) ? B : (int)cur[u];
             const uint32_t sl   = (uint32_t)s_slot[key] - win0;
             const bool     take = (i < s1) && (sl < ns);
             const uint32_t base = take ? mine[sl] : 0u;

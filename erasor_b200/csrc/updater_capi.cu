@@ -54,6 +54,8 @@ struct erasor_updater_ctx {
     size_t num_pcs_init = 0;
     int stack_count = 0;
     uint64_t launches = 0;
+    uint64_t map_version = 0;                       // bumped whenever the map changes (processed node, reset)
+    uint64_t save_version = ~0ull; float save_leaf = 0.0f; size_t save_n = 0;   // what save_out currently holds
 };
 
 namespace {
@@ -186,6 +188,7 @@ int erasor_updater_reset(erasor_updater_t u, const float* initial_map_xyzi, size
     u->n_global = u->up.is_large_scale ? n_map : 0;
     u->n_complement = 0; u->n_query = u->n_voi = u->n_out = u->n_rej = 0;
     u->submap_uninit = true; u->stack_count = 0;
+    u->map_version++;
     return ERASOR_OK;
 }
 
@@ -241,6 +244,7 @@ int erasor_updater_process_node(erasor_updater_t u, int seq, const double* odom7
     UCK(cudaStreamSynchronize(u->st));
     std::swap(u->map_a, u->map_b);
     u->n_map = n_new;
+    u->map_version++;
     if (processed) *processed = 1;
     return ERASOR_OK;
 }
@@ -287,9 +291,14 @@ int erasor_updater_save_static_map(erasor_updater_t u, float voxel_size, float* 
         if (u->n_complement) UCK(cudaMemcpyAsync(u->map_b.as<float4>() + u->n_map, u->complement.p, sizeof(float4) * u->n_complement, cudaMemcpyDeviceToDevice, u->st));
         src = u->map_b.as<float4>(); ns = u->n_map + u->n_complement;
     }
-    size_t k = 0;
-    int rc = voxelize(u, src, ns, voxel_size, u->save_out, &k);
-    if (rc) return rc;
+    // the usual call pattern is size query (out == NULL) followed by the fetch: the second call reuses the first one's result
+    // instead of voxelising the whole map again
+    size_t k = u->save_n;
+    if (!(u->save_version == u->map_version && u->save_leaf == voxel_size)) {
+        int rc = voxelize(u, src, ns, voxel_size, u->save_out, &k);
+        if (rc) return rc;
+        u->save_version = u->map_version; u->save_leaf = voxel_size; u->save_n = k;
+    }
     *n = k;
     if (!out_xyzi) return ERASOR_OK;
     if (cap < k) { u->err = "output buffer too small"; return ERASOR_E_CAPACITY; }
@@ -305,6 +314,7 @@ int erasor_updater_voxelize(erasor_updater_t u, const float* xyzi, size_t n_in, 
     UCK(u->scan.ensure(sizeof(float4) * std::max<size_t>(n_in, 1)));
     if (n_in) UCK(cudaMemcpyAsync(u->scan.p, xyzi, sizeof(float4) * n_in, cudaMemcpyHostToDevice, u->st));
     size_t k = 0;
+    u->save_version = ~0ull;                         // save_out is about to hold something else
     int rc = voxelize(u, u->scan.as<float4>(), n_in, leaf, u->save_out, &k);
     if (rc) return rc;
     *n = k;

@@ -3,7 +3,8 @@ user with the raw dataset can feed the device-resident OfflineMapUpdater (erasor
 examples/offline_map_updater_main.cpp) without ROS, rosbag or Python 2.
 
 What the reference's scripts/semantickitti2bag/kitti2node.py does, and this module reproduces:
-  * frames:  [init] + range(init, end, interval)  -- the first frame twice, "since the cpp drops the first data" (:386-388)
+  * frames:  [init] + range(init, end, interval)  -- the first frame twice in the BAG, "since the cpp drops the first data"
+    (:386-388); the C++ nodes therefore see range(init, end, interval), and so do the ROS-free callers here (iter_nodes)
   * pose of a node = tf_origin . T_w_cam0[i] . CAM2BASE  as translation + quaternion (x, y, z, w)  (:258-277, :296-309)
   * cloud = velodyne xyz with the FULL 32-bit SemanticKITTI label (semantic | instance << 16) cast NUMERICALLY to float32 in
     `intensity` (:322-324); the C++ side decodes it with static_cast<uint32_t>(intensity), & 0xFFFF for the class,
@@ -110,12 +111,17 @@ def is_dynamic(intensity: np.ndarray) -> np.ndarray:
     return np.isin(sem, DYNAMIC_CLASSES)
 
 
-def iter_nodes(dataset_root: str, sequence: str, init_stamp: int, end_stamp: int, interval: int
+def iter_nodes(dataset_root: str, sequence: str, init_stamp: int, end_stamp: int, interval: int, ros_duplicate_first: bool = False
                ) -> Iterator[Tuple[int, np.ndarray, np.ndarray]]:
-    """Yields (header.seq, odom[7], cloud[n, 4]) in the order the reference's bag holds them."""
+    """Yields (header.seq, odom[7], cloud[n, 4]) as the reference's C++ nodes RECEIVE them: range(init, end, interval).
+    The bag itself holds the first frame twice (frame_range) only because the subscribers drop their first message
+    (kitti2node.py:386-388); feeding that duplicate to a ROS-free caller would shift `stack_count % removal_interval`
+    (OfflineMapUpdater.cpp:206) and mapgen's accumulation by one node.  ros_duplicate_first=True reproduces the bag
+    contents (for export / bag parity)."""
     seq_dir = os.path.join(dataset_root, "sequences", sequence)
     poses = read_poses(os.path.join(seq_dir, "poses.txt"))
-    for f in frame_range(init_stamp, end_stamp, interval):
+    frames = frame_range(init_stamp, end_stamp, interval)
+    for f in (frames if ros_duplicate_first else frames[1:]):
         if f >= len(poses):
             raise IndexError(f"frame {f} beyond poses.txt ({len(poses)} poses)")
         scan = read_scan(os.path.join(seq_dir, "velodyne", f"{f:06d}.bin"))

@@ -67,8 +67,9 @@ def test_quaternion_round_trip():
 
 def test_nodes_follow_the_reference_conventions(dataset):
     root, poses, scans, labels = dataset
-    nodes = list(K.iter_nodes(root, "05", 2, 11, 3))
+    nodes = list(K.iter_nodes(root, "05", 2, 11, 3, ros_duplicate_first=True))          # the bag's contents
     assert [s for s, _, _ in nodes] == [2, 2, 5, 8]
+    assert [s for s, _, _ in K.iter_nodes(root, "05", 2, 11, 3)] == [2, 5, 8]           # what the C++ nodes receive (first message dropped)
     for seq, odom, cloud in nodes:
         tf = K.TF_ORIGIN @ poses[seq] @ K.CAM2BASE                                       # kitti2node.py:274-275
         assert np.allclose(odom[:3], tf[:3, 3], atol=1e-9)
@@ -84,7 +85,7 @@ def test_nodes_follow_the_reference_conventions(dataset):
 
 def test_export_layout_for_the_cpp_driver(dataset, tmp_path):
     root, poses, scans, labels = dataset
-    nodes = list(K.iter_nodes(root, "05", 0, 6, 2))
+    nodes = list(K.iter_nodes(root, "05", 0, 6, 2, ros_duplicate_first=True))
     out = tmp_path / "env"
     K.export_env_layout(nodes, str(out))
     rows = [l.strip().split(",") for l in open(out / "poses_lidar2body.csv")][1:]

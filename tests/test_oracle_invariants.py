@@ -160,7 +160,6 @@ def test_voxelize_preserving_labels(oracle_mod):
     key = np.floor(pts[:, :3] * np.float32(5.0)).astype(np.int64)
     assert len(out) == len(np.unique(key, axis=0))
     # labels are restored, never averaged: every output intensity is one of the input labels of a nearby point
-    d = np.linalg.norm(out[:, None, :3] - pts[None, :2000, :3], axis=2) if False else None
     assert set(np.unique(out[:, 3])).issubset(set(np.unique(pts[:, 3])))
     # brute-force 1-NN label check on a sample
     for i in rng.integers(0, len(out), 50):

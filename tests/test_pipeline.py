@@ -82,8 +82,8 @@ def test_sequence_pipeline_with_oracle_backends(oracle_mod, tmp_path):
     res = pipeline.run_semantickitti(root, "99", 0, 8, 1, str(cfg), out_dir=str(out),
                                      voxelize=lambda c, leaf: oracle_mod.voxelize(c, leaf),
                                      make_updater=lambda up, ep, m: _OracleUpdaterAdapter(oracle_mod, up, ep, m))
-    assert res["nodes"] == 9                                   # frame 0 twice (kitti2node.py:388)
-    assert 1 <= res["processed_scans"] <= 5                    # every removal_interval-th node
+    assert res["nodes"] == 8                                   # what the C++ subscribers receive: the bag's doubled first frame is dropped
+    assert res["processed_scans"] == 4                         # removal_interval 2: nodes 2, 4, 6, 8 of the 8 received (frames 1, 3, 5, 7)
     naive, static = res["naive_map"], res["static_map"]
     assert len(static) > 1000 and len(static) <= len(naive)
     n_dyn_before = int(kitti.is_dynamic(naive[:, 3]).sum())
