@@ -24,7 +24,7 @@ OK, E_INVALID, E_CUDA, E_STATE, E_CAPACITY, E_UNSUPPORTED = 0, -1, -2, -3, -4, -
 EXPORTS = [
     "erasor_create", "erasor_destroy", "erasor_last_error", "erasor_abi_version", "erasor_stream", "erasor_synchronize",
     "erasor_set_inputs", "erasor_compare", "erasor_get_output_sizes", "erasor_get_static_estimate", "erasor_get_outliers",
-    "erasor_get_max_range", "erasor_get_bins", "erasor_get_status", "erasor_get_planes", "erasor_get_static_mask",
+    "erasor_get_max_range", "erasor_get_ground_viz", "erasor_get_bins", "erasor_get_status", "erasor_get_planes", "erasor_get_static_mask",
     "erasor_get_fence_counts", "erasor_process_frames", "erasor_process_frames_async", "erasor_wait", "erasor_process_frames_fold",
     "erasor_process_frames_fold_async", "erasor_fold_keep_masks", "erasor_reset_keep_mask", "erasor_get_frame_stats", "erasor_kernel_launch_count",
     "erasor_map_create", "erasor_map_destroy", "erasor_map_size", "erasor_map_reset_keep", "erasor_map_get_keep", "erasor_map_keep_device",
@@ -73,6 +73,7 @@ def _load():
     L.erasor_get_output_sizes.argtypes = [c_void_p, POINTER(c_size_t), POINTER(c_size_t), POINTER(c_size_t), POINTER(c_size_t)]
     L.erasor_get_static_estimate.argtypes = [c_void_p, c_void_p, c_size_t, POINTER(c_size_t), c_void_p, c_size_t, POINTER(c_size_t), c_int]
     L.erasor_get_outliers.argtypes = [c_void_p, c_void_p, c_size_t, POINTER(c_size_t), c_void_p, c_size_t, POINTER(c_size_t), c_int]
+    L.erasor_get_ground_viz.argtypes = [c_void_p, c_void_p, c_size_t, POINTER(c_size_t), c_int]
     L.erasor_get_max_range.restype = c_double
     L.erasor_get_max_range.argtypes = [c_void_p]
     L.erasor_get_bins.argtypes = [c_void_p, c_int, POINTER(c_int32), fp, fp, POINTER(c_uint32)]
@@ -232,6 +233,14 @@ class Handle:
         a, c = c_size_t(), c_size_t()
         self._ck(self.L.erasor_get_outliers(self.h, mr.ctypes.data, nm, ctypes.byref(a), cr.ctypes.data, nq, ctypes.byref(c), PTR_HOST))
         return mr, cr
+
+    def get_ground_viz(self) -> np.ndarray:
+        n = c_size_t(0)
+        self._ck(self.L.erasor_get_ground_viz(self.h, None, 0, ctypes.byref(n), PTR_HOST))
+        out = np.empty((n.value, 4), dtype=np.float32)
+        if n.value:
+            self._ck(self.L.erasor_get_ground_viz(self.h, out.ctypes.data, n.value, ctypes.byref(n), PTR_HOST))
+        return out
 
     def get_max_range(self) -> float:
         return self.L.erasor_get_max_range(self.h)

@@ -92,8 +92,8 @@ struct NcclApi {
 struct erasor_ctx {
     erasor_params_t p{};
     int             device = 0;
-    cudaStream_t    stream = nullptr, stream_b = nullptr, stream_c = nullptr;   // b/c: concurrent R-GPF size classes
-    cudaEvent_t     ev_fork = nullptr, ev_join_b = nullptr, ev_join_c = nullptr;
+    cudaStream_t    stream = nullptr, stream_a = nullptr, stream_b = nullptr, stream_c = nullptr;   // a/b/c: concurrent R-GPF size classes (high priority)
+    cudaEvent_t     ev_fork = nullptr, ev_join_a = nullptr, ev_join_b = nullptr, ev_join_c = nullptr;
     int             sm_count = 148;
     std::string     err;
     HostBinTables   tables;
@@ -143,6 +143,12 @@ struct erasor_ctx {
     bool     fused_srt = true;                 // mask modes: Scan Ratio Test inside the scatter kernel (ERASOR_B200_UNFUSED_SRT=1: separate k3_srt)
     uint64_t graph_kernel_nodes = 0;
     bool     pending = false;                  // an asynchronous submission has not been waited for yet
+    // R-GPF class C (bins beyond 2560 points) is launched only while such bins are being seen (its CTAs need whole SMs even to
+    // find their queue empty, which serialises overlapped submissions); if one turns up unannounced, erasor_wait runs the class.
+    int      class_c_state = -1;               // -1 unknown (launch it), 0 none in the last run, > 0 seen
+    uint32_t class_c_count_host = 0;           // queue[kBucketC0] of the submission in flight
+    struct { bool with_c = true, host = false; int mode = 1; uint8_t* d_keep = nullptr; uint8_t* user_keep = nullptr; size_t n_keep = 0;
+             uint8_t* keep_out = nullptr; size_t n_map_global = 0; K4Fold fold{nullptr, nullptr, 0u, 0u}; } last;
 
     // node mode
     erasor_map_ctx* map = nullptr;
@@ -153,7 +159,7 @@ struct erasor_ctx {
 
     // single-frame state machine
     int      stage = 0;                        // 0: nothing, 1: inputs set, 2: compared
-    uint32_t out_sizes[4] = {0, 0, 0, 0};
+    uint32_t out_sizes[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // arranged, complement, map_rejected, curr_rejected, ground_viz
     uint32_t complement_start = 0;
     uint32_t n_recs_host = 0;
 
@@ -223,7 +229,7 @@ uint32_t choose_chunk(const erasor_ctx* h, const uint64_t* map_off, const uint64
     // wave costs a whole CTA latency.  Frames are chunked separately, so the count is taken over the real frame sizes.
     // The dense per-chunk count rows cost 4*(B+1) bytes each: keep the chunk at >= 5*B points (<= 5 % extra traffic).
     const size_t total = (size_t)(map_off[F] + qry_off[F]);
-    const size_t slots = (size_t)h->sm_count * h->ctas_per_sm;
+    const size_t slots = (size_t)h->sm_count * (k1_big_tables(h->p.num_rings, h->B) ? 1 : h->ctas_per_sm);
     auto count = [&](size_t ch) {
         size_t n = 0;
         for (int f = 0; f < F; ++f) n += (size_t)((map_off[f + 1] - map_off[f] + ch - 1) / ch) + (size_t)((qry_off[f + 1] - qry_off[f] + ch - 1) / ch);
@@ -375,7 +381,8 @@ int run_k1(erasor_ctx* h, int mode) {
 }
 
 // K3 -> K2 -> K4 ; mode 0: every bin scattered + partitioned copies (cloud outputs), mode 1 / 2: flagged only + masks
-int run_compare(erasor_ctx* h, int version, int mode, uint8_t* keep_mask, uint8_t* ground_mask, const K4Fold& fold) {
+// classes: which R-GPF size classes to launch (bits 0|1: A and B, bit 2: C); 0x8 alone = R-GPF only, for the class-C fix-up
+int run_compare(erasor_ctx* h, int version, int mode, uint8_t* keep_mask, uint8_t* ground_mask, const K4Fold& fold, int classes = 7, bool only_rgpf = false) {
     const int B = h->B, F = h->F;
     const NodePose* poses = mode == 2 ? h->d_poses.as<NodePose>() : nullptr;
     uint32_t* nflag = h->d_nflag.as<uint32_t>() + h->f0;
@@ -385,7 +392,7 @@ int run_compare(erasor_ctx* h, int version, int mode, uint8_t* keep_mask, uint8_
     sp.minimum_num_pts = h->p.minimum_num_pts;
     sp.version = version; sp.R = h->p.num_rings; sp.S = h->p.num_sectors; sp.B = B; sp.scatter_mode = mode == 0 ? 0 : 1;
     const bool fused = mode != 0 && h->fused_srt;      // mask modes: SRT inside the scatter kernel
-    if (!fused) {
+    if (!fused && !only_rgpf) {
         Scope s(h, 3);
         h->launches++;
         CK(launch_k3(h->stream, sp, F, h->d_chunk_range.as<uint32_t>(), h->d_chcnt.as<uint32_t>(), h->d_zmin.as<uint32_t>(),
@@ -394,7 +401,7 @@ int run_compare(erasor_ctx* h, int version, int mode, uint8_t* keep_mask, uint8_
                      h->d_frame_rec_base.as<uint32_t>(), h->d_recs.as<FlagRec>(), h->d_nrecs.as<uint32_t>(), h->rec_capacity,
                      h->d_queue.as<uint32_t>(), h->d_bucket.as<uint32_t>()));
     }
-    {
+    if (!only_rgpf) {
         Scope s(h, 2);
         if (mode == 0) {
             if (h->n_chunks_map) h->launches++;
@@ -423,18 +430,22 @@ int run_compare(erasor_ctx* h, int version, int mode, uint8_t* keep_mask, uint8_
         GpfParams gp{};
         gp.th_dist = h->p.gf_dist_thr; gp.th_seeds = h->p.gf_th_seeds_height; gp.num_lowest_pts = h->p.num_lowest_pts;
         gp.num_lpr = h->p.gf_num_lpr; gp.iters = std::min(h->p.gf_iter, kMaxIter); gp.cov_mode = h->p.cov_mode;
-        h->launches += k4_num_launches();
+        const bool with_c = (classes & 4) != 0;
+        h->launches += k4_num_launches(with_c);
         CK(cudaEventRecord(h->ev_fork, h->stream));
+        CK(cudaStreamWaitEvent(h->stream_a, h->ev_fork, 0));
         CK(cudaStreamWaitEvent(h->stream_b, h->ev_fork, 0));
-        CK(cudaStreamWaitEvent(h->stream_c, h->ev_fork, 0));
-        CK(launch_k4(h->stream, h->stream_b, h->stream_c, gp, h->d_recs.as<FlagRec>(), h->d_queue.as<uint32_t>(), h->d_bucket.as<uint32_t>(), h->rec_capacity,
+        if (with_c) CK(cudaStreamWaitEvent(h->stream_c, h->ev_fork, 0));
+        CK(launch_k4(h->stream_a, h->stream_b, h->stream_c, gp, h->d_recs.as<FlagRec>(), h->d_queue.as<uint32_t>(), h->d_bucket.as<uint32_t>(), h->rec_capacity,
                      h->d_map_sorted.as<float4>(), h->d_map_src.as<uint32_t>(), h->cur_map,
                      h->d_frame_off.as<uint32_t>(), mode == 0 ? h->d_part.as<float4>() : nullptr, keep_mask, ground_mask,
-                     h->d_frame_rej.as<uint32_t>() + h->f0, h->d_scratch.as<unsigned char>(), h->sm_count, h->d_fence.as<unsigned long long>(), fold));
+                     h->d_frame_rej.as<uint32_t>() + h->f0, h->d_scratch.as<unsigned char>(), h->sm_count, h->d_fence.as<unsigned long long>(), fold, classes));
+        CK(cudaEventRecord(h->ev_join_a, h->stream_a));
         CK(cudaEventRecord(h->ev_join_b, h->stream_b));
-        CK(cudaEventRecord(h->ev_join_c, h->stream_c));
+        if (with_c) CK(cudaEventRecord(h->ev_join_c, h->stream_c));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_join_a, 0));
         CK(cudaStreamWaitEvent(h->stream, h->ev_join_b, 0));
-        CK(cudaStreamWaitEvent(h->stream, h->ev_join_c, 0));
+        if (with_c) CK(cudaStreamWaitEvent(h->stream, h->ev_join_c, 0));
     }
     return ERASOR_OK;
 }
@@ -503,9 +514,16 @@ int erasor_create(const erasor_params_t* params, int device, erasor_handle_t* ou
         erasor_destroy(h);
         return ERASOR_E_UNSUPPORTED;
     }
-    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
-    if ((e = cudaStreamCreateWithFlags(&h->stream_b, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
-    if ((e = cudaStreamCreateWithFlags(&h->stream_c, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    // R-GPF's bins are long serial chains: its CTAs go first whenever SM resources free up (highest stream priority), the
+    // bandwidth / issue-bound kernels of this and of overlapped handles fill in around them
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (const char* np = std::getenv("ERASOR_B200_NO_PRIORITY")) { if (np[0] == '1') prio_hi = prio_lo; }
+    if ((e = cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_lo)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithPriority(&h->stream_a, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithPriority(&h->stream_b, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithPriority(&h->stream_c, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    if ((e = cudaEventCreateWithFlags(&h->ev_join_a, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&h->ev_join_b, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&h->ev_join_c, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
@@ -537,8 +555,10 @@ void erasor_destroy(erasor_handle_t h) {
     h->h_pose.release();
     h->h_stage.release();
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join_a) cudaEventDestroy(h->ev_join_a);
     if (h->ev_join_b) cudaEventDestroy(h->ev_join_b);
     if (h->ev_join_c) cudaEventDestroy(h->ev_join_c);
+    if (h->stream_a) cudaStreamDestroy(h->stream_a);
     if (h->stream_b) cudaStreamDestroy(h->stream_b);
     if (h->stream_c) cudaStreamDestroy(h->stream_c);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -618,7 +638,7 @@ int erasor_compare(erasor_handle_t h, int version, int frame) {
                      h->d_map_rej.as<float4>(), h->d_curr_rej.as<float4>(), h->d_jobs.as<CopyJob>(), h->d_out_sizes.as<uint32_t>(),
                      h->d_k5tmp.as<uint32_t>(), h->sm_count * 4));
     }
-    CK(cudaMemcpyAsync(h->out_sizes, h->d_out_sizes.p, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->out_sizes, h->d_out_sizes.p, sizeof(uint32_t) * 5, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(&h->complement_start, h->d_dst_start.as<uint32_t>() + B, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(&h->n_recs_host, h->d_nrecs.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -667,6 +687,22 @@ int erasor_get_outliers(erasor_handle_t h, float* map_rejected_xyzi, size_t cap_
     int rc;
     if (map_rejected_xyzi && (rc = copy_out(h, h->d_map_rej.p, map_rejected_xyzi, sizeof(float4) * h->out_sizes[2], ptr_kind))) return rc;
     if (curr_rejected_xyzi && (rc = copy_out(h, h->d_curr_rej.p, curr_rejected_xyzi, sizeof(float4) * h->out_sizes[3], ptr_kind))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return ERASOR_OK;
+}
+
+// ERASOR::ground_viz (public member, erasor.h:127): the R-GPF ground points of the flagged bins of the last compare, in
+// processing order -- the tail get_static_estimate appends to `arranged` (erasor.cpp:616)
+int erasor_get_ground_viz(erasor_handle_t h, float* ground_xyzi, size_t cap, size_t* n_ground, int ptr_kind) {
+    if (!h) return ERASOR_E_INVALID;
+    if (h->stage < 2) { h->err = "erasor_get_ground_viz before erasor_compare"; return ERASOR_E_STATE; }
+    const size_t n = h->out_sizes[4];
+    if (n_ground) *n_ground = n;
+    if (!ground_xyzi) return ERASOR_OK;
+    if (cap < n) { h->err = "output buffer too small"; return ERASOR_E_CAPACITY; }
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = copy_out(h, h->d_arranged.as<float4>() + (h->out_sizes[0] - n), ground_xyzi, sizeof(float4) * n, ptr_kind))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     return ERASOR_OK;
 }
@@ -810,6 +846,7 @@ int submit(erasor_ctx* h, const Submit& S) {
         CK(h->h_pose.ensure(sizeof(NodePose) * (size_t)S.F));
         std::memcpy(h->h_pose.p, S.poses, sizeof(NodePose) * (size_t)S.F);
     }
+    const bool with_c = h->class_c_state != 0;
     auto enqueue = [&]() -> int {
         int r;
         if (S.mode == 1) {
@@ -828,7 +865,10 @@ int submit(erasor_ctx* h, const Submit& S) {
         K4Fold fold{nullptr, nullptr, 0u, 0u};
         if (S.mode == 2)        fold = K4Fold{h->map->d_keep, nullptr, (uint32_t)n_map_global, 0u};
         else if (S.fold_global) fold = K4Fold{S.fold_global, S.fold_index, (uint32_t)std::min<size_t>(S.fold_n, 0xFFFFFFFFu), 0u};
-        if ((r = run_compare(h, h->p.version, S.mode, d_keep, nullptr, fold))) return r;
+        if ((r = run_compare(h, h->p.version, S.mode, d_keep, nullptr, fold, with_c ? 7 : 3))) return r;
+        h->last.with_c = with_c; h->last.host = host; h->last.mode = S.mode; h->last.d_keep = d_keep; h->last.user_keep = S.keep_mask; h->last.n_keep = n_keep;
+        h->last.keep_out = S.keep_out; h->last.n_map_global = n_map_global; h->last.fold = fold;
+        CK(cudaMemcpyAsync(&h->class_c_count_host, h->d_queue.as<uint32_t>() + kBucketC0, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
         if (host && n_keep) CK(cudaMemcpyAsync(S.keep_mask, d_keep, n_keep, cudaMemcpyDeviceToHost, h->stream));
         if (S.keep_out && n_map_global)
             CK(cudaMemcpyAsync(S.keep_out, h->map->d_keep, n_map_global, host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, h->stream));
@@ -846,7 +886,7 @@ int submit(erasor_ctx* h, const Submit& S) {
     if (graphable) {
         erasor_ctx::StepGraph key{};
         key.ptr[0] = S.map_xyzi; key.ptr[1] = S.qry_xyzi; key.ptr[2] = S.keep_mask; key.ptr[3] = S.fold_index; key.ptr[4] = S.fold_global;
-        key.ptr[5] = S.keep_out; key.ptr[6] = S.mode == 2 ? (const void*)h->map : nullptr; key.ptr[7] = nullptr;
+        key.ptr[5] = S.keep_out; key.ptr[6] = S.mode == 2 ? (const void*)h->map : nullptr; key.ptr[7] = with_c ? (const void*)h : nullptr;
         key.fold_n = S.fold_n; key.kind = S.ptr_kind; key.mode = S.mode; key.f0 = S.f0; key.epoch = h->desc_epoch; key.alloc = h->alloc_epoch;
         auto same = [&](const erasor_ctx::StepGraph& g) {
             return std::equal(g.ptr, g.ptr + 8, key.ptr) && g.fold_n == key.fold_n && g.kind == key.kind && g.mode == key.mode && g.f0 == key.f0 &&
@@ -887,6 +927,15 @@ int submit(erasor_ctx* h, const Submit& S) {
     } else {
         Scope whole(h, 0);
         if ((rc = enqueue())) return rc;
+    }
+    {   // what erasor_wait needs for the class-C fix-up (set here as well: a replayed graph does not run enqueue())
+        const bool hst = S.ptr_kind != ERASOR_PTR_DEVICE;
+        h->last.with_c = with_c; h->last.host = hst; h->last.mode = S.mode; h->last.user_keep = S.keep_mask; h->last.n_keep = n_keep;
+        h->last.d_keep = n_keep ? (hst ? h->d_keep.as<uint8_t>() : S.keep_mask) : nullptr;
+        h->last.keep_out = S.keep_out; h->last.n_map_global = n_map_global;
+        if (S.mode == 2)        h->last.fold = K4Fold{h->map->d_keep, nullptr, (uint32_t)n_map_global, 0u};
+        else if (S.fold_global) h->last.fold = K4Fold{S.fold_global, S.fold_index, (uint32_t)std::min<size_t>(S.fold_n, 0xFFFFFFFFu), 0u};
+        else                    h->last.fold = K4Fold{nullptr, nullptr, 0u, 0u};
     }
     h->pending = true;
     return ERASOR_OK;
@@ -986,6 +1035,17 @@ int erasor_wait(erasor_handle_t h) {
     if (h->pending) {
         h->pending = false;
         if (h->n_recs_host > h->rec_capacity) { h->err = "internal: flagged-bin records overflowed the work queue"; return ERASOR_E_CAPACITY; }
+        h->class_c_state = (int)std::min<uint32_t>(h->class_c_count_host, 0x7FFFFFFFu);
+        if (!h->last.with_c && h->class_c_count_host > 0) {
+            // bins beyond class B's capacity turned up in a submission that ran without class C: run that class now (R-GPF only; the
+            // bins are independent, the masks only gain zeros), then repeat the output copies.  The next submissions launch it up front.
+            int rc = run_compare(h, h->p.version, h->last.mode, h->last.d_keep, nullptr, h->last.fold, 4, true);
+            if (rc) return rc;
+            if (h->last.host && h->last.n_keep) CK(cudaMemcpyAsync(h->last.user_keep, h->last.d_keep, h->last.n_keep, cudaMemcpyDeviceToHost, h->stream));
+            if (h->last.keep_out && h->last.n_map_global)
+                CK(cudaMemcpyAsync(h->last.keep_out, h->map->d_keep, h->last.n_map_global, h->last.host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+        }
     }
     return ERASOR_OK;
 }

@@ -242,6 +242,8 @@ k1_rpod_bin(BinTablesView T, const float4* __restrict__ map_pts, const float4* _
     if (fc.slow) atomicAdd(&fence[3], (unsigned long long)fc.slow);
 }
 
+bool k1_big_tables(int R, int B) { return k1_smem_bytes(R, B) > 56 * 1024; }
+
 size_t k1_smem_bytes(int R, int B) {
     return sizeof(float2) * ((R + 2) & ~1) + sizeof(uint32_t) * ((size_t)(B + 1) + 2 * (size_t)B);
 }
@@ -250,9 +252,25 @@ cudaError_t launch_k1(cudaStream_t st, const BinTablesView& T, const float4* map
                       const ChunkDesc* chunks, int n_chunks, uint16_t* bin_map, uint16_t* bin_qry, uint32_t* ch_cnt,
                       uint32_t* zmin, uint32_t* zmax, uint32_t* cnt_tab, int B, int F, unsigned long long* fence, const NodePose* poses) {
     if (n_chunks == 0) return cudaSuccess;
-    constexpr int THREADS = 256, UNROLL = 4;
+    constexpr int UNROLL = 4;
     const size_t smem = k1_smem_bytes(T.R, B);
     cudaError_t e;
+    // Bin tables beyond ~56 KB (40 x 360 bins: 173 KB) leave one CTA per SM: give that CTA 32 warps instead of 8, the
+    // kernel needs ~32 resident warps per SM to cover its latencies (measured: 1 / 2 / 4 CTAs of 8 warps -> 128 / 75 / 62 us).
+    if (k1_big_tables(T.R, B)) {
+        constexpr int THREADS = 1024;
+        if (poses) {
+            auto kern = k1_rpod_bin<THREADS, UNROLL, true, true>;
+            if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
+            kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, poses);
+        } else {
+            auto kern = k1_rpod_bin<THREADS, UNROLL, true, false>;
+            if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
+            kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, nullptr);
+        }
+        return cudaGetLastError();
+    }
+    constexpr int THREADS = 256;
     if (poses) {
         auto kern = k1_rpod_bin<THREADS, UNROLL, true, true>;
         if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
@@ -568,7 +586,7 @@ __device__ __forceinline__ void k2_count_pass(const uint16_t* __restrict__ ids, 
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const uint32_t i = i0 + (uint32_t)u * 32u + lane;
-            const int      key  = (cur[u] == (uint32_t)kNoBin16) ? B : (int)cur[u];
+            const int      key  = (int)min(cur[u], (uint32_t)B);      // kNoBin16 -> B; also fences whatever the unchecked prefetch read behind the chunk
             const uint32_t sl   = (uint32_t)s_slot[key] - win0;                 // 0xFFFF (not scattered) and other windows: >= ns
             const bool     take = (i < s1) && (sl < ns);
             const unsigned tmask = __ballot_sync(FULL_MASK, take);
@@ -600,7 +618,7 @@ __device__ __forceinline__ void k2_scatter_pass(const uint16_t* __restrict__ ids
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const uint32_t i = i0 + (uint32_t)u * 32u + lane;
-            const int      key  = (cur[u] == (uint32_t)kNoBin16) ? B : (int)cur[u];
+            const int      key  = (int)min(cur[u], (uint32_t)B);      // kNoBin16 -> B; also fences whatever the unchecked prefetch read behind the chunk
             const uint32_t sl   = (uint32_t)s_slot[key] - win0;
             const bool     take = (i < s1) && (sl < ns);
             const uint32_t base = take ? mine[sl] : 0u;
@@ -844,9 +862,12 @@ k2_srt_scatter(SrtParams P, int F, const ChunkDesc* __restrict__ chunks, const u
 static void k2_smem_plan(int B, bool with_complement, uint32_t& SW, size_t& smem) {
     constexpr int W = 8;
     const size_t fixed  = ((sizeof(uint16_t) * ((size_t)B + 2)) + 15) & ~(size_t)15;
-    const size_t budget = 200 * 1024;
+    // one window over all slots while that leaves >= 2 CTAs per SM (<= 100 KB); beyond (40 x 360 bins) a 1536-slot window:
+    // mask mode rarely has more flagged bins per frame than that, cloud mode takes ceil((B + 1) / 1536) passes
     const uint32_t n_slots_max = with_complement ? (uint32_t)B + 1u : (uint32_t)B;
-    SW   = (uint32_t)std::min<size_t>(std::max<uint32_t>(n_slots_max, 1u), (budget - fixed) / (sizeof(uint32_t) * (W + 1)));
+    const size_t full = sizeof(uint32_t) * (size_t)(W + 1) * n_slots_max + fixed;
+    const size_t budget = full <= 100 * 1024 ? full : std::min<size_t>(full, fixed + sizeof(uint32_t) * (size_t)(W + 1) * 1536);
+    SW   = (uint32_t)std::min<size_t>(std::max<uint32_t>(n_slots_max, 1u), std::max<size_t>(1, (budget - fixed) / (sizeof(uint32_t) * (W + 1))));
     smem = sizeof(uint32_t) * (size_t)(W + 1) * SW + fixed;
 }
 
@@ -1772,12 +1793,12 @@ static cudaError_t launch_k4_class(cudaStream_t st, const GpfParams& P, FlagRec*
     return cudaGetLastError();
 }
 
-int k4_num_launches() { return 3; }
+int k4_num_launches(bool with_class_c) { return with_class_c ? 3 : 2; }
 
 cudaError_t launch_k4(cudaStream_t st, cudaStream_t st_b, cudaStream_t st_c, const GpfParams& P, FlagRec* recs, uint32_t* queue,
                       const uint32_t* bucket_list, uint32_t rec_capacity, const float4* sorted_pts, uint32_t* sorted_src, const float4* in_pts,
                       const uint32_t* frame_off, float4* part_pts, uint8_t* keep_mask, uint8_t* ground_mask, uint32_t* frame_rejected,
-                      unsigned char* gscratch, int sm_count, unsigned long long* fence, const K4Fold& fold) {
+                      unsigned char* gscratch, int sm_count, unsigned long long* fence, const K4Fold& fold, int classes) {
     // The three size classes touch disjoint bins, so they run concurrently on three streams (the caller forks / joins).
     // Shared memory is sized so that one class-A CTA (8 bins) and two class-B CTAs are resident per SM at the same time:
     //   A  8 x 8.75 KB slices + 18.7 KB products  ~ 90 KB      B  52.6 KB + 9.3 KB products ~ 62 KB each   (A + 2B ~ 214 KB of 227 KB)
@@ -1785,10 +1806,16 @@ cudaError_t launch_k4(cudaStream_t st, cudaStream_t st_b, cudaStream_t st_c, con
     // usual case for KITTI-sized maps) do not have to wait for shared memory held by A and B.
     static_assert(kClassAMax <= 512 && kClassBMax <= 4096, "sort networks: 16 keys per lane");
     cudaError_t e;
-    // class C: n > 2560, one 1024-thread CTA with most of an SM's shared memory; beyond ~8.7 k points global scratch
-    e = launch_k4_class<1024, 1024>(st_c, P, recs, queue, bucket_list, rec_capacity, kBucketC0, kBucketB0, 2, 180 * 1024, sorted_pts, sorted_src,
-                                    in_pts, frame_off, part_pts, keep_mask, ground_mask, frame_rejected, gscratch, sm_count, fence, fold);
-    if (e != cudaSuccess) return e;
+    // class C: n > 2560, one 1024-thread CTA with most of an SM's shared memory; beyond ~8.7 k points global scratch.
+    // Each of its CTAs needs a whole SM's registers just to find its queue empty, which stalls behind (and in front of) the
+    // kernels of overlapped submissions: the caller leaves it out (classes & 4 == 0) while no such bin has been seen, and
+    // runs it afterwards (classes == 4) if one turns up.
+    if (classes & 4) {
+        e = launch_k4_class<1024, 1024>(st_c, P, recs, queue, bucket_list, rec_capacity, kBucketC0, kBucketB0, 2, 180 * 1024, sorted_pts, sorted_src,
+                                        in_pts, frame_off, part_pts, keep_mask, ground_mask, frame_rejected, gscratch, sm_count, fence, fold);
+        if (e != cudaSuccess) return e;
+    }
+    if (!(classes & 3)) return cudaSuccess;
     // class B: 512 < n <= 2560, one 256-thread CTA per bin
     e = launch_k4_class<256, 256>(st_b, P, recs, queue, bucket_list, rec_capacity, kBucketB0, kBucketA0, 1, 21 * kClassBMax + 64, sorted_pts,
                                   sorted_src, in_pts, frame_off, part_pts, keep_mask, ground_mask, frame_rejected, gscratch, sm_count * 2, fence, fold);
@@ -2037,6 +2064,7 @@ k5_plan(int B, int version, int skip_voxelize, const uint32_t* __restrict__ cnt 
         out_sizes[1] = cm[B];
         out_sizes[2] = rj_total;
         out_sizes[3] = cr_total;
+        out_sizes[4] = gv_total;          // ground_viz = the tail of arranged (erasor.cpp:616)
     }
 }
 

@@ -17,6 +17,7 @@ struct CopyJob {
 };
 
 size_t k1_smem_bytes(int R, int B);
+bool   k1_big_tables(int R, int B);      // one 1024-thread CTA per SM instead of four 256-thread ones
 size_t k3_smem_bytes(int B);
 
 cudaError_t launch_init_tables(cudaStream_t st, uint32_t* zmin, uint32_t* zmax, size_t n, uint32_t* cnt, size_t n_cnt, uint32_t* n_recs,
@@ -44,14 +45,14 @@ cudaError_t launch_k2(cudaStream_t st, const ChunkDesc* chunks, uint32_t chunk_b
                       const uint16_t* bin_ids, const float4* pts, const NodePose* poses, const uint32_t* ch_cnt, const uint32_t* dst_start,
                       const uint32_t* flag_slot, const uint32_t* n_flagged, float4* out_pts, uint32_t* out_src, int B);
 
-int k4_num_launches();
+int k4_num_launches(bool with_class_c);
 // sorted_pts / sorted_src: K2's output (bins contiguous in source order + source index of every slot); in_pts is unused
 // since K2 also serves mask mode, kept in the signature for ABI stability of the launch wrapper.
 // queue / bucket_list: the size-bucketed work queue K3 filled (device_types.h).
 cudaError_t launch_k4(cudaStream_t st, cudaStream_t st_b, cudaStream_t st_c, const GpfParams& P, FlagRec* recs, uint32_t* queue,
                       const uint32_t* bucket_list, uint32_t rec_capacity, const float4* sorted_pts, uint32_t* sorted_src, const float4* in_pts, const uint32_t* frame_off,
                       float4* part_pts, uint8_t* keep_mask, uint8_t* ground_mask, uint32_t* frame_rejected, unsigned char* gscratch,
-                      int sm_count, unsigned long long* fence, const K4Fold& fold);
+                      int sm_count, unsigned long long* fence, const K4Fold& fold, int classes /*bit 0|1: A and B, bit 2: C*/);
 
 cudaError_t launch_k4b(cudaStream_t st, float leaf, int B, const FlagRec* recs, const uint32_t* n_recs, uint32_t rec_capacity,
                        const uint32_t* cnt, const uint32_t* dst_start, const float4* qry_sorted, const float4* part_pts,

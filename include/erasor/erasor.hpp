@@ -10,6 +10,7 @@
 // arithmetic.  The rviz / debug publishers of the reference (erasor.h:67-77) are not mirrored.
 #pragma once
 #include <algorithm>
+#include <array>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -38,11 +39,11 @@ inline erasor_params_t default_params() {
 class ERASOR {
 public:
     // replaces ERASOR(ros::NodeHandle*): parameters are read once, R-PODs are allocated once (erasor.h:46-103)
-    explicit ERASOR(const erasor_params_t& params, int device = 0) : params_(params) {
+    explicit ERASOR(const erasor_params_t& params, int device = 0) : params_(params), device_(device) {
         const int rc = erasor_create(&params_, device, &h_);
         if (rc != ERASOR_OK) throw std::runtime_error(std::string("ERASOR: ") + erasor_last_error(nullptr));
     }
-    ~ERASOR() { erasor_destroy(h_); }
+    ~ERASOR() { erasor_destroy(h_); if (map_) erasor_map_destroy(map_); }
     ERASOR(const ERASOR&) = delete;
     ERASOR& operator=(const ERASOR&) = delete;
 
@@ -72,6 +73,49 @@ public:
     }
     double get_max_range() { return erasor_get_max_range(h_); }               // erasor.cpp:628
 
+    // ---- the reference's public data members (erasor.h:127, 139-145), refreshed by refresh_debug_members() ----------
+    // The reference fills them as a side effect of compare_*; here they cost device -> host copies, so they are filled on
+    // request: call refresh_debug_members() after compare_* (OfflineMapUpdater.cpp never reads them; rviz publishers do).
+    PointCloud ground_viz;             // erasor.h:127  ground points of the flagged bins (also the tail of `arranged`)
+    PointCloud debug_curr_rejected;    // erasor.h:139
+    PointCloud debug_map_rejected;     // erasor.h:140
+    PointCloud map_complement;         // erasor.h:141
+    void refresh_debug_members() {
+        size_t ng = 0;
+        check(erasor_get_ground_viz(h_, nullptr, 0, &ng, ERASOR_PTR_HOST));
+        ground_viz.resize(ng);
+        if (ng) check(erasor_get_ground_viz(h_, reinterpret_cast<float*>(ground_viz.data()), ng, &ng, ERASOR_PTR_HOST));
+        get_outliers(debug_map_rejected, debug_curr_rejected);
+        PointCloud arranged_unused;
+        get_static_estimate(arranged_unused, map_complement);
+    }
+    // r_pod_map / r_pod_curr (erasor.h:143-144) as flat tables: bin = sector * num_rings + ring.  which: ERASOR_CLOUD_MAP / _QUERY
+    struct RPodTables { std::vector<int32_t> bin_of_point; std::vector<float> min_h, max_h; std::vector<uint32_t> count; };
+    RPodTables r_pod(int which, size_t n_points) {
+        RPodTables t;
+        const size_t B = static_cast<size_t>(params_.num_rings) * params_.num_sectors;
+        t.bin_of_point.resize(n_points); t.min_h.resize(B); t.max_h.resize(B); t.count.resize(B);
+        check(erasor_get_bins(h_, which, t.bin_of_point.data(), t.min_h.data(), t.max_h.data(), t.count.data()));
+        return t;
+    }
+    // ERASOR::is_dynamic_obj_close (public, erasor.h:132 / erasor.cpp:573-595) on the status of the last compare: is any of
+    // the 8 neighbours of bin (r_target, theta_target) CURR_IS_HIGHER?  The theta wrap uses num_rings like the reference
+    // (sic); candidates that wrap out of range are skipped (the reference would index out of bounds).
+    bool is_dynamic_obj_close(int r_target, int theta_target, int r_size = 1, int theta_size = 1) {
+        const std::vector<float> st = get_status();
+        const int R = params_.num_rings, S = params_.num_sectors;
+        for (int j = theta_target - theta_size; j <= theta_target + theta_size; ++j) {
+            int tj = j;
+            if (j < 0) tj = j + R; else if (j >= S) tj = j - R;
+            if (tj < 0 || tj >= S) continue;
+            for (int r = std::max(0, r_target - r_size); r <= std::min(r_target + r_size, R - 1); ++r) {
+                if (r == r_target && tj == theta_target) continue;
+                if (st[static_cast<size_t>(tj) * R + r] == ERASOR_STATUS_CURR_IS_HIGHER) return true;
+            }
+        }
+        return false;
+    }
+
     // Frame-independent batch mode (no counterpart in the reference; BASELINE.json north_star): F independent
     // (map VoI, query VoI) pairs in one submission.  keep[f][i] == 0 where frame f rejects the i-th point of its map VoI.
     std::vector<std::vector<uint8_t>> process_frames(const std::vector<PointCloud>& map_vois, const std::vector<PointCloud>& query_vois) {
@@ -92,6 +136,47 @@ public:
         return out;
     }
 
+    // ---- map-resident frame-independent mode + the single collective (north_star's multi-GPU form), C++ face ---------
+    // Upload the global map once (load_global_map), then per batch only poses + body-frame queries cross PCIe.
+    void load_global_map(const PointCloud& map_origin_frame) {
+        if (map_) { erasor_attach_map(h_, nullptr); erasor_map_destroy(map_); map_ = nullptr; }
+        int dev = 0;
+        if (erasor_map_create(reinterpret_cast<const float*>(map_origin_frame.data()), map_origin_frame.size(), ERASOR_PTR_HOST, device_, &map_) != ERASOR_OK)
+            throw std::runtime_error(std::string("ERASOR: ") + erasor_last_error(nullptr));
+        (void)dev;
+        check(erasor_attach_map(h_, map_));
+    }
+    // poses: x y z qx qy qz qw (body -> origin) per node; queries voxelised and in the body frame.  Returns the map's keep
+    // mask after this batch (1 = static so far); it accumulates over calls (reset_static_mask() starts a job).
+    std::vector<uint8_t> process_nodes(const std::vector<std::array<double, 7>>& poses, const std::vector<PointCloud>& query_vois, double voi_max_range = 0.0) {
+        if (!map_) throw std::logic_error("ERASOR: load_global_map first");
+        if (poses.size() != query_vois.size() || poses.empty()) throw std::invalid_argument("ERASOR: one pose per query VoI");
+        const size_t F = poses.size();
+        std::vector<uint64_t> qo(F + 1, 0);
+        for (size_t f = 0; f < F; ++f) qo[f + 1] = qo[f] + query_vois[f].size();
+        PointCloud q(qo[F]);
+        for (size_t f = 0; f < F; ++f) std::copy(query_vois[f].begin(), query_vois[f].end(), q.begin() + static_cast<std::ptrdiff_t>(qo[f]));
+        std::vector<uint8_t> keep(std::max<size_t>(erasor_map_size(map_), 1));
+        check(erasor_process_nodes(h_, poses[0].data(), reinterpret_cast<const float*>(q.data()), qo.data(), static_cast<int>(F), voi_max_range,
+                                   nullptr, keep.data(), ERASOR_PTR_HOST));
+        keep.resize(erasor_map_size(map_));
+        return keep;
+    }
+    void reset_static_mask() { if (map_ && erasor_map_reset_keep(map_) != ERASOR_OK) throw std::runtime_error("ERASOR: erasor_map_reset_keep"); }
+    // frame-sharded job: every rank processes its own nodes, then ONE all-gather (bit-packed masks over NVLink) + AND gives
+    // every rank the job's static mask.  id128 from erasor_comm_unique_id() on rank 0, shipped by the host program.
+    void init_communicator(const uint8_t* id128, int n_ranks, int rank) { check(erasor_comm_init(h_, id128, n_ranks, rank)); }
+    std::vector<uint8_t> allgather_static_mask() {
+        if (!map_) throw std::logic_error("ERASOR: load_global_map first");
+        const size_t n = erasor_map_size(map_);
+        check(erasor_allgather_and_keep(h_, erasor_map_keep_device(map_), n));
+        check(erasor_synchronize(h_));
+        std::vector<uint8_t> keep(std::max<size_t>(n, 1));
+        if (erasor_map_get_keep(map_, keep.data(), ERASOR_PTR_HOST) != ERASOR_OK) throw std::runtime_error("ERASOR: erasor_map_get_keep");
+        keep.resize(n);
+        return keep;
+    }
+
     // what the reference exposes as /SCDR/debug/polygons_marker likelihoods (erasor.cpp:439-441,570);
     // index = sector * num_rings + ring
     std::vector<float> get_status() {
@@ -110,7 +195,15 @@ private:
         throw std::runtime_error(msg);
     }
     erasor_params_t params_;
+    int             device_ = 0;
     erasor_handle_t h_ = nullptr;
+    erasor_map_t    map_ = nullptr;
 };
 
 }  // namespace erasor_b200
+
+// The reference's class lives in the global namespace (`class ERASOR`, erasor.h:43).  Define ERASOR_B200_GLOBAL_NAMES before
+// including this header to get that spelling, so that OfflineMapUpdater.cpp's `unique_ptr<ERASOR> erasor_` compiles unchanged.
+#ifdef ERASOR_B200_GLOBAL_NAMES
+using ERASOR = erasor_b200::ERASOR;
+#endif

@@ -208,3 +208,10 @@ private:
 };
 
 }  // namespace erasor_b200
+
+// The reference declares `namespace erasor { class OfflineMapUpdater; }` (OfflineMapUpdater.h:8).  With
+// ERASOR_B200_GLOBAL_NAMES defined, the same qualified name resolves to this class, so that main()-level code written
+// against the reference (`erasor::OfflineMapUpdater updater;`) only changes its constructor argument.
+#ifdef ERASOR_B200_GLOBAL_NAMES
+namespace erasor { using OfflineMapUpdater = erasor_b200::OfflineMapUpdater; }
+#endif

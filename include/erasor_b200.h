@@ -107,6 +107,9 @@ int erasor_get_static_estimate(erasor_handle_t h, float* arranged_xyzi, size_t c
 /* replaces ERASOR::get_outliers(map_rejected, curr_rejected) (erasor.cpp:322-327) */
 int erasor_get_outliers(erasor_handle_t h, float* map_rejected_xyzi, size_t cap_map, size_t* n_map_rejected,
                         float* curr_rejected_xyzi, size_t cap_curr, size_t* n_curr_rejected, int ptr_kind);
+/* ERASOR::ground_viz (public member, erasor.h:127): ground points of the flagged bins, the tail of `arranged`.
+ * ground_xyzi may be NULL to query *n_ground. */
+int erasor_get_ground_viz(erasor_handle_t h, float* ground_xyzi, size_t cap, size_t* n_ground, int ptr_kind);
 /* replaces ERASOR::get_max_range() (erasor.cpp:628) */
 double erasor_get_max_range(erasor_handle_t h);
 

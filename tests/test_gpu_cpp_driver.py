@@ -115,3 +115,6 @@ def test_cpp_class_demo(tmp_path, version):
     rej, _ = o.cloud(o.MAP_REJECTED)
     assert f"ERASOR Input: {len(m)} = {len(arr)} + {len(cmp_)} - {len(rej)}" in r.stdout, r.stdout
     assert "batch mode:" in r.stdout
+    gv, _ = o.cloud(o.GROUND_VIZ)
+    assert f"members: ground_viz {len(gv)}, debug_map_rejected {len(rej)}, map_complement {len(cmp_)}" in r.stdout, r.stdout   # erasor.h:127,139-141
+    assert f"node mode: {len(rej)} map points rejected" in r.stdout, r.stdout     # map-resident mode through the C++ class

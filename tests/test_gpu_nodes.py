@@ -224,3 +224,22 @@ def test_two_gpu_exchange_through_the_c_abi(capi, tmp_path):
                         "--master-port", "29617", script], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "exchange ok" in r.stdout
+
+
+def test_class_c_bins_turning_up_late(capi, oracle_mod):
+    """R-GPF's class C (bins beyond 2560 points) is only launched while such bins are being seen; a submission that meets one
+    unannounced gets the class run by erasor_wait.  Batch masks must equal the oracle before, at and after the switch."""
+    from test_gpu_parity import _crafted_bin_frame
+    p = P.preset("seq_05").replace(skip_voxelize=1)
+    rng = np.random.default_rng(5)
+    small = _crafted_bin_frame(rng, 200, "rough")
+    big = _crafted_bin_frame(rng, 3500, "rough")
+    h = capi.Handle(p)
+    o = oracle_mod.Oracle(p)
+    for tag, (m, q) in (("small", small), ("small again (class C now off)", small), ("big (fix-up)", big), ("big (class C launched)", big), ("small", small)):
+        keep = h.process_frames(m, np.array([0, len(m)], dtype=np.uint64), q, np.array([0, len(q)], dtype=np.uint64))
+        o.run(m, q)
+        _, rej = o.cloud(o.MAP_REJECTED)
+        ok = np.ones(len(m), dtype=np.uint8); ok[rej] = 0
+        assert len(rej) > 0 and np.array_equal(keep, ok), tag
+    h.close()
