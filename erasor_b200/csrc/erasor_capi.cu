@@ -115,7 +115,9 @@ struct erasor_ctx {
     DevBuf d_fence;                            // 4 x u64: negzero, empty fits, ambiguous, slow-path points
     DevBuf d_poses;                            // node mode: NodePose per frame
     DevBuf d_pack, d_gather;                   // exchange step: packed keep bits of this rank / of every rank
-    PinnedBuf h_stage, h_pose;
+    PinnedBuf h_stage, h_pose, h_words;        // h_words: small device -> host read-backs of a submission (pinned: an asynchronous copy into
+                                               // pageable memory blocks the launching thread until the whole stream has drained, which
+                                               // serialised overlapped handles)
     std::vector<DevBuf*> all_bufs() {
         return {&d_ring, &d_pos, &d_neg, &d_guard, &d_map_in, &d_qry_in, &d_bin_map, &d_bin_qry, &d_chunks, &d_chunk_range, &d_frame_off, &d_chcnt, &d_zmin,
                 &d_zmax, &d_cnt, &d_dst_start, &d_status, &d_action, &d_flag_slot, &d_nflag, &d_recs, &d_nrecs, &d_queue, &d_bucket, &d_frame_rej,
@@ -161,7 +163,8 @@ struct erasor_ctx {
     int      stage = 0;                        // 0: nothing, 1: inputs set, 2: compared
     uint32_t out_sizes[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // arranged, complement, map_rejected, curr_rejected, ground_viz
     uint32_t complement_start = 0;
-    uint32_t n_recs_host = 0;
+    uint32_t n_recs_host = 0;                  // (cloud mode; the mask modes read back into h_words)
+    volatile uint32_t* words() { return h_words.as<volatile uint32_t>(); }   // [0] flagged-bin records, [1] class-C bins of the submission in flight
 
     uint64_t launches = 0;
     bool     timing = false;
@@ -528,6 +531,8 @@ int erasor_create(const erasor_params_t* params, int device, erasor_handle_t* ou
     if ((e = cudaEventCreateWithFlags(&h->ev_join_b, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&h->ev_join_c, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     const size_t rb = sizeof(double) * h->tables.ring_thr.size(), sb = sizeof(SectorBoundary) * h->tables.sec_pos.size();
+    if ((e = h->h_words.ensure(64)) != cudaSuccess) return fail("cudaMallocHost", e);
+    std::memset(h->h_words.p, 0, 64);
     const size_t gb = sizeof(float) * h->tables.ring_guard.size();
     if ((e = h->d_guard.ensure(gb)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMemcpy(h->d_guard.p, h->tables.ring_guard.data(), gb, cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy", e);
@@ -553,6 +558,7 @@ void erasor_destroy(erasor_handle_t h) {
     if (h->comm) { NcclApi* api = nccl_api(h->err); if (api) api->CommDestroy(h->comm); h->comm = nullptr; }
     for (DevBuf* b : h->all_bufs()) b->release();
     h->h_pose.release();
+    h->h_words.release();
     h->h_stage.release();
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join_a) cudaEventDestroy(h->ev_join_a);
@@ -868,11 +874,11 @@ int submit(erasor_ctx* h, const Submit& S) {
         if ((r = run_compare(h, h->p.version, S.mode, d_keep, nullptr, fold, with_c ? 7 : 3))) return r;
         h->last.with_c = with_c; h->last.host = host; h->last.mode = S.mode; h->last.d_keep = d_keep; h->last.user_keep = S.keep_mask; h->last.n_keep = n_keep;
         h->last.keep_out = S.keep_out; h->last.n_map_global = n_map_global; h->last.fold = fold;
-        CK(cudaMemcpyAsync(&h->class_c_count_host, h->d_queue.as<uint32_t>() + kBucketC0, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_words.as<uint32_t>() + 1, h->d_queue.as<uint32_t>() + kBucketC0, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
         if (host && n_keep) CK(cudaMemcpyAsync(S.keep_mask, d_keep, n_keep, cudaMemcpyDeviceToHost, h->stream));
         if (S.keep_out && n_map_global)
             CK(cudaMemcpyAsync(S.keep_out, h->map->d_keep, n_map_global, host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, h->stream));
-        CK(cudaMemcpyAsync(&h->n_recs_host, h->d_nrecs.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_words.as<uint32_t>(), h->d_nrecs.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
         return ERASOR_OK;
     };
     bool graphable = h->use_graphs && !h->timing;
@@ -1034,6 +1040,8 @@ int erasor_wait(erasor_handle_t h) {
     CK(cudaStreamSynchronize(h->stream));
     if (h->pending) {
         h->pending = false;
+        h->n_recs_host = h->words()[0];
+        h->class_c_count_host = h->words()[1];
         if (h->n_recs_host > h->rec_capacity) { h->err = "internal: flagged-bin records overflowed the work queue"; return ERASOR_E_CAPACITY; }
         h->class_c_state = (int)std::min<uint32_t>(h->class_c_count_host, 0x7FFFFFFFu);
         if (!h->last.with_c && h->class_c_count_host > 0) {
