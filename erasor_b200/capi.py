@@ -32,7 +32,7 @@ EXPORTS = [
     "erasor_comm_unique_id", "erasor_comm_init", "erasor_comm_destroy", "erasor_allgather_and_keep", "erasor_and_keep_masks",
     "erasor_get_kernel_time_ms", "erasor_reset_kernel_times", "erasor_get_rgpf_profile", "erasor_get_srt_profile",
     "erasor_updater_create", "erasor_updater_destroy", "erasor_updater_reset", "erasor_updater_last_error", "erasor_updater_process_node",
-    "erasor_updater_map_size", "erasor_updater_get_cloud", "erasor_updater_save_static_map", "erasor_updater_voxelize",
+    "erasor_updater_map_size", "erasor_updater_get_cloud", "erasor_updater_save_static_map", "erasor_updater_voxelize", "erasor_updater_mapgen_node",
     "erasor_updater_erasor", "erasor_updater_kernel_launch_count",
 ]
 
@@ -128,6 +128,7 @@ def _load():
     L.erasor_updater_get_cloud.argtypes = [c_void_p, c_int, c_void_p, c_size_t, POINTER(c_size_t), c_int]
     L.erasor_updater_save_static_map.argtypes = [c_void_p, c_float, c_void_p, c_size_t, POINTER(c_size_t)]
     L.erasor_updater_voxelize.argtypes = [c_void_p, c_void_p, c_size_t, c_float, c_void_p, c_size_t, POINTER(c_size_t)]
+    L.erasor_updater_mapgen_node.argtypes = [c_void_p, POINTER(c_double), c_void_p, c_size_t, c_int, c_void_p, c_size_t, POINTER(c_size_t)]
     L.erasor_updater_erasor.restype = c_void_p
     L.erasor_updater_erasor.argtypes = [c_void_p]
     L.erasor_updater_kernel_launch_count.restype = c_uint64
@@ -563,6 +564,16 @@ class Updater:
         out = np.empty((max(len(c), 1), 4), dtype=np.float32)
         n = c_size_t(0)
         self._ck(self.L.erasor_updater_voxelize(self.h, c.ctypes.data, len(c), leaf, out.ctypes.data, len(out), ctypes.byref(n)))
+        return out[:n.value].copy()
+
+    def mapgen_node(self, odom7, lidar) -> np.ndarray:
+        """mapgen's accumPointCloud up to cloud_curr, on the device (body cut, lift, pose, 0.2 m voxelisation)."""
+        o = np.ascontiguousarray(odom7, dtype=np.float64)
+        c = _cloud(lidar)
+        out = np.empty((max(len(c), 1), 4), dtype=np.float32)
+        n = c_size_t(0)
+        self._ck(self.L.erasor_updater_mapgen_node(self.h, o.ctypes.data_as(POINTER(c_double)), c.ctypes.data, len(c), PTR_HOST, out.ctypes.data, len(out),
+                                                   ctypes.byref(n)))
         return out[:n.value].copy()
 
     def kernel_launch_count(self) -> int:

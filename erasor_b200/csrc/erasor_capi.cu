@@ -114,6 +114,7 @@ struct erasor_ctx {
     DevBuf d_vox, d_vox_cnt, d_vox_start, d_vox_scratch;
     DevBuf d_fence;                            // 4 x u64: negzero, empty fits, ambiguous, slow-path points
     DevBuf d_poses;                            // node mode: NodePose per frame
+    DevBuf d_list_idx, d_list_cnt;             // node mode: per chunk, the map index of every VoI point (dense, map order) and their number
     DevBuf d_pack, d_gather;                   // exchange step: packed keep bits of this rank / of every rank
     PinnedBuf h_stage, h_pose, h_words;        // h_words: small device -> host read-backs of a submission (pinned: an asynchronous copy into
                                                // pageable memory blocks the launching thread until the whole stream has drained, which
@@ -122,7 +123,7 @@ struct erasor_ctx {
         return {&d_ring, &d_pos, &d_neg, &d_guard, &d_map_in, &d_qry_in, &d_bin_map, &d_bin_qry, &d_chunks, &d_chunk_range, &d_frame_off, &d_chcnt, &d_zmin,
                 &d_zmax, &d_cnt, &d_dst_start, &d_status, &d_action, &d_flag_slot, &d_nflag, &d_recs, &d_nrecs, &d_queue, &d_bucket, &d_frame_rej,
                 &d_map_sorted, &d_map_src, &d_qry_sorted, &d_qry_src, &d_part, &d_scratch, &d_keep, &d_ground, &d_arranged, &d_map_rej, &d_curr_rej,
-                &d_jobs, &d_out_sizes, &d_k5tmp, &d_fence, &d_vox, &d_vox_cnt, &d_vox_start, &d_vox_scratch, &d_frame_rec_base, &d_poses, &d_pack,
+                &d_jobs, &d_out_sizes, &d_k5tmp, &d_fence, &d_vox, &d_vox_cnt, &d_vox_start, &d_vox_scratch, &d_frame_rec_base, &d_poses, &d_list_idx, &d_list_cnt, &d_pack,
                 &d_gather};
     }
 
@@ -322,7 +323,11 @@ int prepare_batch(erasor_ctx* h, const uint64_t* map_off, const uint64_t* qry_of
     CK(h->d_bucket.ensure(sizeof(uint32_t) * (size_t)kNumBuckets * h->rec_capacity));
     CK(h->d_map_src.ensure(sizeof(uint32_t) * std::max<size_t>(NM, 1)));
     CK(h->d_scratch.ensure((size_t)24 * std::max<size_t>(NM, 1) + 64));
-    if (node) CK(h->d_poses.ensure(sizeof(NodePose) * (size_t)F));
+    if (node) {
+        CK(h->d_poses.ensure(sizeof(NodePose) * (size_t)F));
+        CK(h->d_list_idx.ensure(sizeof(uint32_t) * (NM + kIdPad)));
+        CK(h->d_list_cnt.ensure(sizeof(uint32_t) * std::max<size_t>(n_chunks, 1)));
+    }
     if (mode == 0) {
         CK(h->d_qry_sorted.ensure(sizeof(float4) * std::max<size_t>(NQ, 1)));
         CK(h->d_qry_src.ensure(sizeof(uint32_t) * std::max<size_t>(NQ, 1)));
@@ -378,7 +383,8 @@ int run_k1(erasor_ctx* h, int mode) {
         CK(launch_k1(h->stream, h->view, h->cur_map, h->cur_qry, h->d_chunks.as<ChunkDesc>(), (int)(h->n_chunks_map + h->n_chunks_qry),
                      h->d_bin_map.as<uint16_t>(), h->d_bin_qry.as<uint16_t>(), h->d_chcnt.as<uint32_t>(), h->d_zmin.as<uint32_t>(),
                      h->d_zmax.as<uint32_t>(), h->d_cnt.as<uint32_t>(), B, F, h->d_fence.as<unsigned long long>(),
-                     mode == 2 ? h->d_poses.as<NodePose>() : nullptr));
+                     mode == 2 ? h->d_poses.as<NodePose>() : nullptr, mode == 2 ? h->d_list_idx.as<uint32_t>() : nullptr,
+                     mode == 2 ? h->d_list_cnt.as<uint32_t>() : nullptr));
     }
     return ERASOR_OK;
 }
@@ -409,23 +415,26 @@ int run_compare(erasor_ctx* h, int version, int mode, uint8_t* keep_mask, uint8_
         if (mode == 0) {
             if (h->n_chunks_map) h->launches++;
             CK(launch_k2(h->stream, h->d_chunks.as<ChunkDesc>(), 0u, h->n_chunks_map, h->d_bin_map.as<uint16_t>(), h->cur_map, nullptr,
-                         h->d_chcnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>(), nullptr, nullptr, h->d_map_sorted.as<float4>(), h->d_map_src.as<uint32_t>(), B));
+                         h->d_chcnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>(), nullptr, nullptr, h->d_map_sorted.as<float4>(), h->d_map_src.as<uint32_t>(), B,
+                         nullptr, nullptr));
             if (h->n_chunks_qry) h->launches++;
             CK(launch_k2(h->stream, h->d_chunks.as<ChunkDesc>(), h->n_chunks_map, h->n_chunks_qry, h->d_bin_qry.as<uint16_t>(), h->cur_qry, nullptr,
                          h->d_chcnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>() + (size_t)F * (B + 2), nullptr, nullptr, h->d_qry_sorted.as<float4>(),
-                         h->d_qry_src.as<uint32_t>(), B));
+                         h->d_qry_src.as<uint32_t>(), B, nullptr, nullptr));
         } else if (fused) {
             if (h->n_chunks_map) h->launches++;
             CK(launch_k2_srt(h->stream, sp, F, h->d_chunks.as<ChunkDesc>(), h->d_chunk_range.as<uint32_t>(), h->n_chunks_map, h->d_bin_map.as<uint16_t>(),
                              h->cur_map, poses, h->d_chcnt.as<uint32_t>(), h->d_zmin.as<uint32_t>(), h->d_zmax.as<uint32_t>(), h->d_cnt.as<uint32_t>(),
                              h->d_frame_off.as<uint32_t>(), nflag, h->d_recs.as<FlagRec>(), h->d_nrecs.as<uint32_t>(), h->rec_capacity,
-                             h->d_queue.as<uint32_t>(), h->d_bucket.as<uint32_t>(), h->d_map_sorted.as<float4>(), h->d_map_src.as<uint32_t>()));
+                             h->d_queue.as<uint32_t>(), h->d_bucket.as<uint32_t>(), h->d_map_sorted.as<float4>(), h->d_map_src.as<uint32_t>(),
+                             poses ? h->d_list_idx.as<uint32_t>() : nullptr, poses ? h->d_list_cnt.as<uint32_t>() : nullptr));
         } else {
             // mask modes, unfused (ERASOR_B200_UNFUSED_SRT=1): the same stable scatter, restricted to the flagged bins (K3's dense slots)
             if (h->n_chunks_map) h->launches++;
             CK(launch_k2(h->stream, h->d_chunks.as<ChunkDesc>(), 0u, h->n_chunks_map, h->d_bin_map.as<uint16_t>(), h->cur_map, poses,
                          h->d_chcnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>(), h->d_flag_slot.as<uint32_t>(), nflag,
-                         h->d_map_sorted.as<float4>(), h->d_map_src.as<uint32_t>(), B));
+                         h->d_map_sorted.as<float4>(), h->d_map_src.as<uint32_t>(), B,
+                         poses ? h->d_list_idx.as<uint32_t>() : nullptr, poses ? h->d_list_cnt.as<uint32_t>() : nullptr));
         }
     }
     {

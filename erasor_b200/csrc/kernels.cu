@@ -157,7 +157,8 @@ __global__ void __launch_bounds__(THREADS)
 k1_rpod_bin(BinTablesView T, const float4* __restrict__ map_pts, const float4* __restrict__ qry_pts,
             const ChunkDesc* __restrict__ chunks, uint16_t* __restrict__ bin_map, uint16_t* __restrict__ bin_qry,
             uint32_t* __restrict__ ch_cnt, uint32_t* __restrict__ zmin, uint32_t* __restrict__ zmax, uint32_t* __restrict__ cnt_tab,
-            int B, int F, unsigned long long* __restrict__ fence, const NodePose* __restrict__ poses) {
+            int B, int F, unsigned long long* __restrict__ fence, const NodePose* __restrict__ poses,
+            uint32_t* __restrict__ list_idx, uint32_t* __restrict__ list_cnt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2*   s_ring = reinterpret_cast<float2*>(smem_raw);               // {up, dn} guard thresholds of r^2 per ring boundary
     uint32_t* s_cnt  = reinterpret_cast<uint32_t*>(s_ring + ((T.R + 2) & ~1));
@@ -183,6 +184,70 @@ k1_rpod_bin(BinTablesView T, const float4* __restrict__ map_pts, const float4* _
     const float  smax_lo = T.smax_lo, smax_hi = T.smax_hi;
     const int    R = T.R, S = T.S;
 
+    if (node_map) {
+        // ---- node mode, map cloud: fetch_VoI fused in.  Tiles of 1024 map points:
+        //   phase 1  coalesced load + radius test, then a CTA-wide ORDERED compaction of the points inside the VoI into shared memory
+        //            (ballot ranks inside a warp, a 32-counter scan across (item, warp));
+        //   phase 2  the dense survivors get the expensive part -- origin -> body transform, polar bin, table update -- on full
+        //            warps (in map order a third of the lanes of a mixed row lie outside the radius, ncu r02), and leave a dense
+        //            (bin id, map index) list per chunk, still in map order, which is all K2 has to walk afterwards.
+        constexpr int TILE = 1024, ITEMS = TILE / THREADS;
+        static_assert(ITEMS * NW == 32, "one warp scans the (item, warp) counters");
+        __shared__ float4   s_stage[NODE ? TILE : 1];
+        __shared__ uint32_t s_wcnt[32];
+        uint16_t* __restrict__ lbin = bin_map + cd.bin_begin;
+        uint32_t* __restrict__ lidx = list_idx + cd.bin_begin;
+        uint32_t emitted = 0;
+        for (uint32_t tile0 = 0; tile0 < cd.len; tile0 += TILE) {
+            float4 p[ITEMS];
+            unsigned bal[ITEMS];
+#pragma unroll
+            for (int u = 0; u < ITEMS; ++u) {
+                const uint32_t i = tile0 + (uint32_t)u * THREADS + tid;
+                const bool ok = i < cd.len;
+                p[u] = ok ? ld_stream_f4(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool in = ok && in_voi_radius(s_pose, p[u].x, p[u].y);
+                bal[u] = __ballot_sync(FULL_MASK, in);
+                if (lane == 0) s_wcnt[u * NW + warp] = __popc(bal[u]);
+            }
+            __syncthreads();
+            uint32_t incl = s_wcnt[lane];
+            const uint32_t mine = incl;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += v; }
+            const uint32_t n_in = __shfl_sync(FULL_MASK, incl, 31);
+            const uint32_t excl = incl - mine;
+#pragma unroll
+            for (int u = 0; u < ITEMS; ++u) {
+                const uint32_t b0 = __shfl_sync(FULL_MASK, excl, u * NW + warp);
+                if ((bal[u] >> lane) & 1u) {
+                    const uint32_t pos = b0 + __popc(bal[u] & ((1u << lane) - 1u));
+                    s_stage[pos] = make_float4(p[u].x, p[u].y, p[u].z, __uint_as_float(tile0 + (uint32_t)u * THREADS + tid));
+                }
+            }
+            __syncthreads();
+            for (uint32_t j0 = warp * 32u; j0 < n_in; j0 += THREADS) {
+                const uint32_t j = j0 + lane;
+                const bool ok = j < n_in;
+                const float4 q = s_stage[ok ? j : 0u];
+                const float4 pp = affine12(s_pose.T, q);
+                int b = bin_fast(pp.x, pp.y, pp.z, z_lo, z_hi, smax_lo, smax_hi, inv_ring, inv_ss, eps_q, R, S, s_ring);
+                if (__any_sync(FULL_MASK, ok && b == -3)) {
+                    if (ok && b == -3) b = bin_exact(T, pp.x, pp.y, pp.z, &fc);   // exact path (rare)
+                }
+                int key = -2;
+                if (ok) {
+                    lbin[emitted + j] = (b < 0) ? kNoBin16 : (uint16_t)b;
+                    lidx[emitted + j] = cd.begin + __float_as_uint(q.w);          // index in the resident map
+                    key = (b < 0) ? B : b;
+                }
+                k1_aggregate(key, float_to_ordered(pp.z), lane, s_cnt, s_mn, s_mx, B);
+            }
+            emitted += n_in;
+            __syncthreads();                                   // the staging area and the counters are reused
+        }
+        if (tid == 0) list_cnt[blockIdx.x] = emitted;
+    } else
     for (uint32_t base = warp * (32u * UNROLL); base < cd.len; base += NW * (32u * UNROLL)) {
         float4 p[UNROLL];
         const bool full = base + 32u * UNROLL <= cd.len;          // warp-uniform
@@ -195,26 +260,15 @@ k1_rpod_bin(BinTablesView T, const float4* __restrict__ map_pts, const float4* _
         for (int u = 0; u < UNROLL; ++u) {
             const uint32_t i = base + u * 32u + lane;
             const bool ok = full || i < cd.len;
-            bool inside = true;                                  // inside the frame's VoI (always, outside node mode)
-            float4 pp = p[u];
-            if (node_map) {
-                inside = in_voi_radius(s_pose, pp.x, pp.y);
-                // the map is scanned in its own order, so whole warps fall outside the node's radius: they only clear their bin ids
-                if (!__any_sync(FULL_MASK, ok && inside)) {
-                    if (ok) dst[i] = kNoBin16;
-                    continue;
-                }
-                pp = affine12(s_pose.T, pp);
-            }
+            const float4 pp = p[u];
             int b = bin_fast(pp.x, pp.y, pp.z, z_lo, z_hi, smax_lo, smax_hi, inv_ring, inv_ss, eps_q, R, S, s_ring);
-            if (NODE && !inside) b = -1;
             if (__any_sync(FULL_MASK, ok && b == -3)) {
                 if (ok && b == -3) b = bin_exact(T, pp.x, pp.y, pp.z, &fc);   // exact path (rare)
             }
             int key = -2;
             if (ok) {
                 dst[i] = (b < 0) ? kNoBin16 : (uint16_t)b;
-                if (inside) key = (b < 0) ? B : b;
+                key = (b < 0) ? B : b;
             }
             k1_aggregate(key, float_to_ordered(pp.z), lane, s_cnt, s_mn, s_mx, B);
         }
@@ -250,7 +304,8 @@ size_t k1_smem_bytes(int R, int B) {
 
 cudaError_t launch_k1(cudaStream_t st, const BinTablesView& T, const float4* map_pts, const float4* qry_pts,
                       const ChunkDesc* chunks, int n_chunks, uint16_t* bin_map, uint16_t* bin_qry, uint32_t* ch_cnt,
-                      uint32_t* zmin, uint32_t* zmax, uint32_t* cnt_tab, int B, int F, unsigned long long* fence, const NodePose* poses) {
+                      uint32_t* zmin, uint32_t* zmax, uint32_t* cnt_tab, int B, int F, unsigned long long* fence, const NodePose* poses,
+                      uint32_t* list_idx, uint32_t* list_cnt) {
     if (n_chunks == 0) return cudaSuccess;
     constexpr int UNROLL = 4;
     const size_t smem = k1_smem_bytes(T.R, B);
@@ -262,11 +317,11 @@ cudaError_t launch_k1(cudaStream_t st, const BinTablesView& T, const float4* map
         if (poses) {
             auto kern = k1_rpod_bin<THREADS, UNROLL, true, true>;
             if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
-            kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, poses);
+            kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, poses, list_idx, list_cnt);
         } else {
             auto kern = k1_rpod_bin<THREADS, UNROLL, true, false>;
             if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
-            kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, nullptr);
+            kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, nullptr, nullptr, nullptr);
         }
         return cudaGetLastError();
     }
@@ -274,11 +329,11 @@ cudaError_t launch_k1(cudaStream_t st, const BinTablesView& T, const float4* map
     if (poses) {
         auto kern = k1_rpod_bin<THREADS, UNROLL, true, true>;
         if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
-        kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, poses);
+        kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, poses, list_idx, list_cnt);
     } else {
         auto kern = k1_rpod_bin<THREADS, UNROLL, true, false>;
         if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
-        kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, nullptr);
+        kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, nullptr, nullptr, nullptr);
     }
     return cudaGetLastError();
 }
@@ -606,7 +661,7 @@ template <bool NODE>
 __device__ __forceinline__ void k2_scatter_pass(const uint16_t* __restrict__ ids, uint32_t s0, uint32_t s1, const uint16_t* __restrict__ s_slot,
                                                 uint32_t win0, uint32_t ns, uint32_t* __restrict__ mine, int B, int lane,
                                                 const float4* __restrict__ src, const float* __restrict__ s_T, uint32_t out_base, uint32_t local0,
-                                                float4* __restrict__ out_pts, uint32_t* __restrict__ out_src) {
+                                                float4* __restrict__ out_pts, uint32_t* __restrict__ out_src, const uint32_t* __restrict__ lidx) {
     uint32_t cur[8], nxt[8];
     const uint16_t* __restrict__ pb = ids + (size_t)s0 + lane;      // one 64-bit base per block, constant offsets per load
 #pragma unroll
@@ -635,16 +690,22 @@ __device__ __forceinline__ void k2_scatter_pass(const uint16_t* __restrict__ ids
 #pragma unroll
         for (int g = 0; g < 8; g += 4) {
             float4 pv[4];
+            uint32_t si[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {                       // NODE: the chunk's list holds the map index of every entry
+                si[u] = local0 + i0 + (uint32_t)(g + u) * 32u + lane;
+                if (NODE && dst[g + u] != kSkip) si[u] = lidx[i0 + (uint32_t)(g + u) * 32u + lane];
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                if (dst[g + u] != kSkip) pv[u] = src[i0 + (uint32_t)(g + u) * 32u + lane];
+                if (dst[g + u] != kSkip) pv[u] = NODE ? src[si[u]] : src[i0 + (uint32_t)(g + u) * 32u + lane];
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 if (dst[g + u] != kSkip) {
                     const size_t o = (size_t)out_base + dst[g + u];
                     out_pts[o] = NODE ? affine12(s_T, pv[u]) : pv[u];
-                    out_src[o] = local0 + i0 + (uint32_t)(g + u) * 32u + lane;
+                    out_src[o] = si[u];
                 }
             }
         }
@@ -658,12 +719,14 @@ __global__ void __launch_bounds__(W * 32, 4)      // 4 CTAs per SM: the chunking
 k2_scatter_win(const ChunkDesc* __restrict__ chunks, uint32_t chunk_base, const uint16_t* __restrict__ bin_ids,
                const float4* __restrict__ pts, const NodePose* __restrict__ poses, const uint32_t* __restrict__ ch_cnt,
                const uint32_t* __restrict__ dst_start /*[F][B+2] of this cloud*/, const uint32_t* __restrict__ flag_slot /*[F][B]; null: every bin + complement*/,
-               const uint32_t* __restrict__ n_flagged /*[F]*/, float4* __restrict__ out_pts, uint32_t* __restrict__ out_src, int B, uint32_t SW) {
+               const uint32_t* __restrict__ n_flagged /*[F]*/, float4* __restrict__ out_pts, uint32_t* __restrict__ out_src, int B, uint32_t SW,
+               const uint32_t* __restrict__ list_idx, const uint32_t* __restrict__ list_cnt) {
     extern __shared__ uint32_t s_tab[];   // [W][ns] per-warp counters / destinations | [SW] bases | u16 slot of every bin [B+1]
     __shared__ float s_T[12];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t row = chunk_base + blockIdx.x;
-    const ChunkDesc cd = chunks[row];
+    ChunkDesc cd = chunks[row];
+    if (NODE) cd.len = list_cnt[row];                     // K1 left a dense (bin id, map index) list of the chunk's VoI points
     const uint32_t* ds   = dst_start + (size_t)cd.frame * (B + 2);
     const uint32_t* pref = ch_cnt + (size_t)row * (B + 1);
     uint32_t* s_base = s_tab + (size_t)W * SW;
@@ -680,7 +743,8 @@ k2_scatter_win(const ChunkDesc* __restrict__ chunks, uint32_t chunk_base, const 
     const uint32_t s0 = min(cd.len, (uint32_t)warp * sub), s1 = min(cd.len, s0 + sub);
     const uint16_t* ids = bin_ids + cd.bin_begin;
     const uint32_t local0 = cd.begin - cd.frame_begin;
-    const float4* src = pts + cd.begin;
+    const float4* src = NODE ? pts : pts + cd.begin;
+    const uint32_t* lidx = NODE ? list_idx + cd.bin_begin : nullptr;
 
     for (uint32_t win0 = 0; win0 < n_slots; win0 += SW) {
         const uint32_t ns = min(SW, n_slots - win0);          // row stride of this window
@@ -705,7 +769,7 @@ k2_scatter_win(const ChunkDesc* __restrict__ chunks, uint32_t chunk_base, const 
             }
         }
         __syncthreads();
-        k2_scatter_pass<NODE>(ids, s0, s1, s_slot, win0, ns, mine, B, lane, src, s_T, cd.out_base, local0, out_pts, out_src);
+        k2_scatter_pass<NODE>(ids, s0, s1, s_slot, win0, ns, mine, B, lane, src, s_T, cd.out_base, local0, out_pts, out_src, lidx);
     }
 }
 
@@ -723,7 +787,8 @@ k2_srt_scatter(SrtParams P, int F, const ChunkDesc* __restrict__ chunks, const u
                const uint32_t* __restrict__ cnt /*[2][F][B+1]*/, const uint32_t* __restrict__ frame_off /*[2][F+1]*/,
                uint32_t* __restrict__ n_flagged /*[F]*/, FlagRec* __restrict__ recs, uint32_t* __restrict__ n_recs, uint32_t rec_capacity,
                uint32_t* __restrict__ queue, uint32_t* __restrict__ bucket_list,
-               float4* __restrict__ out_pts, uint32_t* __restrict__ out_src, uint32_t SW) {
+               float4* __restrict__ out_pts, uint32_t* __restrict__ out_src, uint32_t SW,
+               const uint32_t* __restrict__ list_idx, const uint32_t* __restrict__ list_cnt) {
     extern __shared__ uint32_t s_tab[];   // [W][ns] rows | [SW] bases | u16 slot of every bin [B+1]
     __shared__ float    s_T[12];
     __shared__ uint32_t s_part[34];
@@ -732,7 +797,8 @@ k2_srt_scatter(SrtParams P, int F, const ChunkDesc* __restrict__ chunks, const u
     const int B = P.B;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t row = blockIdx.x;
-    const ChunkDesc cd = chunks[row];
+    ChunkDesc cd = chunks[row];
+    if (NODE) cd.len = list_cnt[row];                     // K1 left a dense (bin id, map index) list of the chunk's VoI points
     const int f = (int)cd.frame;
     const uint32_t row0 = chunk_range[f];                    // first chunk of the frame's map cloud
     const bool leader = row == row0;
@@ -789,7 +855,8 @@ k2_srt_scatter(SrtParams P, int F, const ChunkDesc* __restrict__ chunks, const u
     const uint32_t s0 = min(cd.len, (uint32_t)warp * sub), s1 = min(cd.len, s0 + sub);
     const uint16_t* ids = bin_ids + cd.bin_begin;
     const uint32_t local0 = cd.begin - cd.frame_begin;
-    const float4* src = pts + cd.begin;
+    const float4* src = NODE ? pts : pts + cd.begin;
+    const uint32_t* lidx = NODE ? list_idx + cd.bin_begin : nullptr;
     const uint32_t fbase = frame_off[f];
     uint32_t win_carry = 0u;                                  // points of the flagged bins of earlier windows
 
@@ -854,7 +921,7 @@ k2_srt_scatter(SrtParams P, int F, const ChunkDesc* __restrict__ chunks, const u
             }
         }
         __syncthreads();
-        k2_scatter_pass<NODE>(ids, s0, s1, s_slot, win0, ns, mine, B, lane, src, s_T, cd.out_base, local0, out_pts, out_src);
+        k2_scatter_pass<NODE>(ids, s0, s1, s_slot, win0, ns, mine, B, lane, src, s_T, cd.out_base, local0, out_pts, out_src, lidx);
         win_carry += win_total;
     }
 }
@@ -874,7 +941,8 @@ static void k2_smem_plan(int B, bool with_complement, uint32_t& SW, size_t& smem
 cudaError_t launch_k2_srt(cudaStream_t st, const SrtParams& P, int F, const ChunkDesc* chunks, const uint32_t* chunk_range, uint32_t n_chunks_map,
                           const uint16_t* bin_ids, const float4* pts, const NodePose* poses, const uint32_t* ch_cnt, const uint32_t* zmin,
                           const uint32_t* zmax, const uint32_t* cnt, const uint32_t* frame_off, uint32_t* n_flagged, FlagRec* recs, uint32_t* n_recs,
-                          uint32_t rec_capacity, uint32_t* queue, uint32_t* bucket_list, float4* out_pts, uint32_t* out_src) {
+                          uint32_t rec_capacity, uint32_t* queue, uint32_t* bucket_list, float4* out_pts, uint32_t* out_src,
+                          const uint32_t* list_idx, const uint32_t* list_cnt) {
     if (n_chunks_map == 0) return cudaSuccess;
     constexpr int W = 8;
     uint32_t SW; size_t smem;
@@ -884,19 +952,20 @@ cudaError_t launch_k2_srt(cudaStream_t st, const SrtParams& P, int F, const Chun
         auto kern = k2_srt_scatter<W, true>;
         if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
         kern<<<n_chunks_map, W * 32, smem, st>>>(P, F, chunks, chunk_range, bin_ids, pts, poses, ch_cnt, zmin, zmax, cnt, frame_off, n_flagged, recs, n_recs,
-                                                 rec_capacity, queue, bucket_list, out_pts, out_src, SW);
+                                                 rec_capacity, queue, bucket_list, out_pts, out_src, SW, list_idx, list_cnt);
     } else {
         auto kern = k2_srt_scatter<W, false>;
         if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
         kern<<<n_chunks_map, W * 32, smem, st>>>(P, F, chunks, chunk_range, bin_ids, pts, nullptr, ch_cnt, zmin, zmax, cnt, frame_off, n_flagged, recs, n_recs,
-                                                 rec_capacity, queue, bucket_list, out_pts, out_src, SW);
+                                                 rec_capacity, queue, bucket_list, out_pts, out_src, SW, list_idx, list_cnt);
     }
     return cudaGetLastError();
 }
 
 cudaError_t launch_k2(cudaStream_t st, const ChunkDesc* chunks, uint32_t chunk_base, uint32_t n_chunks,
                       const uint16_t* bin_ids, const float4* pts, const NodePose* poses, const uint32_t* ch_cnt, const uint32_t* dst_start,
-                      const uint32_t* flag_slot, const uint32_t* n_flagged, float4* out_pts, uint32_t* out_src, int B) {
+                      const uint32_t* flag_slot, const uint32_t* n_flagged, float4* out_pts, uint32_t* out_src, int B,
+                      const uint32_t* list_idx, const uint32_t* list_cnt) {
     if (n_chunks == 0) return cudaSuccess;
     constexpr int W = 8;
     uint32_t SW; size_t smem;
@@ -905,11 +974,11 @@ cudaError_t launch_k2(cudaStream_t st, const ChunkDesc* chunks, uint32_t chunk_b
     if (poses) {
         auto kern = k2_scatter_win<W, true>;
         if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
-        kern<<<n_chunks, W * 32, smem, st>>>(chunks, chunk_base, bin_ids, pts, poses, ch_cnt, dst_start, flag_slot, n_flagged, out_pts, out_src, B, SW);
+        kern<<<n_chunks, W * 32, smem, st>>>(chunks, chunk_base, bin_ids, pts, poses, ch_cnt, dst_start, flag_slot, n_flagged, out_pts, out_src, B, SW, list_idx, list_cnt);
     } else {
         auto kern = k2_scatter_win<W, false>;
         if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
-        kern<<<n_chunks, W * 32, smem, st>>>(chunks, chunk_base, bin_ids, pts, nullptr, ch_cnt, dst_start, flag_slot, n_flagged, out_pts, out_src, B, SW);
+        kern<<<n_chunks, W * 32, smem, st>>>(chunks, chunk_base, bin_ids, pts, nullptr, ch_cnt, dst_start, flag_slot, n_flagged, out_pts, out_src, B, SW, nullptr, nullptr);
     }
     return cudaGetLastError();
 }

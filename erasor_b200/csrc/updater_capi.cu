@@ -325,6 +325,43 @@ int erasor_updater_voxelize(erasor_updater_t u, const float* xyzi, size_t n_in, 
     return ERASOR_OK;
 }
 
+// mapgen's per-node producer on the device (reference src/mapgen/mapgen.hpp:198-239, accumPointCloud up to cloud_curr):
+// drop the points within CAR_BODY_SIZE = 2.7 m of the sensor, lift by 1.73 m, move to the map frame with the node's pose,
+// voxelize_preserving_labels at 0.2 m.  The map bookkeeping around it (concatenation, large-scale parking) stays with the caller.
+int erasor_updater_mapgen_node(erasor_updater_t u, const double* odom7, const float* lidar_xyzi, size_t n_lidar, int ptr_kind,
+                               float* out_xyzi, size_t cap, size_t* n) {
+    if (!u || !odom7 || !n || (n_lidar && !lidar_xyzi)) { if (u) u->err = "null argument"; return ERASOR_E_INVALID; }
+    UCK(cudaSetDevice(u->device));
+    const float4* d_scan = reinterpret_cast<const float4*>(lidar_xyzi);
+    if (ptr_kind != ERASOR_PTR_DEVICE) {
+        UCK(u->scan.ensure(sizeof(float4) * std::max<size_t>(n_lidar, 1)));
+        if (n_lidar) UCK(cudaMemcpyAsync(u->scan.p, lidar_xyzi, sizeof(float4) * n_lidar, cudaMemcpyHostToDevice, u->st));
+        d_scan = u->scan.as<float4>();
+    }
+    const float max_dist_square = (float)std::pow(2.7, 2);                    // `float max_dist_square = pow(CAR_BODY_SIZE, 2)` (:219)
+    PartPred P{PART_NOT_NEAR, 0, 0.0, 0.0, (double)max_dist_square};
+    Mat4 I{};
+    for (int i = 0; i < 4; ++i) I.m[i * 5] = 1.0f;
+    size_t n_keep = 0;
+    int rc = partition(u, P, I, false, d_scan, n_lidar, u->voi, u->outskirts, &n_keep);
+    if (rc) return rc;
+    Mat4 lift = I, pose;
+    lift.m[11] = 1.73f;                                                        // tf_lidar2origin (:209-214)
+    pose_to_mat(odom7, pose);                                                  // :234
+    u->launches += 2;
+    UCK(launch_affine_copy(u->st, lift, true, u->voi.as<float4>(), u->voi.as<float4>(), (uint32_t)n_keep));   // :231-232
+    UCK(launch_affine_copy(u->st, pose, true, u->voi.as<float4>(), u->voi.as<float4>(), (uint32_t)n_keep));   // :236-237
+    size_t k = 0;
+    u->save_version = ~0ull;
+    if ((rc = voxelize(u, u->voi.as<float4>(), n_keep, 0.2f, u->save_out, &k))) return rc;                    // :239 (fixed 0.2)
+    *n = k;
+    if (!out_xyzi) return ERASOR_OK;
+    if (cap < k) { u->err = "output buffer too small"; return ERASOR_E_CAPACITY; }
+    if (k) UCK(cudaMemcpyAsync(out_xyzi, u->save_out.p, sizeof(float4) * k, ptr_kind == ERASOR_PTR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, u->st));
+    UCK(cudaStreamSynchronize(u->st));
+    return ERASOR_OK;
+}
+
 uint64_t erasor_updater_kernel_launch_count(erasor_updater_t u) { return u ? u->launches + erasor_kernel_launch_count(u->er) : 0; }
 
 }  // extern "C"

@@ -43,6 +43,13 @@ __device__ __forceinline__ bool part_pred(const PartPred& P, float4 p) {
         const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
         return d2 < P.limit;
     }
+    if (P.kind == PART_NOT_NEAR) {
+        // mapgen's vehicle-body cut (src/mapgen/mapgen.hpp:218-229): dist_square = pow(pt.x, 2) + pow(pt.y, 2) in double;
+        // points with dist_square < max_dist_square are dropped, everything else (NaN included) is kept
+        const double xd = (double)p.x, yd = (double)p.y;
+        const double d2 = __dadd_rn(__dmul_rn(xd, xd), __dmul_rn(yd, yd));
+        return !(d2 < P.limit);
+    }
     // set_submap: fabs(x - pt.x) < submap_size && fabs(y - pt.y) < submap_size
     const double dx = fabs(__dsub_rn(P.x, (double)p.x)), dy = fabs(__dsub_rn(P.y, (double)p.y));
     return (dx < P.limit) && (dy < P.limit);

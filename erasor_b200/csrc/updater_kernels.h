@@ -9,12 +9,12 @@ namespace erasor {
 
 struct Mat4 { float m[16]; };            // row-major 4x4, like Eigen::Matrix4f(r, c) = m[4 r + c]
 
-enum { PART_RADIUS = 0, PART_SUBMAP = 1 };
+enum { PART_RADIUS = 0, PART_SUBMAP = 1, PART_NOT_NEAR = 2 };
 struct PartPred {
     int    kind;
     int    pad_;
     double x, y;                         // criterion point
-    double limit;                        // PART_RADIUS: max_dist_square; PART_SUBMAP: submap_size
+    double limit;                        // PART_RADIUS: max_dist_square; PART_SUBMAP: submap_size; PART_NOT_NEAR: squared vehicle-body radius
 };
 
 struct VoxGrid {                         // pcl::VoxelGrid state of one filter call, kept on the device

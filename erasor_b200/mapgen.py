@@ -11,7 +11,8 @@ The arithmetic that matters for parity is here in float32 exactly as PCL's trans
 device kernel behind `erasor_updater_voxelize` (`device_voxelizer()`), the same one the updater uses for the query scans and
 `save_static_map` and that tests/test_gpu_updater.py checks bit for bit.  tests/test_mapgen.py runs this module against the
 oracle's C++ restatement of mapgen with the oracle's voxeliser injected.
-Status: the composition with the device voxeliser has not been run on a GPU yet (host logic and arithmetic are CPU-tested).
+With `device_producer()` the whole per-node step (cut, lift, transform, voxelise) runs on the device through
+`erasor_updater_mapgen_node`; tests/test_gpu_mapgen.py holds both device compositions bit-identical to the oracle's mapgen.
 """
 from __future__ import annotations
 
@@ -58,8 +59,9 @@ def transform_point_cloud(cloud: np.ndarray, T: np.ndarray) -> np.ndarray:
 class NaiveMapGenerator:
     """mapgen's accumulate / save cycle.  `voxelize(cloud[n,4] float32, leaf) -> cloud` is voxelize_preserving_labels."""
 
-    def __init__(self, voxelize: Voxelizer, leafsize: float = 0.05, is_large_scale: bool = False):
+    def __init__(self, voxelize: Voxelizer, leafsize: float = 0.05, is_large_scale: bool = False, node_producer=None):
         self.voxelize = voxelize
+        self.node_producer = node_producer              # optional (odom7, lidar) -> cloud_curr: erasor_updater_mapgen_node
         self.leafsize = float(leafsize)                  # /map/voxelsize, main.cpp:83
         self.is_large_scale = bool(is_large_scale)       # /large_scale/is_large_scale, main.cpp:91
         self.cloud_map = np.zeros((0, 4), dtype=np.float32)
@@ -70,6 +72,10 @@ class NaiveMapGenerator:
 
     def accum_point_cloud(self, odom7, lidar: np.ndarray) -> None:
         c = np.ascontiguousarray(lidar, dtype=np.float32).reshape(-1, 4)
+        if self.node_producer is not None:                  # the whole per-node step on the device
+            self.cloud_curr = self.node_producer(odom7, c)
+            self._append_curr()
+            return
         max_dist_square = np.float64(np.float32(CAR_BODY_SIZE ** 2))                           # float threshold (:219)
         dist_square = c[:, 0].astype(np.float64) ** 2 + c[:, 1].astype(np.float64) ** 2        # double distance (:221)
         c = c[~(dist_square < max_dist_square)]
@@ -77,6 +83,9 @@ class NaiveMapGenerator:
         lift[2, 3] = LIDAR_HEIGHT
         world = transform_point_cloud(transform_point_cloud(c, lift), pose_to_matrix(odom7))
         self.cloud_curr = self.voxelize(world, NODE_VOXEL)
+        self._append_curr()
+
+    def _append_curr(self) -> None:
         if self._is_initial:
             self.cloud_map = self.cloud_curr.copy()
             self._is_initial = False
@@ -103,9 +112,19 @@ def device_voxelizer(device: int = 0) -> Voxelizer:
     return lambda cloud, leaf: upd.voxelize(cloud, leaf)
 
 
-def build_map(nodes, leafsize: float = 0.05, is_large_scale: bool = False, voxelize: Optional[Voxelizer] = None):
-    """nodes: iterable of (seq, odom7, cloud) (e.g. erasor_b200.kitti.iter_nodes) -> (original, voxelized) map clouds."""
-    gen = NaiveMapGenerator(voxelize if voxelize is not None else device_voxelizer(), leafsize, is_large_scale)
+def device_producer(device: int = 0):
+    """(voxelize, node_producer) backed by one device updater object: the per-node step and the final voxelisation on the GPU."""
+    from . import capi, params
+    upd = capi.Updater(params.updater_preset("seq_05"), params.preset("seq_05"), np.zeros((1, 4), dtype=np.float32), device=device)
+    return (lambda cloud, leaf: upd.voxelize(cloud, leaf)), (lambda odom7, lidar: upd.mapgen_node(odom7, lidar))
+
+
+def build_map(nodes, leafsize: float = 0.05, is_large_scale: bool = False, voxelize: Optional[Voxelizer] = None, node_producer=None):
+    """nodes: iterable of (seq, odom7, cloud) (e.g. erasor_b200.kitti.iter_nodes) -> (original, voxelized) map clouds.
+    Without an injected voxeliser everything heavy runs on the device (needs a CUDA device)."""
+    if voxelize is None:
+        voxelize, node_producer = device_producer()
+    gen = NaiveMapGenerator(voxelize, leafsize, is_large_scale, node_producer)
     for _, odom, cloud in nodes:
         gen.accum_point_cloud(odom, cloud)
     return gen.save_naive_map()

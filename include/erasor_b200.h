@@ -268,6 +268,10 @@ int  erasor_updater_get_cloud(erasor_updater_t u, int which, float* xyzi, size_t
 int  erasor_updater_save_static_map(erasor_updater_t u, float voxel_size, float* out_xyzi, size_t cap, size_t* n);
 /* erasor_utils::voxelize_preserving_labels on a free-standing host cloud (erasor_utils.cpp:80-114) */
 int  erasor_updater_voxelize(erasor_updater_t u, const float* xyzi, size_t n_in, float leaf, float* out_xyzi, size_t cap, size_t* n);
+/* mapgen's per-node producer on the device (reference src/mapgen/mapgen.hpp:198-239): 2.7 m vehicle-body cut, 1.73 m lift,
+ * pose transform, voxelize_preserving_labels at 0.2 m -> cloud_curr.  out_xyzi needs room for n_lidar points (cap). */
+int  erasor_updater_mapgen_node(erasor_updater_t u, const double* odom7, const float* lidar_xyzi, size_t n_lidar, int ptr_kind,
+                                float* out_xyzi, size_t cap, size_t* n);
 /* the ERASOR handle inside the updater (for the parity taps above) */
 erasor_handle_t erasor_updater_erasor(erasor_updater_t u);
 uint64_t erasor_updater_kernel_launch_count(erasor_updater_t u);

@@ -334,6 +334,12 @@ void ERASOR::estimate_plane_(const Cloud& ground) {            // erasor.cpp:183
 
 static bool point_cmp(PointXYZI a, PointXYZI b) { return a.z < b.z; }   // erasor.cpp:200-202
 
+// "Blast radius" study switches (scripts/blast_radius.py; never set by tests or the bench): alternative legal outcomes of the
+// choices the reference leaves to its libraries / compiler, to measure how far the results can move if a real PCL build
+// differs from the pinned ones.  [0] ties of the z-sort in REVERSE source order (the opposite extreme from the stable
+// order), [1] the classification dot product (erasor.cpp:271) FMA-contracted, [2] 1-NN distance ties to the HIGHEST index.
+int g_study[3] = {0, 0, 0};
+
 void ERASOR::extract_initial_seeds_(const Cloud& p_sorted, Cloud& init_seeds) {   // erasor.cpp:204-231
     init_seeds.clear();
     Cloud  g_seeds_pc;
@@ -359,7 +365,8 @@ void ERASOR::extract_ground(const Cloud& src, Cloud& dst, Cloud& outliers) {    
     if (!outliers.empty()) outliers.clear();
 
     auto src_copy = src;
-    if (p.sort_mode == 0) std::sort(src_copy.begin(), src_copy.end(), point_cmp);
+    if (g_study[0]) { std::reverse(src_copy.begin(), src_copy.end()); std::stable_sort(src_copy.begin(), src_copy.end(), point_cmp); }
+    else if (p.sort_mode == 0) std::sort(src_copy.begin(), src_copy.end(), point_cmp);
     else                  std::stable_sort(src_copy.begin(), src_copy.end(), point_cmp);
     // 1. remove_outliers (erasor.cpp:242-251)
     auto it = src_copy.begin();
@@ -384,7 +391,8 @@ void ERASOR::extract_ground(const Cloud& src, Cloud& dst, Cloud& outliers) {    
         }
         // points(n,3) * normal_ : depth-3 product accumulated in order, no FMA  [3P Eigen GEBP]
         for (size_t r = 0; r < src.size(); r++) {
-            const float result = (src[r].x * normal_[0] + src[r].y * normal_[1]) + src[r].z * normal_[2];
+            const float result = g_study[1] ? std::fmaf(src[r].z, normal_[2], std::fmaf(src[r].y, normal_[1], src[r].x * normal_[0]))
+                                            : (src[r].x * normal_[0] + src[r].y * normal_[1]) + src[r].z * normal_[2];
             if (result < th_dist_d_) {
                 ground_pc_.push_back(src[r]);
             } else {
@@ -708,7 +716,7 @@ void voxelize_preserving_labels(const Cloud& src, Cloud& dst, double leaf_size) 
                         for (unsigned i : itc->second) {
                             const float ddx = pt.x - src[i].x, ddy = pt.y - src[i].y, ddz = pt.z - src[i].z;
                             const float d = (ddx * ddx + ddy * ddy) + ddz * ddz;    // flann::L2_Simple<float>
-                            if (d < best_d || (d == best_d && i < best_i)) { best_d = d; best_i = i; }
+                            if (d < best_d || (d == best_d && (g_study[2] ? (best_i == 0xFFFFFFFFu || i > best_i) : i < best_i))) { best_d = d; best_i = i; }
                         }
                     }
         };

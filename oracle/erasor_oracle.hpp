@@ -192,6 +192,7 @@ void jacobi_svd_3x3_full_u(const float A[9], float U[9], float sv[3]);
 // erasor_utils::voxelize_preserving_labels (erasor_utils.cpp:80-114) = pcl::VoxelGrid + FLANN 1-NN.
 void voxelize_preserving_labels(const Cloud& src, Cloud& dst, double leaf_size);
 // pcl::transformPointCloud(cloud_in, cloud_out, Eigen::Matrix4f) (PCL 1.8 scalar path); T row-major 4x4.
+extern int g_study[3];   // blast-radius study switches (erasor_oracle.cpp); all 0 outside scripts/blast_radius.py
 void transform_point_cloud(const Cloud& in, Cloud& out, const float T[16]);
 // Eigen::Matrix4f::inverse() stand-in (general 4x4, float cofactors).
 void invert_4x4(const float T[16], float Tinv[16]);

@@ -127,6 +127,11 @@ size_t oracle_get_cloud(void* h, int which, float* xyzi, uint32_t* src, size_t c
     return from_cloud(*pick(static_cast<Session*>(h), which), xyzi, src, cap);
 }
 
+// blast-radius study switches (scripts/blast_radius.py only)
+void oracle_set_study(int reverse_sort_ties, int fma_classification, int nn_tie_highest) {
+    g_study[0] = reverse_sort_ties; g_study[1] = fma_classification; g_study[2] = nn_tie_highest;
+}
+
 // ---- unit entry points for the [3P] restatements ----
 unsigned oracle_mean_cov(const float* xyzi, size_t n, int mode, float* cov9, float* mean4) {
     Cloud c; to_cloud(xyzi, n, 0u, c);
