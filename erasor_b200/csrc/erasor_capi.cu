@@ -326,7 +326,7 @@ int prepare_batch(erasor_ctx* h, const uint64_t* map_off, const uint64_t* qry_of
     if (node) {
         CK(h->d_poses.ensure(sizeof(NodePose) * (size_t)F));
         CK(h->d_list_idx.ensure(sizeof(uint32_t) * (NM + kIdPad)));
-        CK(h->d_list_cnt.ensure(sizeof(uint32_t) * std::max<size_t>(n_chunks, 1)));
+        CK(h->d_list_cnt.ensure(sizeof(uint32_t) * kListWarps * std::max<size_t>(n_chunks, 1)));
     }
     if (mode == 0) {
         CK(h->d_qry_sorted.ensure(sizeof(float4) * std::max<size_t>(NQ, 1)));
@@ -416,11 +416,11 @@ int run_compare(erasor_ctx* h, int version, int mode, uint8_t* keep_mask, uint8_
             if (h->n_chunks_map) h->launches++;
             CK(launch_k2(h->stream, h->d_chunks.as<ChunkDesc>(), 0u, h->n_chunks_map, h->d_bin_map.as<uint16_t>(), h->cur_map, nullptr,
                          h->d_chcnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>(), nullptr, nullptr, h->d_map_sorted.as<float4>(), h->d_map_src.as<uint32_t>(), B,
-                         nullptr, nullptr));
+                         nullptr, nullptr, 8));
             if (h->n_chunks_qry) h->launches++;
             CK(launch_k2(h->stream, h->d_chunks.as<ChunkDesc>(), h->n_chunks_map, h->n_chunks_qry, h->d_bin_qry.as<uint16_t>(), h->cur_qry, nullptr,
                          h->d_chcnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>() + (size_t)F * (B + 2), nullptr, nullptr, h->d_qry_sorted.as<float4>(),
-                         h->d_qry_src.as<uint32_t>(), B, nullptr, nullptr));
+                         h->d_qry_src.as<uint32_t>(), B, nullptr, nullptr, 8));
         } else if (fused) {
             if (h->n_chunks_map) h->launches++;
             CK(launch_k2_srt(h->stream, sp, F, h->d_chunks.as<ChunkDesc>(), h->d_chunk_range.as<uint32_t>(), h->n_chunks_map, h->d_bin_map.as<uint16_t>(),
@@ -434,7 +434,8 @@ int run_compare(erasor_ctx* h, int version, int mode, uint8_t* keep_mask, uint8_
             CK(launch_k2(h->stream, h->d_chunks.as<ChunkDesc>(), 0u, h->n_chunks_map, h->d_bin_map.as<uint16_t>(), h->cur_map, poses,
                          h->d_chcnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>(), h->d_flag_slot.as<uint32_t>(), nflag,
                          h->d_map_sorted.as<float4>(), h->d_map_src.as<uint32_t>(), B,
-                         poses ? h->d_list_idx.as<uint32_t>() : nullptr, poses ? h->d_list_cnt.as<uint32_t>() : nullptr));
+                         poses ? h->d_list_idx.as<uint32_t>() : nullptr, poses ? h->d_list_cnt.as<uint32_t>() : nullptr,
+                         k1_big_tables(h->p.num_rings, B) ? 32 : 8));
         }
     }
     {

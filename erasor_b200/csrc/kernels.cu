@@ -185,68 +185,58 @@ k1_rpod_bin(BinTablesView T, const float4* __restrict__ map_pts, const float4* _
     const int    R = T.R, S = T.S;
 
     if (node_map) {
-        // ---- node mode, map cloud: fetch_VoI fused in.  Tiles of 1024 map points:
-        //   phase 1  coalesced load + radius test, then a CTA-wide ORDERED compaction of the points inside the VoI into shared memory
-        //            (ballot ranks inside a warp, a 32-counter scan across (item, warp));
-        //   phase 2  the dense survivors get the expensive part -- origin -> body transform, polar bin, table update -- on full
-        //            warps (in map order a third of the lanes of a mixed row lie outside the radius, ncu r02), and leave a dense
-        //            (bin id, map index) list per chunk, still in map order, which is all K2 has to walk afterwards.
-        constexpr int TILE = 1024, ITEMS = TILE / THREADS;
-        static_assert(ITEMS * NW == 32, "one warp scans the (item, warp) counters");
-        __shared__ float4   s_stage[NODE ? TILE : 1];
-        __shared__ uint32_t s_wcnt[32];
-        uint16_t* __restrict__ lbin = bin_map + cd.bin_begin;
-        uint32_t* __restrict__ lidx = list_idx + cd.bin_begin;
-        uint32_t emitted = 0;
-        for (uint32_t tile0 = 0; tile0 < cd.len; tile0 += TILE) {
-            float4 p[ITEMS];
-            unsigned bal[ITEMS];
-#pragma unroll
-            for (int u = 0; u < ITEMS; ++u) {
-                const uint32_t i = tile0 + (uint32_t)u * THREADS + tid;
-                const bool ok = i < cd.len;
-                p[u] = ok ? ld_stream_f4(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const bool in = ok && in_voi_radius(s_pose, p[u].x, p[u].y);
-                bal[u] = __ballot_sync(FULL_MASK, in);
-                if (lane == 0) s_wcnt[u * NW + warp] = __popc(bal[u]);
+        // ---- node mode, map cloud: fetch_VoI fused in.  Every warp streams its own contiguous sub-range of the chunk (four
+        // float4 loads in flight per lane, no block-wide barrier) and compacts the points inside the VoI, in order, into a
+        // 64-entry ring in shared memory; whenever the ring holds a full row the warp runs the expensive part on it --
+        // origin -> body transform, polar bin, table update -- with all 32 lanes busy (in map order a third of the lanes of a
+        // mixed row lie outside the radius, ncu r02), and appends (bin id, map index) to its dense list.  K2 walks those
+        // lists, warp by warp in the same split, instead of every map point.
+        __shared__ float4 s_ring_q[NODE ? NW * 64 : 1];
+        float4* __restrict__ q = s_ring_q + warp * 64;
+        const uint32_t sub = (((cd.len + NW - 1) / NW) + 31u) & ~31u;
+        const uint32_t w0 = min(cd.len, (uint32_t)warp * sub), w1 = min(cd.len, w0 + sub);
+        uint16_t* __restrict__ lbin = bin_map + cd.bin_begin + w0;
+        uint32_t* __restrict__ lidx = list_idx + cd.bin_begin + w0;
+        uint32_t qh = 0, qt = 0;                       // ring head / tail as running counts (qt - qh < 64)
+        auto dense_row = [&](uint32_t n) {             // the first n (<= 32) entries of the ring
+            const bool ok = (uint32_t)lane < n;
+            const float4 e = q[(qh + lane) & 63u];
+            const float4 pp = affine12(s_pose.T, e);
+            int b = bin_fast(pp.x, pp.y, pp.z, z_lo, z_hi, smax_lo, smax_hi, inv_ring, inv_ss, eps_q, R, S, s_ring);
+            if (__any_sync(FULL_MASK, ok && b == -3)) {
+                if (ok && b == -3) b = bin_exact(T, pp.x, pp.y, pp.z, &fc);   // exact path (rare)
             }
-            __syncthreads();
-            uint32_t incl = s_wcnt[lane];
-            const uint32_t mine = incl;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += v; }
-            const uint32_t n_in = __shfl_sync(FULL_MASK, incl, 31);
-            const uint32_t excl = incl - mine;
-#pragma unroll
-            for (int u = 0; u < ITEMS; ++u) {
-                const uint32_t b0 = __shfl_sync(FULL_MASK, excl, u * NW + warp);
-                if ((bal[u] >> lane) & 1u) {
-                    const uint32_t pos = b0 + __popc(bal[u] & ((1u << lane) - 1u));
-                    s_stage[pos] = make_float4(p[u].x, p[u].y, p[u].z, __uint_as_float(tile0 + (uint32_t)u * THREADS + tid));
-                }
+            int key = -2;
+            if (ok) {
+                lbin[qh + lane] = (b < 0) ? kNoBin16 : (uint16_t)b;
+                lidx[qh + lane] = cd.begin + __float_as_uint(e.w);              // index in the resident map
+                key = (b < 0) ? B : b;
             }
-            __syncthreads();
-            for (uint32_t j0 = warp * 32u; j0 < n_in; j0 += THREADS) {
-                const uint32_t j = j0 + lane;
-                const bool ok = j < n_in;
-                const float4 q = s_stage[ok ? j : 0u];
-                const float4 pp = affine12(s_pose.T, q);
-                int b = bin_fast(pp.x, pp.y, pp.z, z_lo, z_hi, smax_lo, smax_hi, inv_ring, inv_ss, eps_q, R, S, s_ring);
-                if (__any_sync(FULL_MASK, ok && b == -3)) {
-                    if (ok && b == -3) b = bin_exact(T, pp.x, pp.y, pp.z, &fc);   // exact path (rare)
-                }
-                int key = -2;
-                if (ok) {
-                    lbin[emitted + j] = (b < 0) ? kNoBin16 : (uint16_t)b;
-                    lidx[emitted + j] = cd.begin + __float_as_uint(q.w);          // index in the resident map
-                    key = (b < 0) ? B : b;
-                }
-                k1_aggregate(key, float_to_ordered(pp.z), lane, s_cnt, s_mn, s_mx, B);
+            k1_aggregate(key, float_to_ordered(pp.z), lane, s_cnt, s_mn, s_mx, B);
+            qh += n;
+            __syncwarp();                              // the row's ring slots may be overwritten from here on
+        };
+        for (uint32_t base = w0; base < w1; base += 32u * UNROLL) {
+            float4 p[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const uint32_t i = base + u * 32u + lane;
+                p[u] = (i < w1) ? ld_stream_f4(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            emitted += n_in;
-            __syncthreads();                                   // the staging area and the counters are reused
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const uint32_t i = base + u * 32u + lane;
+                const bool in = (i < w1) && in_voi_radius(s_pose, p[u].x, p[u].y);
+                const unsigned bal = __ballot_sync(FULL_MASK, in);
+                if (bal == 0u) continue;                                         // warp-uniform
+                if (in) q[(qt + __popc(bal & ((1u << lane) - 1u))) & 63u] = make_float4(p[u].x, p[u].y, p[u].z, __uint_as_float(i));
+                qt += __popc(bal);
+                __syncwarp();
+                if (qt - qh >= 32u) dense_row(32u);
+            }
         }
-        if (tid == 0) list_cnt[blockIdx.x] = emitted;
+        if (qt != qh) dense_row(qt - qh);
+        if (lane == 0) list_cnt[(size_t)blockIdx.x * kListWarps + warp] = qt;
     } else
     for (uint32_t base = warp * (32u * UNROLL); base < cd.len; base += NW * (32u * UNROLL)) {
         float4 p[UNROLL];
@@ -720,13 +710,12 @@ k2_scatter_win(const ChunkDesc* __restrict__ chunks, uint32_t chunk_base, const 
                const float4* __restrict__ pts, const NodePose* __restrict__ poses, const uint32_t* __restrict__ ch_cnt,
                const uint32_t* __restrict__ dst_start /*[F][B+2] of this cloud*/, const uint32_t* __restrict__ flag_slot /*[F][B]; null: every bin + complement*/,
                const uint32_t* __restrict__ n_flagged /*[F]*/, float4* __restrict__ out_pts, uint32_t* __restrict__ out_src, int B, uint32_t SW,
-               const uint32_t* __restrict__ list_idx, const uint32_t* __restrict__ list_cnt) {
+               const uint32_t* __restrict__ list_idx, const uint32_t* __restrict__ list_cnt, int k1_warps) {
     extern __shared__ uint32_t s_tab[];   // [W][ns] per-warp counters / destinations | [SW] bases | u16 slot of every bin [B+1]
     __shared__ float s_T[12];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t row = chunk_base + blockIdx.x;
-    ChunkDesc cd = chunks[row];
-    if (NODE) cd.len = list_cnt[row];                     // K1 left a dense (bin id, map index) list of the chunk's VoI points
+    const ChunkDesc cd = chunks[row];
     const uint32_t* ds   = dst_start + (size_t)cd.frame * (B + 2);
     const uint32_t* pref = ch_cnt + (size_t)row * (B + 1);
     uint32_t* s_base = s_tab + (size_t)W * SW;
@@ -739,8 +728,15 @@ k2_scatter_win(const ChunkDesc* __restrict__ chunks, uint32_t chunk_base, const 
         for (int b = tid; b <= B; b += W * 32) s_slot[b] = (ds[b] == kSkip) ? (uint16_t)0xFFFFu : (uint16_t)b;   // (the query cloud's complement is not scattered)
     }
     if (NODE && tid < 12) s_T[tid] = poses[cd.frame].T[tid];
-    const uint32_t sub = (((cd.len + W - 1) / W) + 31u) & ~31u;
-    const uint32_t s0 = min(cd.len, (uint32_t)warp * sub), s1 = min(cd.len, s0 + sub);
+    // this warp's part of the chunk: a contiguous sub-range of its points -- or, in node mode, the dense VoI lists that
+    // k1_warps / W of K1's warps left for their sub-ranges (same split, same order)
+    const int      nseg = NODE ? k1_warps / W : 1;
+    const uint32_t sub  = (((cd.len + (NODE ? k1_warps : W) - 1) / (NODE ? k1_warps : W)) + 31u) & ~31u;
+    auto seg_range = [&](int g, uint32_t& s0, uint32_t& s1) {
+        const uint32_t kw = (uint32_t)warp * nseg + g;
+        s0 = min(cd.len, kw * sub);
+        s1 = NODE ? s0 + list_cnt[(size_t)row * kListWarps + kw] : min(cd.len, s0 + sub);
+    };
     const uint16_t* ids = bin_ids + cd.bin_begin;
     const uint32_t local0 = cd.begin - cd.frame_begin;
     const float4* src = NODE ? pts : pts + cd.begin;
@@ -752,7 +748,7 @@ k2_scatter_win(const ChunkDesc* __restrict__ chunks, uint32_t chunk_base, const 
         __syncthreads();                                      // slot table ready / previous window's rows consumed
         for (uint32_t i = tid; i < (uint32_t)W * ns; i += W * 32) s_tab[i] = 0u;
         __syncthreads();
-        k2_count_pass(ids, s0, s1, s_slot, win0, ns, mine, B, lane);
+        for (int g = 0; g < nseg; ++g) { uint32_t s0, s1; seg_range(g, s0, s1); k2_count_pass(ids, s0, s1, s_slot, win0, ns, mine, B, lane); }
         // bases of the window's slots: dst_start + points of the bin in earlier chunks of the frame
         for (int b = tid; b <= B; b += W * 32) {
             const uint32_t sl = (uint32_t)s_slot[b] - win0;
@@ -769,7 +765,10 @@ k2_scatter_win(const ChunkDesc* __restrict__ chunks, uint32_t chunk_base, const 
             }
         }
         __syncthreads();
-        k2_scatter_pass<NODE>(ids, s0, s1, s_slot, win0, ns, mine, B, lane, src, s_T, cd.out_base, local0, out_pts, out_src, lidx);
+        for (int g = 0; g < nseg; ++g) {
+            uint32_t s0, s1; seg_range(g, s0, s1);
+            k2_scatter_pass<NODE>(ids, s0, s1, s_slot, win0, ns, mine, B, lane, src, s_T, cd.out_base, local0, out_pts, out_src, lidx);
+        }
     }
 }
 
@@ -788,7 +787,7 @@ k2_srt_scatter(SrtParams P, int F, const ChunkDesc* __restrict__ chunks, const u
                uint32_t* __restrict__ n_flagged /*[F]*/, FlagRec* __restrict__ recs, uint32_t* __restrict__ n_recs, uint32_t rec_capacity,
                uint32_t* __restrict__ queue, uint32_t* __restrict__ bucket_list,
                float4* __restrict__ out_pts, uint32_t* __restrict__ out_src, uint32_t SW,
-               const uint32_t* __restrict__ list_idx, const uint32_t* __restrict__ list_cnt) {
+               const uint32_t* __restrict__ list_idx, const uint32_t* __restrict__ list_cnt, int k1_warps) {
     extern __shared__ uint32_t s_tab[];   // [W][ns] rows | [SW] bases | u16 slot of every bin [B+1]
     __shared__ float    s_T[12];
     __shared__ uint32_t s_part[34];
@@ -797,8 +796,7 @@ k2_srt_scatter(SrtParams P, int F, const ChunkDesc* __restrict__ chunks, const u
     const int B = P.B;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t row = blockIdx.x;
-    ChunkDesc cd = chunks[row];
-    if (NODE) cd.len = list_cnt[row];                     // K1 left a dense (bin id, map index) list of the chunk's VoI points
+    const ChunkDesc cd = chunks[row];
     const int f = (int)cd.frame;
     const uint32_t row0 = chunk_range[f];                    // first chunk of the frame's map cloud
     const bool leader = row == row0;
@@ -851,8 +849,15 @@ k2_srt_scatter(SrtParams P, int F, const ChunkDesc* __restrict__ chunks, const u
     __syncthreads();
     const uint32_t rec_base = leader ? s_bcast[0] : 0u;
 
-    const uint32_t sub = (((cd.len + W - 1) / W) + 31u) & ~31u;
-    const uint32_t s0 = min(cd.len, (uint32_t)warp * sub), s1 = min(cd.len, s0 + sub);
+    // this warp's part of the chunk: a contiguous sub-range of its points -- or, in node mode, the dense VoI lists that
+    // k1_warps / W of K1's warps left for their sub-ranges (same split, same order)
+    const int      nseg = NODE ? k1_warps / W : 1;
+    const uint32_t sub  = (((cd.len + (NODE ? k1_warps : W) - 1) / (NODE ? k1_warps : W)) + 31u) & ~31u;
+    auto seg_range = [&](int g, uint32_t& s0, uint32_t& s1) {
+        const uint32_t kw = (uint32_t)warp * nseg + g;
+        s0 = min(cd.len, kw * sub);
+        s1 = NODE ? s0 + list_cnt[(size_t)row * kListWarps + kw] : min(cd.len, s0 + sub);
+    };
     const uint16_t* ids = bin_ids + cd.bin_begin;
     const uint32_t local0 = cd.begin - cd.frame_begin;
     const float4* src = NODE ? pts : pts + cd.begin;
@@ -909,7 +914,7 @@ k2_srt_scatter(SrtParams P, int F, const ChunkDesc* __restrict__ chunks, const u
         __syncthreads();
         for (uint32_t i = tid; i < (uint32_t)W * ns; i += NT) s_tab[i] = 0u;
         __syncthreads();
-        k2_count_pass(ids, s0, s1, s_slot, win0, ns, mine, B, lane);
+        for (int g = 0; g < nseg; ++g) { uint32_t s0, s1; seg_range(g, s0, s1); k2_count_pass(ids, s0, s1, s_slot, win0, ns, mine, B, lane); }
         __syncthreads();
         for (uint32_t j = tid; j < ns; j += NT) {
             uint32_t run = s_base[j];
@@ -921,7 +926,10 @@ k2_srt_scatter(SrtParams P, int F, const ChunkDesc* __restrict__ chunks, const u
             }
         }
         __syncthreads();
-        k2_scatter_pass<NODE>(ids, s0, s1, s_slot, win0, ns, mine, B, lane, src, s_T, cd.out_base, local0, out_pts, out_src, lidx);
+        for (int g = 0; g < nseg; ++g) {
+            uint32_t s0, s1; seg_range(g, s0, s1);
+            k2_scatter_pass<NODE>(ids, s0, s1, s_slot, win0, ns, mine, B, lane, src, s_T, cd.out_base, local0, out_pts, out_src, lidx);
+        }
         win_carry += win_total;
     }
 }
@@ -945,6 +953,7 @@ cudaError_t launch_k2_srt(cudaStream_t st, const SrtParams& P, int F, const Chun
                           const uint32_t* list_idx, const uint32_t* list_cnt) {
     if (n_chunks_map == 0) return cudaSuccess;
     constexpr int W = 8;
+    const int k1_warps = k1_big_tables(P.R, P.B) ? 32 : 8;       // the split K1 compacted the chunk's VoI points in
     uint32_t SW; size_t smem;
     k2_smem_plan(P.B, false, SW, smem);
     cudaError_t e;
@@ -952,12 +961,12 @@ cudaError_t launch_k2_srt(cudaStream_t st, const SrtParams& P, int F, const Chun
         auto kern = k2_srt_scatter<W, true>;
         if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
         kern<<<n_chunks_map, W * 32, smem, st>>>(P, F, chunks, chunk_range, bin_ids, pts, poses, ch_cnt, zmin, zmax, cnt, frame_off, n_flagged, recs, n_recs,
-                                                 rec_capacity, queue, bucket_list, out_pts, out_src, SW, list_idx, list_cnt);
+                                                 rec_capacity, queue, bucket_list, out_pts, out_src, SW, list_idx, list_cnt, k1_warps);
     } else {
         auto kern = k2_srt_scatter<W, false>;
         if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
         kern<<<n_chunks_map, W * 32, smem, st>>>(P, F, chunks, chunk_range, bin_ids, pts, nullptr, ch_cnt, zmin, zmax, cnt, frame_off, n_flagged, recs, n_recs,
-                                                 rec_capacity, queue, bucket_list, out_pts, out_src, SW, list_idx, list_cnt);
+                                                 rec_capacity, queue, bucket_list, out_pts, out_src, SW, list_idx, list_cnt, k1_warps);
     }
     return cudaGetLastError();
 }
@@ -965,7 +974,7 @@ cudaError_t launch_k2_srt(cudaStream_t st, const SrtParams& P, int F, const Chun
 cudaError_t launch_k2(cudaStream_t st, const ChunkDesc* chunks, uint32_t chunk_base, uint32_t n_chunks,
                       const uint16_t* bin_ids, const float4* pts, const NodePose* poses, const uint32_t* ch_cnt, const uint32_t* dst_start,
                       const uint32_t* flag_slot, const uint32_t* n_flagged, float4* out_pts, uint32_t* out_src, int B,
-                      const uint32_t* list_idx, const uint32_t* list_cnt) {
+                      const uint32_t* list_idx, const uint32_t* list_cnt, int k1_warps) {
     if (n_chunks == 0) return cudaSuccess;
     constexpr int W = 8;
     uint32_t SW; size_t smem;
@@ -974,11 +983,11 @@ cudaError_t launch_k2(cudaStream_t st, const ChunkDesc* chunks, uint32_t chunk_b
     if (poses) {
         auto kern = k2_scatter_win<W, true>;
         if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
-        kern<<<n_chunks, W * 32, smem, st>>>(chunks, chunk_base, bin_ids, pts, poses, ch_cnt, dst_start, flag_slot, n_flagged, out_pts, out_src, B, SW, list_idx, list_cnt);
+        kern<<<n_chunks, W * 32, smem, st>>>(chunks, chunk_base, bin_ids, pts, poses, ch_cnt, dst_start, flag_slot, n_flagged, out_pts, out_src, B, SW, list_idx, list_cnt, k1_warps);
     } else {
         auto kern = k2_scatter_win<W, false>;
         if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
-        kern<<<n_chunks, W * 32, smem, st>>>(chunks, chunk_base, bin_ids, pts, nullptr, ch_cnt, dst_start, flag_slot, n_flagged, out_pts, out_src, B, SW, nullptr, nullptr);
+        kern<<<n_chunks, W * 32, smem, st>>>(chunks, chunk_base, bin_ids, pts, nullptr, ch_cnt, dst_start, flag_slot, n_flagged, out_pts, out_src, B, SW, nullptr, nullptr, W);
     }
     return cudaGetLastError();
 }

@@ -46,7 +46,7 @@ cudaError_t launch_k2_srt(cudaStream_t st, const SrtParams& P, int F, const Chun
 cudaError_t launch_k2(cudaStream_t st, const ChunkDesc* chunks, uint32_t chunk_base, uint32_t n_chunks,
                       const uint16_t* bin_ids, const float4* pts, const NodePose* poses, const uint32_t* ch_cnt, const uint32_t* dst_start,
                       const uint32_t* flag_slot, const uint32_t* n_flagged, float4* out_pts, uint32_t* out_src, int B,
-                      const uint32_t* list_idx, const uint32_t* list_cnt);
+                      const uint32_t* list_idx, const uint32_t* list_cnt, int k1_warps /*warps of the K1 launch that wrote the lists (8 or 32)*/);
 
 int k4_num_launches(bool with_class_c);
 // sorted_pts / sorted_src: K2's output (bins contiguous in source order + source index of every slot); in_pts is unused
