@@ -9,6 +9,7 @@ namespace erasor {
 constexpr uint32_t kSkip      = 0xFFFFFFFFu;   // dst_start value of a bin that is not scattered
 constexpr uint16_t kNoBin16   = 0xFFFFu;       // bin id of a point that failed the z window / range test
 constexpr uint32_t kIdPad     = 1024;          // slack entries behind the bin-id arrays: K2 prefetches ids without bounds checks
+constexpr uint32_t kMapPad    = 256;           // slack points behind the resident map: node-mode K1 streams it without bounds checks
 constexpr int      kListWarps = 32;            // node mode: per-chunk stride of the per-warp VoI list counters (K1 runs 8 or 32 warps)
 constexpr int      kMaxIter   = 8;             // gf_iter upper bound for the tap arrays
 

@@ -142,7 +142,8 @@ struct erasor_ctx {
     struct StepGraph { const void* ptr[8]; size_t fold_n; int kind, mode, f0; uint64_t epoch, alloc; cudaGraphExec_t exec; };
     std::vector<StepGraph> graphs;             // captured mask-mode steps, one per (pointers, geometry)
     bool     use_graphs = true;
-    int      ctas_per_sm = 4;                  // K1 / K2 grid target: one wave of sm_count * ctas_per_sm CTAs (ERASOR_B200_CTAS_PER_SM)
+    int      ctas_per_sm = 3;                  // K1 / K2 grid target: one wave of sm_count * ctas_per_sm CTAs (ERASOR_B200_CTAS_PER_SM); three
+                                               // leave a quarter of the register file to the R-GPF chains of overlapped submissions (r02 matrix)
     bool     fused_srt = true;                 // mask modes: Scan Ratio Test inside the scatter kernel (ERASOR_B200_UNFUSED_SRT=1: separate k3_srt)
     uint64_t graph_kernel_nodes = 0;
     bool     pending = false;                  // an asynchronous submission has not been waited for yet
@@ -1126,7 +1127,8 @@ int erasor_map_create(const float* map_xyzi, size_t n_map, int ptr_kind, int dev
     auto fail = [&](const char* what, cudaError_t ce) { g_create_error = std::string(what) + ": " + cudaGetErrorString(ce); erasor_map_destroy(m); return ERASOR_E_CUDA; };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
     if ((e = cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
-    if ((e = cudaMalloc(&m->d_pts, sizeof(float4) * std::max<size_t>(n_map, 1))) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = cudaMalloc(&m->d_pts, sizeof(float4) * (n_map + kMapPad))) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = cudaMemsetAsync(m->d_pts + n_map, 0, sizeof(float4) * kMapPad, m->st)) != cudaSuccess) return fail("cudaMemset", e);
     if ((e = cudaMalloc(&m->d_keep, std::max<size_t>(n_map, 1))) != cudaSuccess) return fail("cudaMalloc", e);
     if (n_map) {
         const cudaMemcpyKind k = ptr_kind == ERASOR_PTR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;

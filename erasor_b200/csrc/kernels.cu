@@ -153,7 +153,7 @@ __device__ __forceinline__ bool in_voi_radius(const NodePose& P, float x, float 
 // inside the frame's radius (fetch_VoI) and bin their origin -> body transforms.  Points outside the VoI get no bin id
 // and are not counted anywhere (they are the reference's map_outskirts_, which never reach ERASOR).
 template <int THREADS, int UNROLL, bool ROWS, bool NODE>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 1)      // three 8-warp CTAs per SM (<= 85 registers) or one 32-warp CTA
 k1_rpod_bin(BinTablesView T, const float4* __restrict__ map_pts, const float4* __restrict__ qry_pts,
             const ChunkDesc* __restrict__ chunks, uint16_t* __restrict__ bin_map, uint16_t* __restrict__ bin_qry,
             uint32_t* __restrict__ ch_cnt, uint32_t* __restrict__ zmin, uint32_t* __restrict__ zmax, uint32_t* __restrict__ cnt_tab,
@@ -216,13 +216,12 @@ k1_rpod_bin(BinTablesView T, const float4* __restrict__ map_pts, const float4* _
             qh += n;
             __syncwarp();                              // the row's ring slots may be overwritten from here on
         };
-        for (uint32_t base = w0; base < w1; base += 32u * UNROLL) {
+        // (the resident map carries kMapPad points of slack, so the loads need no bounds checks: positions >= w1 are masked below)
+        const float4* __restrict__ pb = src + w0 + lane;
+        for (uint32_t base = w0; base < w1; base += 32u * UNROLL, pb += 32 * UNROLL) {
             float4 p[UNROLL];
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const uint32_t i = base + u * 32u + lane;
-                p[u] = (i < w1) ? ld_stream_f4(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            for (int u = 0; u < UNROLL; ++u) p[u] = ld_stream_f4(pb + u * 32);
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const uint32_t i = base + u * 32u + lane;
@@ -779,7 +778,7 @@ k2_scatter_win(const ChunkDesc* __restrict__ chunks, uint32_t chunk_base, const 
 // The first chunk of each frame is its LEADER: it also publishes n_flagged[frame] and the flagged-bin records + size
 // buckets R-GPF consumes (what k3_srt does in cloud mode).
 template <int W, bool NODE>
-__global__ void __launch_bounds__(W * 32, 4)
+__global__ void __launch_bounds__(W * 32, 3)
 k2_srt_scatter(SrtParams P, int F, const ChunkDesc* __restrict__ chunks, const uint32_t* __restrict__ chunk_range /*[2][F+1]*/,
                const uint16_t* __restrict__ bin_ids, const float4* __restrict__ pts, const NodePose* __restrict__ poses,
                const uint32_t* __restrict__ ch_cnt /*raw per-chunk counts*/, const uint32_t* __restrict__ zmin, const uint32_t* __restrict__ zmax,
