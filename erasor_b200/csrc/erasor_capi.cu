@@ -142,8 +142,7 @@ struct erasor_ctx {
     struct StepGraph { const void* ptr[8]; size_t fold_n; int kind, mode, f0; uint64_t epoch, alloc; cudaGraphExec_t exec; };
     std::vector<StepGraph> graphs;             // captured mask-mode steps, one per (pointers, geometry)
     bool     use_graphs = true;
-    int      ctas_per_sm = 3;                  // K1 / K2 grid target: one wave of sm_count * ctas_per_sm CTAs (ERASOR_B200_CTAS_PER_SM); three
-                                               // leave a quarter of the register file to the R-GPF chains of overlapped submissions (r02 matrix)
+    int      ctas_per_sm = 4;                  // K1 / K2 grid target: one wave of sm_count * ctas_per_sm CTAs (ERASOR_B200_CTAS_PER_SM)
     bool     fused_srt = true;                 // mask modes: Scan Ratio Test inside the scatter kernel (ERASOR_B200_UNFUSED_SRT=1: separate k3_srt)
     uint64_t graph_kernel_nodes = 0;
     bool     pending = false;                  // an asynchronous submission has not been waited for yet

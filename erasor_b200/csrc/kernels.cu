@@ -153,7 +153,7 @@ __device__ __forceinline__ bool in_voi_radius(const NodePose& P, float x, float 
 // inside the frame's radius (fetch_VoI) and bin their origin -> body transforms.  Points outside the VoI get no bin id
 // and are not counted anywhere (they are the reference's map_outskirts_, which never reach ERASOR).
 template <int THREADS, int UNROLL, bool ROWS, bool NODE>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 1)      // three 8-warp CTAs per SM (<= 85 registers) or one 32-warp CTA
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 1)      // four 8-warp CTAs per SM (64 registers) or one 32-warp CTA
 k1_rpod_bin(BinTablesView T, const float4* __restrict__ map_pts, const float4* __restrict__ qry_pts,
             const ChunkDesc* __restrict__ chunks, uint16_t* __restrict__ bin_map, uint16_t* __restrict__ bin_qry,
             uint32_t* __restrict__ ch_cnt, uint32_t* __restrict__ zmin, uint32_t* __restrict__ zmax, uint32_t* __restrict__ cnt_tab,
@@ -217,11 +217,10 @@ k1_rpod_bin(BinTablesView T, const float4* __restrict__ map_pts, const float4* _
             __syncwarp();                              // the row's ring slots may be overwritten from here on
         };
         // (the resident map carries kMapPad points of slack, so the loads need no bounds checks: positions >= w1 are masked below)
-        const float4* __restrict__ pb = src + w0 + lane;
-        for (uint32_t base = w0; base < w1; base += 32u * UNROLL, pb += 32 * UNROLL) {
+        for (uint32_t base = w0; base < w1; base += 32u * UNROLL) {
             float4 p[UNROLL];
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) p[u] = ld_stream_f4(pb + u * 32);
+            for (int u = 0; u < UNROLL; ++u) p[u] = ld_stream_f4(src + (base + u * 32u + lane));
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const uint32_t i = base + u * 32u + lane;
@@ -778,7 +777,7 @@ k2_scatter_win(const ChunkDesc* __restrict__ chunks, uint32_t chunk_base, const 
 // The first chunk of each frame is its LEADER: it also publishes n_flagged[frame] and the flagged-bin records + size
 // buckets R-GPF consumes (what k3_srt does in cloud mode).
 template <int W, bool NODE>
-__global__ void __launch_bounds__(W * 32, 3)
+__global__ void __launch_bounds__(W * 32, 4)
 k2_srt_scatter(SrtParams P, int F, const ChunkDesc* __restrict__ chunks, const uint32_t* __restrict__ chunk_range /*[2][F+1]*/,
                const uint16_t* __restrict__ bin_ids, const float4* __restrict__ pts, const NodePose* __restrict__ poses,
                const uint32_t* __restrict__ ch_cnt /*raw per-chunk counts*/, const uint32_t* __restrict__ zmin, const uint32_t* __restrict__ zmax,
@@ -1530,7 +1529,7 @@ __device__ __forceinline__ void k4_process_bin(const GpfParams& P, FlagRec& rc, 
     float*    Y   = X + n;
     float*    Z   = Y + n;
     uint8_t*  FLG = reinterpret_cast<uint8_t*>(Z + n);
-    constexpr int HT = (G == 32) ? 32 : 128;      // half tile of the covariance accumulation
+    constexpr int HT = (G == 32) ? 32 : (G == 128 ? 96 : 128);      // half tile of the covariance accumulation (CTA groups: the threads beyond warp 0 stage it)
     constexpr int PB = 9 * (HT + 1);
     float*    PRD = prd;                          // two buffers of 9 x (HT + 1) floats, always shared memory
     long long t_prev = clock64();
@@ -1550,7 +1549,7 @@ __device__ __forceinline__ void k4_process_bin(const GpfParams& P, FlagRec& rc, 
             const uint32_t i = i0 + (uint32_t)u * G;
             if (i < n) {
                 X[i] = p[u].x; Y[i] = p[u].y; Z[i] = p[u].z;
-                if (G > 256) ORD[i] = i;
+                if (G > 256 || (G == 128 && n > 2048u)) ORD[i] = i;      // the radix sort permutes an index list
             }
         }
     }
@@ -1565,12 +1564,18 @@ __device__ __forceinline__ void k4_process_bin(const GpfParams& P, FlagRec& rc, 
         if (n <= 128u)      { if (!group_packed_zsort<4, 1>(Z, ORD, n, lst, 256u, sh.warp))  group_bitonic_zsort<4, 1>(Z, ORD, n); }
         else if (n <= 256u) { if (!group_packed_zsort<8, 1>(Z, ORD, n, lst, 256u, sh.warp))  group_bitonic_zsort<8, 1>(Z, ORD, n); }
         else                { if (!group_packed_zsort<16, 1>(Z, ORD, n, lst, 256u, sh.warp)) group_bitonic_zsort<16, 1>(Z, ORD, n); }
-    } else if constexpr (G == 256) {
-        // class B (n <= 4096): eight warps, cross-warp stages through the ORD|TMP area
+    } else if constexpr (G == 128) {
+        // class B (512 < n <= 2560): four warps -- half the registers per bin of the eight-warp form (a bin keeps them for its
+        // whole serial chain, and registers are what limits how many chains of overlapped submissions an SM holds); cross-warp
+        // stages through the ORD|TMP area; the few bins beyond 16 keys per lane take the radix sort
         uint32_t* lst = reinterpret_cast<uint32_t*>(PRD);
-        if (n <= 1024u)      { if (!group_packed_zsort<4, 8>(Z, ORD, n, lst, 1024u, sh.warp))  group_bitonic_zsort<4, 8>(Z, ORD, n); }
-        else if (n <= 2048u) { if (!group_packed_zsort<8, 8>(Z, ORD, n, lst, 1024u, sh.warp))  group_bitonic_zsort<8, 8>(Z, ORD, n); }
-        else                 { if (!group_packed_zsort<16, 8>(Z, ORD, n, lst, 1024u, sh.warp)) group_bitonic_zsort<16, 8>(Z, ORD, n); }
+        if (n <= 512u)       { if (!group_packed_zsort<4, 4>(Z, ORD, n, lst, 1024u, sh.warp))  group_bitonic_zsort<4, 4>(Z, ORD, n); }
+        else if (n <= 1024u) { if (!group_packed_zsort<8, 4>(Z, ORD, n, lst, 1024u, sh.warp))  group_bitonic_zsort<8, 4>(Z, ORD, n); }
+        else if (n <= 2048u) { if (!group_packed_zsort<16, 4>(Z, ORD, n, lst, 1024u, sh.warp)) group_bitonic_zsort<16, 4>(Z, ORD, n); }
+        else {
+            uint32_t* zs = group_radix_sort<G>(ORD, TMP, n, cnt_scratch, sh.warp, 32, [&](uint32_t id) { return z_sort_key(Z[id]); });
+            if (zs != ORD) { TMP = ORD; ORD = zs; }
+        }
     } else {
         uint32_t* zs = group_radix_sort<G>(ORD, TMP, n, cnt_scratch, sh.warp, 32, [&](uint32_t id) { return z_sort_key(Z[id]); });
         if (zs != ORD) { TMP = ORD; ORD = zs; }
@@ -1793,7 +1798,7 @@ __device__ __forceinline__ void k4_process_bin(const GpfParams& P, FlagRec& rc, 
 // G == 32: every warp of the CTA is a group with its own shared-memory slice (slice_bytes).
 // G == THREADS: the CTA is the group; bins above smem_cap_points work in their slice of the global scratch.
 template <int THREADS, int G>
-__global__ void __launch_bounds__(THREADS, (THREADS == 256) ? 3 : 1)
+__global__ void __launch_bounds__(THREADS, (THREADS == 256) ? 3 : (THREADS == 128 ? 6 : 1))
 k4_rgpf(GpfParams P, FlagRec* __restrict__ recs, uint32_t* __restrict__ queue, const uint32_t* __restrict__ bucket_list,
         uint32_t rec_capacity, int bk0, int bk1, int cls, const float4* __restrict__ sorted_pts, uint32_t* __restrict__ sorted_src,
         const float4* __restrict__ in_pts, const uint32_t* __restrict__ frame_off /*map cloud [F+1]*/,
@@ -1803,8 +1808,8 @@ k4_rgpf(GpfParams P, FlagRec* __restrict__ recs, uint32_t* __restrict__ queue, c
         unsigned long long* __restrict__ fence, K4Fold fold) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NG = THREADS / G;
-    constexpr int HT = (G == 32) ? 32 : 128;
-    constexpr int NCNT = (G > 256) ? 8 * G : 1;          // radix counters: only the class-C sort uses them
+    constexpr int HT = (G == 32) ? 32 : (G == 128 ? 96 : 128);
+    constexpr int NCNT = (G >= 128) ? 8 * G : 1;         // radix counters: class C, and class B's bins beyond 2048 points
     __shared__ K4Shared sh[NG];
     __shared__ float    s_prd[NG][2 * 9 * (HT + 1)];
     __shared__ uint32_t s_cnt[NG][NCNT];
@@ -1861,7 +1866,7 @@ static cudaError_t launch_k4_class(cudaStream_t st, const GpfParams& P, FlagRec*
     constexpr uint32_t per_pt = (G == 32) ? 17u : 21u;
     const uint32_t slice = (smem_bytes / NG) & ~15u;
     const uint32_t cap = (slice - 32) / per_pt;
-    if ((G == 32 && cap < kClassAMax) || (G == 256 && cap < kClassBMax)) return cudaErrorInvalidConfiguration;   // A / B have no scratch path
+    if ((G == 32 && cap < kClassAMax) || (G == 128 && cap < kClassBMax)) return cudaErrorInvalidConfiguration;   // A / B have no scratch path
     auto kern = k4_rgpf<THREADS, G>;
     cudaError_t e = ensure_dyn_smem(kern, smem_bytes);
     if (e != cudaSuccess) return e;
@@ -1877,8 +1882,8 @@ cudaError_t launch_k4(cudaStream_t st, cudaStream_t st_b, cudaStream_t st_c, con
                       const uint32_t* frame_off, float4* part_pts, uint8_t* keep_mask, uint8_t* ground_mask, uint32_t* frame_rejected,
                       unsigned char* gscratch, int sm_count, unsigned long long* fence, const K4Fold& fold, int classes) {
     // The three size classes touch disjoint bins, so they run concurrently on three streams (the caller forks / joins).
-    // Shared memory is sized so that one class-A CTA (8 bins) and two class-B CTAs are resident per SM at the same time:
-    //   A  8 x 8.75 KB slices + 18.7 KB products  ~ 90 KB      B  52.6 KB + 9.3 KB products ~ 62 KB each   (A + 2B ~ 214 KB of 227 KB)
+    // Shared memory: A  8 x 8.75 KB slices + 18.7 KB products ~ 90 KB per CTA (8 bins);  B  52.6 KB + 11 KB products / radix counters ~ 64 KB
+    // per CTA (1 bin, 4 warps).  Registers (80 per thread): A 20 K per 8 bins, B 10 K per bin.
     // Class C wants most of an SM: it is issued first so that its CTAs (which exit at once when the class is empty, the
     // usual case for KITTI-sized maps) do not have to wait for shared memory held by A and B.
     static_assert(kClassAMax <= 512 && kClassBMax <= 4096, "sort networks: 16 keys per lane");
@@ -1893,9 +1898,9 @@ cudaError_t launch_k4(cudaStream_t st, cudaStream_t st_b, cudaStream_t st_c, con
         if (e != cudaSuccess) return e;
     }
     if (!(classes & 3)) return cudaSuccess;
-    // class B: 512 < n <= 2560, one 256-thread CTA per bin
-    e = launch_k4_class<256, 256>(st_b, P, recs, queue, bucket_list, rec_capacity, kBucketB0, kBucketA0, 1, 21 * kClassBMax + 64, sorted_pts,
-                                  sorted_src, in_pts, frame_off, part_pts, keep_mask, ground_mask, frame_rejected, gscratch, sm_count * 2, fence, fold);
+    // class B: 512 < n <= 2560, one 128-thread CTA per bin
+    e = launch_k4_class<128, 128>(st_b, P, recs, queue, bucket_list, rec_capacity, kBucketB0, kBucketA0, 1, 21 * kClassBMax + 64, sorted_pts,
+                                  sorted_src, in_pts, frame_off, part_pts, keep_mask, ground_mask, frame_rejected, gscratch, sm_count * 3, fence, fold);
     if (e != cudaSuccess) return e;
     // class A: n <= 512, one warp per bin, 8 warps per CTA
     return launch_k4_class<256, 32>(st, P, recs, queue, bucket_list, rec_capacity, kBucketA0, kNumBuckets, 0, 8 * (17 * kClassAMax + 48), sorted_pts,
