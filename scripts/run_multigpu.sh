@@ -11,7 +11,7 @@ python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127
 echo "bench rc=$?"; tail -3 gpurun_out/bench_n$N.err
 python - <<PY
 import json
-d = json.load(open("gpurun_out/bench_n$N.json"))
+d = json.loads([l for l in open("gpurun_out/bench_n$N.json") if l.startswith("{")][-1])
 print("N=%d value=%.0f e2e=%.0f ms_per_step=%.4f one_lane=%.0f" % (d["n_gpus"], d["value"], d["e2e"]["value"], d["ms_per_step"], d["lanes"]["value_one_lane"]))
 print(json.dumps(d["exchange"])[:600])
 print(json.dumps(d["quality_final_map"]))
