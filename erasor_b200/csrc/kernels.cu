@@ -935,11 +935,12 @@ k2_srt_scatter(SrtParams P, int F, const ChunkDesc* __restrict__ chunks, const u
 static void k2_smem_plan(int B, bool with_complement, uint32_t& SW, size_t& smem) {
     constexpr int W = 8;
     const size_t fixed  = ((sizeof(uint16_t) * ((size_t)B + 2)) + 15) & ~(size_t)15;
-    // one window over all slots while that leaves >= 2 CTAs per SM (<= 100 KB); beyond (40 x 360 bins) a 1536-slot window:
-    // mask mode rarely has more flagged bins per frame than that, cloud mode takes ceil((B + 1) / 1536) passes
+    // one window over all slots while that leaves two CTAs per SM; beyond that (40 x 360 bins) the largest window that does:
+    // mask mode rarely has more flagged bins per frame than it holds, cloud mode takes ceil((B + 1) / window) passes
     const uint32_t n_slots_max = with_complement ? (uint32_t)B + 1u : (uint32_t)B;
     const size_t full = sizeof(uint32_t) * (size_t)(W + 1) * n_slots_max + fixed;
-    const size_t budget = full <= 100 * 1024 ? full : std::min<size_t>(full, fixed + sizeof(uint32_t) * (size_t)(W + 1) * 1536);
+    const size_t two_per_sm = 111 * 1024;                 // two CTAs per SM: (227 KB - static shared memory) / 2
+    const size_t budget = full <= two_per_sm ? full : two_per_sm;      // 40 x 360: 2304-slot windows (config 5 flags ~2060 bins per frame)
     SW   = (uint32_t)std::min<size_t>(std::max<uint32_t>(n_slots_max, 1u), std::max<size_t>(1, (budget - fixed) / (sizeof(uint32_t) * (W + 1))));
     smem = sizeof(uint32_t) * (size_t)(W + 1) * SW + fixed;
 }
@@ -1903,8 +1904,10 @@ cudaError_t launch_k4(cudaStream_t st, cudaStream_t st_b, cudaStream_t st_c, con
                                   sorted_src, in_pts, frame_off, part_pts, keep_mask, ground_mask, frame_rejected, gscratch, sm_count * 3, fence, fold);
     if (e != cudaSuccess) return e;
     // class A: n <= 512, one warp per bin, 8 warps per CTA
+    // (two CTAs per SM fit by shared memory: with tens of thousands of small flagged bins per step -- 40 x 360 bins, 2 M-point map --
+    //  R-GPF is bound by resident chains per SM, and CTAs that find the queue empty exit at once)
     return launch_k4_class<256, 32>(st, P, recs, queue, bucket_list, rec_capacity, kBucketA0, kNumBuckets, 0, 8 * (17 * kClassAMax + 48), sorted_pts,
-                                    sorted_src, in_pts, frame_off, part_pts, keep_mask, ground_mask, frame_rejected, gscratch, sm_count, fence, fold);
+                                    sorted_src, in_pts, frame_off, part_pts, keep_mask, ground_mask, frame_rejected, gscratch, sm_count * 2, fence, fold);
 }
 
 // ============================================================================================
