@@ -17,8 +17,8 @@ value : scans/s, queries already resident in HBM (device pointers), `--lanes` ha
         asynchronous submissions (consecutive batches overlap on the GPU).
 e2e   : scans/s through the same C-ABI call with pinned HOST buffers: poses + queries H2D and the folded keep
         mask of the map D2H inside the timed region, every step.
-roofline : the kernel with the largest CUDA-event time per step (R-GPF today) against the measured HBM peak, plus
-        every kernel's own line (`by_kernel`; K1 is the one that moves the path's bytes).
+roofline : the kernel with the largest CUDA-event time per step against the measured HBM peak, plus every kernel's own
+        line (`by_kernel`; K1 is the one that moves the path's bytes, R-GPF the latency-bound one).
 cpu_baseline : the oracle port (oracle/, restated reference path: fetch_VoI + ERASOR) on one host core, bounded sample.
 --impl reference : the same oracle port over all host cores (independent nodes in a process pool).
 --config NAME : other BASELINE.json configs (dense twin, 50 M-point VoI, 40x360 x 256 k-point scans); their lines are
@@ -521,7 +521,9 @@ def run_ours(args):
         scans = F * world
         value = scans * args.steps / (ms_res * 1e-3)
         # algorithmic bytes: bytes_frame = 16 (N_m + N_q) + N_m + 16 N_F with N_m = the node's VoI; per kernel:
-        kbytes = {"k1_rpod_bin": 16.0 * (NV + NQ),                       # one float4 read per input point of the path (VoI + query)
+        # K1 in node mode is the FUSED fetch_VoI + binning kernel: SURVEY 8d's rule for it is 16 B per map point scanned (16 N_map_total
+        # per frame) instead of 16 N_m; the unfused figure (VoI + query points only) is kept beside it as `frac_voi_bytes`
+        kbytes = {"k1_rpod_bin": 16.0 * (F * NG + NQ),
                   "k2_scatter": 2.0 * 2 * F * NG + 36.0 * n_f,            # bin ids twice + 36 B per scattered point
                   "k3_srt": 36.0 * F * p.num_bins,
                   "k4_rgpf_all_classes": 16.0 * n_f + 4.0 * n_f + float(n_rej.sum())}
@@ -529,6 +531,9 @@ def run_ours(args):
                          "achieved_gbs": round(kbytes[k] / (kernel_ms[k] * 1e-3) / 1e9, 1) if kernel_ms[k] > 0 else 0.0,
                          "frac": round(kbytes[k] / (kernel_ms[k] * 1e-3) / 1e9 / peak, 4) if kernel_ms[k] > 0 else 0.0,
                          "share_of_event_timed_step": round(kernel_ms[k] / (ms_ev / args.steps), 3)} for k in kernel_ms}
+        by_kernel["k1_rpod_bin"]["frac_voi_bytes"] = round(16.0 * (NV + NQ) / (kernel_ms["k1_rpod_bin"] * 1e-3) / 1e9 / peak, 4) if kernel_ms["k1_rpod_bin"] > 0 else 0.0
+        by_kernel["k1_rpod_bin"]["note"] = ("fused fetch_VoI + R-POD: 16 B per map point scanned per frame (SURVEY 8d fused rule) + 16 B per query point; the resident map "
+                                            "(16 N_map bytes) stays in the 126 MB L2 across the frames of a step, so DRAM traffic is far BELOW these bytes and the kernel is issue-bound")
         dom = max(kernel_ms, key=lambda k: kernel_ms[k])
         step_bytes = 16.0 * (NV + NQ) + NV + 16.0 * n_f
         step_ms = ms_res / args.steps
@@ -552,10 +557,12 @@ def run_ours(args):
                          "frac": by_kernel[dom]["frac"], "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": kbytes[dom], "avg_launch_ms": kernel_ms[dom],
                          "launches_timed": int(kt[dom][1]),
-                         "why": "the dominant kernel by CUDA-event time; R-GPF is bound by a serial float dependency chain per bin (exact-order "
-                                "covariance sums + Jacobi SVD, DESIGN.md section 5), not by bytes -- see by_kernel for the one that moves the bytes (K1)",
+                         "why": "the dominant kernel by CUDA-event time (one lane, plain launches); by_kernel lists all of them: K1 moves the path's bytes "
+                                "and is issue-bound, R-GPF is bound by a serial float dependency chain per bin (exact-order covariance sums + Jacobi SVD, "
+                                "DESIGN.md section 5) and runs under the other kernels of overlapped submissions",
                          "hbm_kernel": "k1_rpod_bin", "by_kernel": by_kernel,
-                         "k1_bytes_scanned_per_launch": 16.0 * (F * NG + NQ),
+                         "k1_dram_traffic_per_launch_ncu": 13.4e6 if (args.config == "seq05" and F == FRAMES_PER_PASS) else None,
+                         "k1_dram_traffic_source": "profiles/r02/ncu_nodes_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum of one k1_rpod_bin launch (map L2-resident)",
                          "ms_per_step_with_event_timing": ms_ev / args.steps},
             "pipeline": {"bytes_per_step": step_bytes, "flagged_bin_points_per_step": n_f, "flagged_bins_per_step": int(len(npts_flagged)),
                          "achieved": step_gbs, "unit": "GB/s", "frac_of_hbm_peak": step_gbs / peak,
