@@ -74,7 +74,6 @@ struct Timer {
 struct erasor_map_ctx {
     int          device = 0;
     float4*      d_pts = nullptr;
-    float4*      d_bbox = nullptr;      // (xmin, xmax, ymin, ymax) of every 128-point block, in map order
     uint8_t*     d_keep = nullptr;
     size_t       n = 0;
     cudaStream_t st = nullptr;
@@ -385,7 +384,7 @@ int run_k1(erasor_ctx* h, int mode) {
                      h->d_bin_map.as<uint16_t>(), h->d_bin_qry.as<uint16_t>(), h->d_chcnt.as<uint32_t>(), h->d_zmin.as<uint32_t>(),
                      h->d_zmax.as<uint32_t>(), h->d_cnt.as<uint32_t>(), B, F, h->d_fence.as<unsigned long long>(),
                      mode == 2 ? h->d_poses.as<NodePose>() : nullptr, mode == 2 ? h->d_list_idx.as<uint32_t>() : nullptr,
-                     mode == 2 ? h->d_list_cnt.as<uint32_t>() : nullptr, mode == 2 ? h->map->d_bbox : nullptr));
+                     mode == 2 ? h->d_list_cnt.as<uint32_t>() : nullptr));
     }
     return ERASOR_OK;
 }
@@ -1135,8 +1134,6 @@ int erasor_map_create(const float* map_xyzi, size_t n_map, int ptr_kind, int dev
         if ((e = cudaMemcpyAsync(m->d_pts, map_xyzi, sizeof(float4) * n_map, k, m->st)) != cudaSuccess) return fail("cudaMemcpy", e);
         if ((e = cudaMemsetAsync(m->d_keep, 1, n_map, m->st)) != cudaSuccess) return fail("cudaMemset", e);
     }
-    if ((e = cudaMalloc(&m->d_bbox, sizeof(float4) * ((n_map + 127) / 128 + 2))) != cudaSuccess) return fail("cudaMalloc", e);
-    if ((e = launch_map_block_bbox(m->st, m->d_pts, n_map, m->d_bbox)) != cudaSuccess) return fail("k_map_block_bbox", e);
     if ((e = cudaStreamSynchronize(m->st)) != cudaSuccess) return fail("cudaStreamSynchronize", e);
     *out = m;
     return ERASOR_OK;
@@ -1147,7 +1144,6 @@ void erasor_map_destroy(erasor_map_t m) {
     cudaSetDevice(m->device);
     if (m->st) { cudaStreamSynchronize(m->st); cudaStreamDestroy(m->st); }
     if (m->d_pts) cudaFree(m->d_pts);
-    if (m->d_bbox) cudaFree(m->d_bbox);
     if (m->d_keep) cudaFree(m->d_keep);
     delete m;
 }

@@ -149,9 +149,6 @@ __device__ __forceinline__ bool in_voi_radius(const NodePose& P, float x, float 
     return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < P.limit;
 }
 
-// node mode: the sub-range of a chunk that one K1 warp streams (and K2 later walks the list of): whole 128-point blocks
-__host__ __device__ __forceinline__ uint32_t k1_node_sub(uint32_t len, int nw) { return (((len + nw - 1) / nw) + 127u) & ~127u; }
-
 // NODE: the map cloud is the resident global map in the origin frame; every frame's chunks scan it, keep the points
 // inside the frame's radius (fetch_VoI) and bin their origin -> body transforms.  Points outside the VoI get no bin id
 // and are not counted anywhere (they are the reference's map_outskirts_, which never reach ERASOR).
@@ -161,7 +158,7 @@ k1_rpod_bin(BinTablesView T, const float4* __restrict__ map_pts, const float4* _
             const ChunkDesc* __restrict__ chunks, uint16_t* __restrict__ bin_map, uint16_t* __restrict__ bin_qry,
             uint32_t* __restrict__ ch_cnt, uint32_t* __restrict__ zmin, uint32_t* __restrict__ zmax, uint32_t* __restrict__ cnt_tab,
             int B, int F, unsigned long long* __restrict__ fence, const NodePose* __restrict__ poses,
-            uint32_t* __restrict__ list_idx, uint32_t* __restrict__ list_cnt, const float4* __restrict__ bbox) {
+            uint32_t* __restrict__ list_idx, uint32_t* __restrict__ list_cnt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2*   s_ring = reinterpret_cast<float2*>(smem_raw);               // {up, dn} guard thresholds of r^2 per ring boundary
     uint32_t* s_cnt  = reinterpret_cast<uint32_t*>(s_ring + ((T.R + 2) & ~1));
@@ -196,12 +193,14 @@ k1_rpod_bin(BinTablesView T, const float4* __restrict__ map_pts, const float4* _
         // lists, warp by warp in the same split, instead of every map point.
         __shared__ float4 s_ring_q[NODE ? NW * 64 : 1];
         float4* __restrict__ q = s_ring_q + warp * 64;
-        const uint32_t sub = k1_node_sub(cd.len, NW);
+        const uint32_t sub = (((cd.len + NW - 1) / NW) + 31u) & ~31u;
         const uint32_t w0 = min(cd.len, (uint32_t)warp * sub), w1 = min(cd.len, w0 + sub);
         uint16_t* __restrict__ lbin = bin_map + cd.bin_begin + w0;
         uint32_t* __restrict__ lidx = list_idx + cd.bin_begin + w0;
-        uint32_t qh = 0, qt = 0;                       // ring head / tail as running counts (qt - qh < 64); qh == entries already listed
-        auto dense = [&](const float4 e, const bool ok, const uint32_t at) {     // e = (x, y, z, index in chunk); list position at + lane
+        uint32_t qh = 0, qt = 0;                       // ring head / tail as running counts (qt - qh < 64)
+        auto dense_row = [&](uint32_t n) {             // the first n (<= 32) entries of the ring
+            const bool ok = (uint32_t)lane < n;
+            const float4 e = q[(qh + lane) & 63u];
             const float4 pp = affine12(s_pose.T, e);
             int b = bin_fast(pp.x, pp.y, pp.z, z_lo, z_hi, smax_lo, smax_hi, inv_ring, inv_ss, eps_q, R, S, s_ring);
             if (__any_sync(FULL_MASK, ok && b == -3)) {
@@ -209,43 +208,19 @@ k1_rpod_bin(BinTablesView T, const float4* __restrict__ map_pts, const float4* _
             }
             int key = -2;
             if (ok) {
-                lbin[at + lane] = (b < 0) ? kNoBin16 : (uint16_t)b;
-                lidx[at + lane] = cd.begin + __float_as_uint(e.w);              // index in the resident map
+                lbin[qh + lane] = (b < 0) ? kNoBin16 : (uint16_t)b;
+                lidx[qh + lane] = cd.begin + __float_as_uint(e.w);              // index in the resident map
                 key = (b < 0) ? B : b;
             }
             k1_aggregate(key, float_to_ordered(pp.z), lane, s_cnt, s_mn, s_mx, B);
-        };
-        auto dense_row = [&](uint32_t n) {             // the first n (<= 32) entries of the ring
-            dense(q[(qh + lane) & 63u], (uint32_t)lane < n, qh);
             qh += n;
             __syncwarp();                              // the row's ring slots may be overwritten from here on
         };
         // (the resident map carries kMapPad points of slack, so the loads need no bounds checks: positions >= w1 are masked below)
-        // One iteration = one 128-point block of the map, whose bounding box erasor_map_create tabulated: a block entirely
-        // outside the node's radius is skipped without touching its points, a block entirely inside skips the per-point test
-        // and the ring (its rows are dense as they are); only blocks cut by the circle take the general path.
-        const float pxf = s_pose.pxf, pyf = s_pose.pyf, lim_lo = s_pose.lim_lo, lim_hi = s_pose.lim_hi;
         for (uint32_t base = w0; base < w1; base += 32u * UNROLL) {
-            static_assert(UNROLL == 4, "one iteration per 128-point bounding-box block");
-            const float4 bb = __ldg(bbox + ((cd.begin + base) >> 7));          // xmin, xmax, ymin, ymax
-            const float dxn = fmaxf(fmaxf(bb.x - pxf, pxf - bb.y), 0.0f), dyn = fmaxf(fmaxf(bb.z - pyf, pyf - bb.w), 0.0f);
-            if (fmaf(dyn, dyn, dxn * dxn) > lim_hi) continue;                  // every point of the block fails the exact test too
             float4 p[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) p[u] = ld_stream_f4(src + (base + u * 32u + lane));
-            const float dxm = fmaxf(fabsf(bb.x - pxf), fabsf(bb.y - pxf)), dym = fmaxf(fabsf(bb.z - pyf), fabsf(bb.w - pyf));
-            if (fmaf(dym, dym, dxm * dxm) < lim_lo) {                          // every point of the block passes: rows are dense already
-                if (qt != qh) dense_row(qt - qh);                              // keep map order: the pending partial row goes first
-#pragma unroll
-                for (int u = 0; u < UNROLL; ++u) {
-                    const uint32_t i = base + u * 32u + lane;
-                    const bool ok = i < w1;                                    // a prefix of the lanes (last block of the sub-range)
-                    dense(make_float4(p[u].x, p[u].y, p[u].z, __uint_as_float(i)), ok, qt);
-                    qt += __popc(__ballot_sync(FULL_MASK, ok));
-                }
-                qh = qt;
-                continue;
-            }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const uint32_t i = base + u * 32u + lane;
@@ -318,7 +293,7 @@ size_t k1_smem_bytes(int R, int B) {
 cudaError_t launch_k1(cudaStream_t st, const BinTablesView& T, const float4* map_pts, const float4* qry_pts,
                       const ChunkDesc* chunks, int n_chunks, uint16_t* bin_map, uint16_t* bin_qry, uint32_t* ch_cnt,
                       uint32_t* zmin, uint32_t* zmax, uint32_t* cnt_tab, int B, int F, unsigned long long* fence, const NodePose* poses,
-                      uint32_t* list_idx, uint32_t* list_cnt, const float4* bbox) {
+                      uint32_t* list_idx, uint32_t* list_cnt) {
     if (n_chunks == 0) return cudaSuccess;
     constexpr int UNROLL = 4;
     const size_t smem = k1_smem_bytes(T.R, B);
@@ -330,11 +305,11 @@ cudaError_t launch_k1(cudaStream_t st, const BinTablesView& T, const float4* map
         if (poses) {
             auto kern = k1_rpod_bin<THREADS, UNROLL, true, true>;
             if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
-            kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, poses, list_idx, list_cnt, bbox);
+            kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, poses, list_idx, list_cnt);
         } else {
             auto kern = k1_rpod_bin<THREADS, UNROLL, true, false>;
             if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
-            kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, nullptr, nullptr, nullptr, nullptr);
+            kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, nullptr, nullptr, nullptr);
         }
         return cudaGetLastError();
     }
@@ -342,11 +317,11 @@ cudaError_t launch_k1(cudaStream_t st, const BinTablesView& T, const float4* map
     if (poses) {
         auto kern = k1_rpod_bin<THREADS, UNROLL, true, true>;
         if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
-        kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, poses, list_idx, list_cnt, bbox);
+        kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, poses, list_idx, list_cnt);
     } else {
         auto kern = k1_rpod_bin<THREADS, UNROLL, true, false>;
         if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
-        kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, nullptr, nullptr, nullptr, nullptr);
+        kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, nullptr, nullptr, nullptr);
     }
     return cudaGetLastError();
 }
@@ -754,7 +729,7 @@ k2_scatter_win(const ChunkDesc* __restrict__ chunks, uint32_t chunk_base, const 
     // this warp's part of the chunk: a contiguous sub-range of its points -- or, in node mode, the dense VoI lists that
     // k1_warps / W of K1's warps left for their sub-ranges (same split, same order)
     const int      nseg = NODE ? k1_warps / W : 1;
-    const uint32_t sub  = NODE ? k1_node_sub(cd.len, k1_warps) : ((((cd.len + W - 1) / W) + 31u) & ~31u);
+    const uint32_t sub  = (((cd.len + (NODE ? k1_warps : W) - 1) / (NODE ? k1_warps : W)) + 31u) & ~31u;
     auto seg_range = [&](int g, uint32_t& s0, uint32_t& s1) {
         const uint32_t kw = (uint32_t)warp * nseg + g;
         s0 = min(cd.len, kw * sub);
@@ -875,7 +850,7 @@ k2_srt_scatter(SrtParams P, int F, const ChunkDesc* __restrict__ chunks, const u
     // this warp's part of the chunk: a contiguous sub-range of its points -- or, in node mode, the dense VoI lists that
     // k1_warps / W of K1's warps left for their sub-ranges (same split, same order)
     const int      nseg = NODE ? k1_warps / W : 1;
-    const uint32_t sub  = NODE ? k1_node_sub(cd.len, k1_warps) : ((((cd.len + W - 1) / W) + 31u) & ~31u);
+    const uint32_t sub  = (((cd.len + (NODE ? k1_warps : W) - 1) / (NODE ? k1_warps : W)) + 31u) & ~31u;
     auto seg_range = [&](int g, uint32_t& s0, uint32_t& s1) {
         const uint32_t kw = (uint32_t)warp * nseg + g;
         s0 = min(cd.len, kw * sub);
@@ -2274,38 +2249,6 @@ cudaError_t launch_and_unpack_keep(cudaStream_t st, const uint32_t* gathered, in
     if (n_words == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)std::min<size_t>((n_words + 7) / 8, 148 * 8);
     k_and_unpack_keep<<<blocks, 256, 0, st>>>(gathered, n_ranks, n_words, n, keep);
-    return cudaGetLastError();
-}
-
-// bounding box (xmin, xmax, ymin, ymax) of every 128-point block of the resident map, in map order; a block holding a
-// non-finite x or y gets an infinite box, so that it is never classified wholesale
-__global__ void __launch_bounds__(256) k_map_block_bbox(const float4* __restrict__ pts, size_t n, float4* __restrict__ bbox, size_t n_blocks) {
-    const size_t blk = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (blk >= n_blocks) return;
-    const float inf = __int_as_float(0x7f800000);
-    float xmin = inf, xmax = -inf, ymin = inf, ymax = -inf;
-    bool bad = false;
-    for (int u = 0; u < 4; ++u) {
-        const size_t i = blk * 128 + (size_t)u * 32 + lane;
-        if (i < n) {
-            const float4 p = pts[i];
-            if (!(fabsf(p.x) < inf) || !(fabsf(p.y) < inf)) bad = true;
-            xmin = fminf(xmin, p.x); xmax = fmaxf(xmax, p.x); ymin = fminf(ymin, p.y); ymax = fmaxf(ymax, p.y);
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        xmin = fminf(xmin, __shfl_xor_sync(FULL_MASK, xmin, o)); xmax = fmaxf(xmax, __shfl_xor_sync(FULL_MASK, xmax, o));
-        ymin = fminf(ymin, __shfl_xor_sync(FULL_MASK, ymin, o)); ymax = fmaxf(ymax, __shfl_xor_sync(FULL_MASK, ymax, o));
-    }
-    bad = __any_sync(FULL_MASK, bad);
-    if (lane == 0) bbox[blk] = bad ? make_float4(-inf, inf, -inf, inf) : make_float4(xmin, xmax, ymin, ymax);
-}
-cudaError_t launch_map_block_bbox(cudaStream_t st, const float4* pts, size_t n, float4* bbox) {
-    const size_t n_blocks = (n + 127) / 128;
-    if (n_blocks == 0) return cudaSuccess;
-    k_map_block_bbox<<<(unsigned)((n_blocks * 32 + 255) / 256), 256, 0, st>>>(pts, n, bbox, n_blocks);
     return cudaGetLastError();
 }
 
