@@ -15,7 +15,7 @@ $NVCC $ARCH $CXXF -Xptxas -v -c updater_kernels.cu -o ../_build/updater_kernels.
 $NVCC $ARCH $CXXF -c updater_capi.cu -o ../_build/updater_capi.o
 g++ -O2 -std=c++17 -fPIC -ffp-contract=off -c binning_tables.cpp -o ../_build/binning_tables.o
 $NVCC $ARCH -shared -o ../_lib/liberasor_b200.so ../_build/kernels.o ../_build/erasor_capi.o ../_build/updater_kernels.o ../_build/updater_capi.o ../_build/binning_tables.o -lquadmath -lcudart -ldl
-g++ -O2 -std=c++17 -fPIC -shared -ffp-contract=off -o ../_lib/liberasor_b200_hostcheck.so host_selftest.cpp binning_tables.cpp -lquadmath
+g++ -O2 -std=c++17 -fPIC -shared -ffp-contract=off -I/usr/local/cuda/include -o ../_lib/liberasor_b200_hostcheck.so host_selftest.cpp binning_tables.cpp -lquadmath
 g++ -std=c++17 -O2 -o ../_lib/offline_map_updater_main ../../examples/offline_map_updater_main.cpp -L../_lib -lerasor_b200 -Wl,-rpath,'$ORIGIN' \
     -L/usr/local/cuda/lib64 -Wl,-rpath,/usr/local/cuda/lib64
 echo "built: $(ls ../_lib)"

@@ -6,6 +6,7 @@
 #include <string>
 
 #include "binning_tables.h"
+#include "pose_math.h"
 
 extern "C" {
 
@@ -51,6 +52,27 @@ int erasor_hostcheck_tables(const erasor_params_t* p, double* ring_thr, double* 
     if (erasor::build_bin_tables(*p, T, err) != 0) return -1;
     std::memcpy(ring_thr, T.ring_thr.data(), sizeof(double) * (T.R + 1));
     *s_max = T.s_max; *z_lo = T.z_lo; *z_hi = T.z_hi; *sec_of_pi = T.sec_of_pi;
+    return 0;
+}
+
+// what erasor_process_nodes hands the device for one node (pose_math.h): criterion point, squared radius, origin -> body rows and the
+// float guard band of the radius pre-test
+int erasor_hostcheck_node_pose(const double* odom7, double voi_max_range, double* px_py_limit, float* T12, float* guards4) {
+    erasor::NodePose np;
+    erasor::node_pose_of(odom7, voi_max_range, np);
+    px_py_limit[0] = np.px; px_py_limit[1] = np.py; px_py_limit[2] = np.limit;
+    for (int i = 0; i < 12; ++i) T12[i] = np.T[i];
+    guards4[0] = np.pxf; guards4[1] = np.pyf; guards4[2] = np.lim_lo; guards4[3] = np.lim_hi;
+    return 0;
+}
+
+// the float guard bands of the device's fast path (binning_tables.cpp): {up_k, dn_k} per ring threshold and around s_max
+int erasor_hostcheck_guards(const erasor_params_t* p, float* ring_guard, float* smax_lo_hi) {
+    erasor::HostBinTables T;
+    std::string err;
+    if (erasor::build_bin_tables(*p, T, err) != 0) return -1;
+    std::memcpy(ring_guard, T.ring_guard.data(), sizeof(float) * T.ring_guard.size());
+    smax_lo_hi[0] = T.smax_lo; smax_lo_hi[1] = T.smax_hi;
     return 0;
 }
 }

@@ -60,6 +60,60 @@ def test_threshold_tables_are_tight(oracle_mod):
     assert sop.value == min(int(np.arctan2(0.0, -1.0) / (2 * 3.1415926535 / p.num_sectors)), p.num_sectors - 1)
 
 
+@pytest.mark.parametrize("name", ["seq_05", "seq_00", "synthetic_40x360"])
+def test_float_guard_bands_never_contradict_the_exact_thresholds(name):
+    """K1's fast path decides ring and range from sf = float(x^2 + y^2) against thresholds widened by the float error (binning_tables.cpp).
+    On points packed around every ring boundary and around max_range: whenever the float test is sure, the exact double test agrees."""
+    p = P.preset(name)
+    L = ctypes.CDLL(HOSTCHECK)
+    pc = p.to_c()
+    R = p.num_rings
+    thr = np.zeros(R + 1); smax = ctypes.c_double(); zlo = ctypes.c_float(); zhi = ctypes.c_float(); sop = ctypes.c_int()
+    assert L.erasor_hostcheck_tables(ctypes.byref(pc), thr.ctypes.data_as(ctypes.c_void_p), ctypes.byref(smax), ctypes.byref(zlo), ctypes.byref(zhi), ctypes.byref(sop)) == 0
+    guard = np.zeros(2 * (R + 1), dtype=np.float32); sm = np.zeros(2, dtype=np.float32)
+    assert L.erasor_hostcheck_guards(ctypes.byref(pc), guard.ctypes.data_as(ctypes.c_void_p), sm.ctypes.data_as(ctypes.c_void_p)) == 0
+    up, dn = guard[0::2], guard[1::2]
+    rng = np.random.default_rng(3)
+    bounds = list(thr[1:R]) + [smax.value]
+    n_sure = 0
+    for T in bounds:
+        r = np.sqrt(T) * (1.0 + rng.uniform(-3e-6, 3e-6, 200000))
+        th = rng.uniform(0, 2 * np.pi, r.size)
+        x, y = (r * np.cos(th)).astype(np.float32), (r * np.sin(th)).astype(np.float32)
+        s = x.astype(np.float64) ** 2 + y.astype(np.float64) ** 2                     # exact: 24-bit mantissas squared, one rounding
+        for sf in ((y * y + x * x).astype(np.float32), np.float32(1) * (x * x + y * y)):   # two float evaluation orders (fma differs by < 1 ulp more)
+            if T == smax.value:
+                assert np.all(s[sf <= sm[0]] <= T) and np.all(s[sf > sm[1]] > T)
+                n_sure += int((sf <= sm[0]).sum() + (sf > sm[1]).sum())
+            else:
+                k = bounds.index(T) + 1
+                assert np.all(s[sf >= up[k]] >= T) and np.all(s[sf < dn[k]] < T)
+                n_sure += int((sf >= up[k]).sum() + (sf < dn[k]).sum())
+    assert n_sure > 0.5 * 2 * 200000 * len(bounds)          # the bands are narrow: most of even these adversarial points are decided in float
+    assert up[0] == -np.inf and dn[R] == np.inf
+
+
+def test_node_pose_matches_the_oracle(oracle_mod):
+    """Host side of erasor_process_nodes (pose_math.h): the origin -> body rows, the criterion point and the squared radius are the
+    oracle's (geoPose2eigen -> float 4x4 -> cofactor inverse, OfflineMapUpdater.cpp:219,246-247,434), bit for bit; the float guard
+    band of the radius pre-test brackets the limit."""
+    L = ctypes.CDLL(HOSTCHECK)
+    rng = np.random.default_rng(9)
+    for _ in range(200):
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        odom = np.concatenate([rng.normal(0, 300, 3), q])
+        rng_m = float(rng.choice([9.5, 20.0, 60.0, 80.0]))
+        ppl = np.zeros(3); T12 = np.zeros(12, dtype=np.float32); g4 = np.zeros(4, dtype=np.float32)
+        assert L.erasor_hostcheck_node_pose(odom.ctypes.data_as(ctypes.c_void_p), ctypes.c_double(rng_m), ppl.ctypes.data_as(ctypes.c_void_p),
+                                            T12.ctypes.data_as(ctypes.c_void_p), g4.ctypes.data_as(ctypes.c_void_p)) == 0
+        T = oracle_mod.pose_to_matrix(odom)
+        Tinv = oracle_mod.invert4(T)
+        assert np.array_equal(T12.view(np.uint32), Tinv[:3].reshape(-1).view(np.uint32))
+        assert ppl[0] == float(T[0, 3]) and ppl[1] == float(T[1, 3]) and ppl[2] == rng_m ** 2
+        assert g4[0] == T[0, 3] and g4[1] == T[1, 3]
+        assert float(g4[2]) < ppl[2] < float(g4[3]) and (float(g4[3]) - float(g4[2])) / ppl[2] < 2.5e-6
+
+
 def test_capi_exports_every_declared_symbol():
     from erasor_b200 import capi
     hdr = open(os.path.join(ROOT, "include", "erasor_b200.h")).read()
