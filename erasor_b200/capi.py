@@ -24,7 +24,7 @@ OK, E_INVALID, E_CUDA, E_STATE, E_CAPACITY, E_UNSUPPORTED = 0, -1, -2, -3, -4, -
 EXPORTS = [
     "erasor_create", "erasor_destroy", "erasor_last_error", "erasor_abi_version", "erasor_stream", "erasor_synchronize",
     "erasor_set_inputs", "erasor_compare", "erasor_get_output_sizes", "erasor_get_static_estimate", "erasor_get_outliers",
-    "erasor_get_max_range", "erasor_get_ground_viz", "erasor_get_bins", "erasor_get_status", "erasor_get_planes", "erasor_get_static_mask",
+    "erasor_get_max_range", "erasor_device_outputs", "erasor_get_ground_viz", "erasor_get_bins", "erasor_get_status", "erasor_get_planes", "erasor_get_static_mask",
     "erasor_get_fence_counts", "erasor_process_frames", "erasor_process_frames_async", "erasor_wait", "erasor_process_frames_fold",
     "erasor_process_frames_fold_async", "erasor_fold_keep_masks", "erasor_reset_keep_mask", "erasor_get_frame_stats", "erasor_kernel_launch_count",
     "erasor_map_create", "erasor_map_destroy", "erasor_map_size", "erasor_map_reset_keep", "erasor_map_get_keep", "erasor_map_keep_device",
@@ -33,7 +33,7 @@ EXPORTS = [
     "erasor_get_kernel_time_ms", "erasor_reset_kernel_times", "erasor_get_rgpf_profile", "erasor_get_srt_profile",
     "erasor_updater_create", "erasor_updater_destroy", "erasor_updater_reset", "erasor_updater_last_error", "erasor_updater_process_node",
     "erasor_updater_map_size", "erasor_updater_get_cloud", "erasor_updater_save_static_map", "erasor_updater_voxelize", "erasor_updater_mapgen_node",
-    "erasor_updater_erasor", "erasor_updater_kernel_launch_count",
+    "erasor_updater_erasor", "erasor_updater_kernel_launch_count", "erasor_updater_get_fused_profile",
 ]
 
 
@@ -133,6 +133,7 @@ def _load():
     L.erasor_updater_erasor.argtypes = [c_void_p]
     L.erasor_updater_kernel_launch_count.restype = c_uint64
     L.erasor_updater_kernel_launch_count.argtypes = [c_void_p]
+    L.erasor_updater_get_fused_profile.argtypes = [c_void_p, c_void_p]
     return L
 
 
@@ -578,3 +579,9 @@ class Updater:
 
     def kernel_launch_count(self) -> int:
         return int(self.L.erasor_updater_kernel_launch_count(self.h))
+
+    def fused_profile(self):
+        """Phase boundaries (ns) of the last fused prologue launch, relative to its start (include/erasor_b200.h)."""
+        t = np.zeros(16, dtype=np.uint64)
+        self._ck(self.L.erasor_updater_get_fused_profile(self.h, t.ctypes.data))
+        return [int(x) - int(t[0]) if x else None for x in t]

@@ -413,14 +413,11 @@ int run_compare(erasor_ctx* h, int version, int mode, uint8_t* keep_mask, uint8_
     if (!only_rgpf) {
         Scope s(h, 2);
         if (mode == 0) {
-            if (h->n_chunks_map) h->launches++;
-            CK(launch_k2(h->stream, h->d_chunks.as<ChunkDesc>(), 0u, h->n_chunks_map, h->d_bin_map.as<uint16_t>(), h->cur_map, nullptr,
-                         h->d_chcnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>(), nullptr, nullptr, h->d_map_sorted.as<float4>(), h->d_map_src.as<uint32_t>(), B,
-                         nullptr, nullptr, 8));
-            if (h->n_chunks_qry) h->launches++;
-            CK(launch_k2(h->stream, h->d_chunks.as<ChunkDesc>(), h->n_chunks_map, h->n_chunks_qry, h->d_bin_qry.as<uint16_t>(), h->cur_qry, nullptr,
-                         h->d_chcnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>() + (size_t)F * (B + 2), nullptr, nullptr, h->d_qry_sorted.as<float4>(),
-                         h->d_qry_src.as<uint32_t>(), B, nullptr, nullptr, 8));
+            if (h->n_chunks_map + h->n_chunks_qry) h->launches++;
+            CK(launch_k2_both(h->stream, h->d_chunks.as<ChunkDesc>(), h->n_chunks_map, h->n_chunks_qry, h->d_chcnt.as<uint32_t>(), B,
+                              h->d_bin_map.as<uint16_t>(), h->cur_map, h->d_dst_start.as<uint32_t>(), h->d_map_sorted.as<float4>(), h->d_map_src.as<uint32_t>(),
+                              h->d_bin_qry.as<uint16_t>(), h->cur_qry, h->d_dst_start.as<uint32_t>() + (size_t)F * (B + 2), h->d_qry_sorted.as<float4>(),
+                              h->d_qry_src.as<uint32_t>()));
         } else if (fused) {
             if (h->n_chunks_map) h->launches++;
             CK(launch_k2_srt(h->stream, sp, F, h->d_chunks.as<ChunkDesc>(), h->d_chunk_range.as<uint32_t>(), h->n_chunks_map, h->d_bin_map.as<uint16_t>(),
@@ -541,8 +538,8 @@ int erasor_create(const erasor_params_t* params, int device, erasor_handle_t* ou
     if ((e = cudaEventCreateWithFlags(&h->ev_join_b, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&h->ev_join_c, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     const size_t rb = sizeof(double) * h->tables.ring_thr.size(), sb = sizeof(SectorBoundary) * h->tables.sec_pos.size();
-    if ((e = h->h_words.ensure(64)) != cudaSuccess) return fail("cudaMallocHost", e);
-    std::memset(h->h_words.p, 0, 64);
+    if ((e = h->h_words.ensure(128)) != cudaSuccess) return fail("cudaMallocHost", e);
+    std::memset(h->h_words.p, 0, 128);
     const size_t gb = sizeof(float) * h->tables.ring_guard.size();
     if ((e = h->d_guard.ensure(gb)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMemcpy(h->d_guard.p, h->tables.ring_guard.data(), gb, cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy", e);
@@ -621,43 +618,63 @@ int erasor_compare(erasor_handle_t h, int version, int frame) {
     CK(h->d_ground.ensure(std::max<size_t>(NM, 1)));
     CK(cudaMemsetAsync(h->d_keep.p, 1, std::max<size_t>(NM, 1), h->stream));
     CK(cudaMemsetAsync(h->d_ground.p, 0, std::max<size_t>(NM, 1), h->stream));
-    int rc = run_compare(h, version, 0, h->d_keep.as<uint8_t>(), h->d_ground.as<uint8_t>(), K4Fold{nullptr, nullptr, 0u, 0u});
+    // R-GPF class C (bins beyond 2560 points, 1024-thread CTAs) is launched only while such bins are being seen; if one turns up
+    // unannounced the class runs after the fact and the output assembly is repeated (same policy as the mask modes, erasor_wait)
+    const bool with_c = h->class_c_state != 0;
+    int rc = run_compare(h, version, 0, h->d_keep.as<uint8_t>(), h->d_ground.as<uint8_t>(), K4Fold{nullptr, nullptr, 0u, 0u}, with_c ? 7 : 3);
     if (rc) return rc;
     const bool vox = (version == 3) && !h->p.skip_voxelize;
     if (vox) {
         CK(h->d_vox.ensure(sizeof(float4) * (NM + NQ + 1)));
         CK(h->d_vox_cnt.ensure(sizeof(uint32_t) * (size_t)B));
         CK(h->d_vox_start.ensure(sizeof(uint32_t) * (size_t)B));
-        CK(h->d_vox_scratch.ensure((size_t)32 * (NM + NQ + 1) + 64));
-        Scope s(h, 4);
-        h->launches++;
-        CK(launch_k4b(h->stream, (float)h->p.map_voxel_size, B, h->d_recs.as<FlagRec>(), h->d_nrecs.as<uint32_t>(), h->rec_capacity,
-                      h->d_cnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>(), h->d_qry_sorted.as<float4>(), h->d_part.as<float4>(),
-                      h->d_vox.as<float4>(), h->d_vox_cnt.as<uint32_t>(), h->d_vox_start.as<uint32_t>(),
-                      h->d_vox_scratch.as<unsigned char>(), h->sm_count * 3));
+        CK(h->d_vox_scratch.ensure((size_t)36 * (NM + NQ + 1) + 64));
     }
-    // output assembly
     CK(h->d_arranged.ensure(sizeof(float4) * (2 * NM + NQ + 1)));
     CK(h->d_map_rej.ensure(sizeof(float4) * std::max<size_t>(NM, 1)));
     CK(h->d_curr_rej.ensure(sizeof(float4) * std::max<size_t>(NQ, 1)));
     CK(h->d_jobs.ensure(sizeof(CopyJob) * 5 * (size_t)B));
     CK(h->d_out_sizes.ensure(sizeof(uint32_t) * 8));
     CK(h->d_k5tmp.ensure(sizeof(uint32_t) * 3 * (size_t)(B + 1)));
-    {
-        Scope s(h, 5);
-        h->launches += 2;
-        CK(launch_k5(h->stream, B, version, h->p.skip_voxelize, h->d_cnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>(), h->d_action.as<uint8_t>(),
-                     h->d_flag_slot.as<uint32_t>(), h->d_recs.as<FlagRec>(), h->d_nrecs.as<uint32_t>(),
-                     vox ? h->d_vox_cnt.as<uint32_t>() : nullptr, vox ? h->d_vox_start.as<uint32_t>() : nullptr,
-                     h->d_map_sorted.as<float4>(), h->d_qry_sorted.as<float4>(), h->d_part.as<float4>(),
-                     vox ? h->d_vox.as<float4>() : nullptr, h->d_arranged.as<float4>(),
-                     h->d_map_rej.as<float4>(), h->d_curr_rej.as<float4>(), h->d_jobs.as<CopyJob>(), h->d_out_sizes.as<uint32_t>(),
-                     h->d_k5tmp.as<uint32_t>(), h->sm_count * 4));
+    // in-bin voxelisation (v3) + output assembly + the sizes the caller needs, read back through pinned memory
+    auto assemble = [&]() -> int {
+        if (vox) {
+            Scope s(h, 4);
+            h->launches++;
+            CK(launch_k4b(h->stream, (float)h->p.map_voxel_size, B, h->d_recs.as<FlagRec>(), h->d_nrecs.as<uint32_t>(), h->rec_capacity,
+                          h->d_cnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>(), h->d_qry_sorted.as<float4>(), h->d_part.as<float4>(),
+                          h->d_vox.as<float4>(), h->d_vox_cnt.as<uint32_t>(), h->d_vox_start.as<uint32_t>(),
+                          h->d_vox_scratch.as<unsigned char>(), h->sm_count));
+        }
+        {
+            Scope s(h, 5);
+            h->launches += 2;
+            CK(launch_k5(h->stream, B, version, h->p.skip_voxelize, h->d_cnt.as<uint32_t>(), h->d_dst_start.as<uint32_t>(), h->d_action.as<uint8_t>(),
+                         h->d_flag_slot.as<uint32_t>(), h->d_recs.as<FlagRec>(), h->d_nrecs.as<uint32_t>(),
+                         vox ? h->d_vox_cnt.as<uint32_t>() : nullptr, vox ? h->d_vox_start.as<uint32_t>() : nullptr,
+                         h->d_map_sorted.as<float4>(), h->d_qry_sorted.as<float4>(), h->d_part.as<float4>(),
+                         vox ? h->d_vox.as<float4>() : nullptr, h->d_arranged.as<float4>(),
+                         h->d_map_rej.as<float4>(), h->d_curr_rej.as<float4>(), h->d_jobs.as<CopyJob>(), h->d_out_sizes.as<uint32_t>(),
+                         h->d_k5tmp.as<uint32_t>(), h->sm_count * 4));
+        }
+        uint32_t* w = h->h_words.as<uint32_t>();
+        CK(cudaMemcpyAsync(w + 4, h->d_out_sizes.p, sizeof(uint32_t) * 5, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(w + 9, h->d_dst_start.as<uint32_t>() + B, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(w + 10, h->d_nrecs.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(w + 11, h->d_queue.as<uint32_t>() + kBucketC0, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return ERASOR_OK;
+    };
+    if ((rc = assemble())) return rc;
+    const uint32_t n_class_c = h->words()[11];
+    if (!with_c && n_class_c > 0) {
+        if ((rc = run_compare(h, version, 0, h->d_keep.as<uint8_t>(), h->d_ground.as<uint8_t>(), K4Fold{nullptr, nullptr, 0u, 0u}, 4, true))) return rc;
+        if ((rc = assemble())) return rc;
     }
-    CK(cudaMemcpyAsync(h->out_sizes, h->d_out_sizes.p, sizeof(uint32_t) * 5, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(&h->complement_start, h->d_dst_start.as<uint32_t>() + B, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(&h->n_recs_host, h->d_nrecs.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    h->class_c_state = (int)std::min<uint32_t>(n_class_c, 0x7FFFFFFFu);
+    for (int i = 0; i < 5; ++i) h->out_sizes[i] = h->words()[4 + i];
+    h->complement_start = h->words()[9];
+    h->n_recs_host = h->words()[10];
     h->stage = 2;
     return ERASOR_OK;
 }
@@ -704,6 +721,16 @@ int erasor_get_outliers(erasor_handle_t h, float* map_rejected_xyzi, size_t cap_
     if (map_rejected_xyzi && (rc = copy_out(h, h->d_map_rej.p, map_rejected_xyzi, sizeof(float4) * h->out_sizes[2], ptr_kind))) return rc;
     if (curr_rejected_xyzi && (rc = copy_out(h, h->d_curr_rej.p, curr_rejected_xyzi, sizeof(float4) * h->out_sizes[3], ptr_kind))) return rc;
     CK(cudaStreamSynchronize(h->stream));
+    return ERASOR_OK;
+}
+
+int erasor_device_outputs(erasor_handle_t h, const float** arranged, const float** complement, const float** map_rejected, const float** curr_rejected) {
+    if (!h) return ERASOR_E_INVALID;
+    if (h->stage < 2) { h->err = "erasor_device_outputs before erasor_compare"; return ERASOR_E_STATE; }
+    if (arranged) *arranged = h->d_arranged.as<float>();
+    if (complement) *complement = reinterpret_cast<const float*>(h->d_map_sorted.as<float4>() + h->complement_start);
+    if (map_rejected) *map_rejected = h->d_map_rej.as<float>();
+    if (curr_rejected) *curr_rejected = h->d_curr_rej.as<float>();
     return ERASOR_OK;
 }
 

@@ -702,17 +702,24 @@ __device__ __forceinline__ void k2_scatter_pass(const uint16_t* __restrict__ ids
     }
 }
 
-template <int W, bool NODE>
+// DUAL (cloud mode): one launch scatters both clouds -- CTAs [0, second.first_row) take the map cloud's chunks with the
+// arguments below, the rest the query cloud's with `second` (chunk rows are numbered map first, then query).
+struct K2Second { uint32_t first_row; const uint16_t* bin_ids; const float4* pts; const uint32_t* dst_start; float4* out_pts; uint32_t* out_src; };
+
+template <int W, bool NODE, bool DUAL>
 __global__ void __launch_bounds__(W * 32, 4)      // 4 CTAs per SM: the chunking aims at one wave of sm_count * 4 CTAs
 k2_scatter_win(const ChunkDesc* __restrict__ chunks, uint32_t chunk_base, const uint16_t* __restrict__ bin_ids,
                const float4* __restrict__ pts, const NodePose* __restrict__ poses, const uint32_t* __restrict__ ch_cnt,
                const uint32_t* __restrict__ dst_start /*[F][B+2] of this cloud*/, const uint32_t* __restrict__ flag_slot /*[F][B]; null: every bin + complement*/,
                const uint32_t* __restrict__ n_flagged /*[F]*/, float4* __restrict__ out_pts, uint32_t* __restrict__ out_src, int B, uint32_t SW,
-               const uint32_t* __restrict__ list_idx, const uint32_t* __restrict__ list_cnt, int k1_warps) {
+               const uint32_t* __restrict__ list_idx, const uint32_t* __restrict__ list_cnt, int k1_warps, K2Second second) {
     extern __shared__ uint32_t s_tab[];   // [W][ns] per-warp counters / destinations | [SW] bases | u16 slot of every bin [B+1]
     __shared__ float s_T[12];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t row = chunk_base + blockIdx.x;
+    if (DUAL && row >= second.first_row) {        // CTA-uniform
+        bin_ids = second.bin_ids; pts = second.pts; dst_start = second.dst_start; out_pts = second.out_pts; out_src = second.out_src;
+    }
     const ChunkDesc cd = chunks[row];
     const uint32_t* ds   = dst_start + (size_t)cd.frame * (B + 2);
     const uint32_t* pref = ch_cnt + (size_t)row * (B + 1);
@@ -979,15 +986,33 @@ cudaError_t launch_k2(cudaStream_t st, const ChunkDesc* chunks, uint32_t chunk_b
     uint32_t SW; size_t smem;
     k2_smem_plan(B, flag_slot == nullptr, SW, smem);
     cudaError_t e;
+    const K2Second none{0u, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (poses) {
-        auto kern = k2_scatter_win<W, true>;
+        auto kern = k2_scatter_win<W, true, false>;
         if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
-        kern<<<n_chunks, W * 32, smem, st>>>(chunks, chunk_base, bin_ids, pts, poses, ch_cnt, dst_start, flag_slot, n_flagged, out_pts, out_src, B, SW, list_idx, list_cnt, k1_warps);
+        kern<<<n_chunks, W * 32, smem, st>>>(chunks, chunk_base, bin_ids, pts, poses, ch_cnt, dst_start, flag_slot, n_flagged, out_pts, out_src, B, SW, list_idx, list_cnt, k1_warps, none);
     } else {
-        auto kern = k2_scatter_win<W, false>;
+        auto kern = k2_scatter_win<W, false, false>;
         if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
-        kern<<<n_chunks, W * 32, smem, st>>>(chunks, chunk_base, bin_ids, pts, nullptr, ch_cnt, dst_start, flag_slot, n_flagged, out_pts, out_src, B, SW, nullptr, nullptr, W);
+        kern<<<n_chunks, W * 32, smem, st>>>(chunks, chunk_base, bin_ids, pts, nullptr, ch_cnt, dst_start, flag_slot, n_flagged, out_pts, out_src, B, SW, nullptr, nullptr, W, none);
     }
+    return cudaGetLastError();
+}
+
+// cloud mode: the map cloud's chunks (rows [0, n_chunks_map)) and the query cloud's (the n_chunks_qry rows behind them) in one launch
+cudaError_t launch_k2_both(cudaStream_t st, const ChunkDesc* chunks, uint32_t n_chunks_map, uint32_t n_chunks_qry, const uint32_t* ch_cnt, int B,
+                           const uint16_t* bin_map, const float4* map_pts, const uint32_t* dst_start_map, float4* out_map, uint32_t* src_map,
+                           const uint16_t* bin_qry, const float4* qry_pts, const uint32_t* dst_start_qry, float4* out_qry, uint32_t* src_qry) {
+    if (n_chunks_map + n_chunks_qry == 0) return cudaSuccess;
+    constexpr int W = 8;
+    uint32_t SW; size_t smem;
+    k2_smem_plan(B, true, SW, smem);
+    auto kern = k2_scatter_win<W, false, true>;
+    cudaError_t e = ensure_dyn_smem(kern, smem);
+    if (e != cudaSuccess) return e;
+    const K2Second second{n_chunks_map, bin_qry, qry_pts, dst_start_qry, out_qry, src_qry};
+    kern<<<n_chunks_map + n_chunks_qry, W * 32, smem, st>>>(chunks, 0u, bin_map, map_pts, nullptr, ch_cnt, dst_start_map, nullptr, nullptr, out_map, src_map, B, SW,
+                                                             nullptr, nullptr, W, second);
     return cudaGetLastError();
 }
 
@@ -1918,7 +1943,15 @@ cudaError_t launch_k4(cudaStream_t st, cudaStream_t st_b, cudaStream_t st_c, con
 //      Unpinned third-party choices, fixed the same way in the oracle: members of one voxel are summed in input
 //      order; 1-NN ties go to the lowest input index.
 // ============================================================================================
-constexpr int K4B_THREADS = 256;
+constexpr int K4B_THREADS = 512;      // one CTA per flagged bin; the per-bin chain (sort, heads, centroids, 1-NN) is what a launch lasts
+
+// conservative distance along one axis from x to the voxel cell `cell` lying `off` cells away from x's own (see
+// updater_kernels.cu::cell_gap): never more than the true gap, so a cell is only skipped when it cannot hold the nearest point
+__device__ __forceinline__ float k4b_cell_gap(float x, int cell, int off, float leaf, float slack) {
+    if (off == 0) return 0.0f;
+    const float g = (off > 0) ? ((float)cell * leaf - x) : (x - (float)(cell + 1) * leaf);
+    return fmaxf(g - slack, 0.0f);
+}
 
 __global__ void __launch_bounds__(K4B_THREADS)
 k4b_voxelize(float leaf_f, int B, const FlagRec* __restrict__ recs, const uint32_t* __restrict__ n_recs, uint32_t rec_capacity,
@@ -1942,7 +1975,7 @@ k4b_voxelize(float leaf_f, int B, const FlagRec* __restrict__ recs, const uint32
         const uint32_t b = rc.bin, qc = cq[b], ng = rc.n_ground_final, n = qc + ng;
         const uint32_t region = dsq[b] + dsm[b];
         uint32_t np2 = 1; while (np2 < n) np2 <<= 1;
-        unsigned char* base = (n <= smem_cap_points) ? smem_raw : (gscratch + (size_t)region * 32u);
+        unsigned char* base = (n <= smem_cap_points) ? smem_raw : (gscratch + (size_t)region * 36u);
         float*    X   = reinterpret_cast<float*>(base);
         float*    Y   = X + n;
         float*    Z   = Y + n;
@@ -1950,6 +1983,7 @@ k4b_voxelize(float leaf_f, int B, const FlagRec* __restrict__ recs, const uint32
         uint32_t* KEY = reinterpret_cast<uint32_t*>(I + n);
         uint32_t* VST = KEY + n;                  // voxel start positions (<= n entries) + 1
         uint32_t* ORD = VST + n + 1;              // np2
+        uint32_t* VK  = ORD + np2;                // voxel key per voxel, ascending (<= n entries)
         if (n == 0) {
             if (tid == 0) { vox_cnt[rc.slot] = 0u; vox_start[rc.slot] = region; }
             continue;
@@ -1992,6 +2026,9 @@ k4b_voxelize(float leaf_f, int B, const FlagRec* __restrict__ recs, const uint32
         const bool overflow = (dx * dy * dz) > 2147483647LL;
         uint32_t nv;
         float4* out = vox_pts + region;
+        // pcl::VoxelGrid's cell grid of this bin (meaningful when !overflow)
+        const int g_mb0 = (int)floorf(FM(mnx, inv)), g_mb1 = (int)floorf(FM(mny, inv)), g_mb2 = (int)floorf(FM(mnz, inv));
+        const int g_div0 = (int)floorf(FM(mxx, inv)) - g_mb0 + 1, g_div1 = (int)floorf(FM(mxy, inv)) - g_mb1 + 1, g_div2 = (int)floorf(FM(mxz, inv)) - g_mb2 + 1;
         if (overflow) {
             // "Leaf size is too small for the input dataset": output = input
             nv = n;
@@ -2027,15 +2064,67 @@ k4b_voxelize(float leaf_f, int B, const FlagRec* __restrict__ recs, const uint32
             }
             __syncthreads();
         }
-        // exact 1-NN of every centroid into the bin's points; copy that point's intensity
+        // exact 1-NN of every centroid into the bin's points (ties to the lowest index); copy that point's intensity.
+        // Through the voxel grid itself: the centroid's own cell first, then the 26 around it -- each skipped when even its
+        // nearest corner is provably farther than the best so far -- and further shells only while something unseen could
+        // still be closer.  Same result as comparing against every point (the fallback for the overflow case and for
+        // non-finite centroids), at a few cells per centroid instead of n distance evaluations.
+        if (!overflow) {
+            for (uint32_t v = tid; v < nv; v += K4B_THREADS) VK[v] = KEY[ORD[VST[v]]];
+            __syncthreads();
+        }
         for (uint32_t v = tid; v < nv; v += K4B_THREADS) {
             const float4 c = out[v];
             float best = __int_as_float(0x7f800000);
-            uint32_t bi = 0;
-            for (uint32_t i = 0; i < n; ++i) {
-                const float ddx = FS(c.x, X[i]), ddy = FS(c.y, Y[i]), ddz = FS(c.z, Z[i]);
-                const float d = FA(FA(FM(ddx, ddx), FM(ddy, ddy)), FM(ddz, ddz));
-                if (d < best) { best = d; bi = i; }
+            uint32_t bi = 0xFFFFFFFFu;
+            const bool finite = (fabsf(c.x) < 3.0e38f) && (fabsf(c.y) < 3.0e38f) && (fabsf(c.z) < 3.0e38f);
+            if (!overflow && finite) {
+                const int ci = (int)FS(floorf(FM(c.x, inv)), (float)g_mb0), cj = (int)FS(floorf(FM(c.y, inv)), (float)g_mb1), ck = (int)FS(floorf(FM(c.z, inv)), (float)g_mb2);
+                const float slack = 1.0e-3f * leaf_f + 4.0e-6f * fmaxf(fabsf(c.x), fmaxf(fabsf(c.y), fabsf(c.z)));
+                int rad = 0;
+                while (true) {
+                    for (int a = -rad; a <= rad; ++a) {
+                        const int ii = ci + a;
+                        if (ii < 0 || ii >= g_div0) continue;
+                        for (int bb = -rad; bb <= rad; ++bb) {
+                            const int jj = cj + bb;
+                            if (jj < 0 || jj >= g_div1) continue;
+                            for (int cc = -rad; cc <= rad; ++cc) {
+                                if (max(abs(a), max(abs(bb), abs(cc))) != rad) continue;
+                                const int kk = ck + cc;
+                                if (kk < 0 || kk >= g_div2) continue;
+                                if (rad > 0) {
+                                    const float gx = k4b_cell_gap(c.x, ii + g_mb0, a, leaf_f, slack);
+                                    const float gy = k4b_cell_gap(c.y, jj + g_mb1, bb, leaf_f, slack);
+                                    const float gz = k4b_cell_gap(c.z, kk + g_mb2, cc, leaf_f, slack);
+                                    if (0.999f * (gx * gx + gy * gy + gz * gz) > best) continue;
+                                }
+                                const uint32_t key = (uint32_t)(ii + jj * g_div0 + kk * g_div0 * g_div1);
+                                uint32_t lo = 0, hi = nv;                 // first voxel with key >= `key`
+                                while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (VK[mid] < key) lo = mid + 1; else hi = mid; }
+                                if (lo >= nv || VK[lo] != key) continue;
+                                for (uint32_t li = VST[lo]; li < VST[lo + 1]; ++li) {
+                                    const uint32_t q = ORD[li];
+                                    const float ddx = FS(c.x, X[q]), ddy = FS(c.y, Y[q]), ddz = FS(c.z, Z[q]);
+                                    const float d = FA(FA(FM(ddx, ddx), FM(ddy, ddy)), FM(ddz, ddz));
+                                    if (d < best || (d == best && q < bi)) { best = d; bi = q; }
+                                }
+                            }
+                        }
+                    }
+                    const float reach = FM(FM((float)rad, leaf_f), 0.9999f);
+                    if (bi != 0xFFFFFFFFu && best < FM(reach, reach)) break;
+                    ++rad;
+                    if (rad > 4096) break;
+                }
+            }
+            if (bi == 0xFFFFFFFFu) {
+                bi = 0;
+                for (uint32_t i = 0; i < n; ++i) {
+                    const float ddx = FS(c.x, X[i]), ddy = FS(c.y, Y[i]), ddz = FS(c.z, Z[i]);
+                    const float d = FA(FA(FM(ddx, ddx), FM(ddy, ddy)), FM(ddz, ddz));
+                    if (d < best) { best = d; bi = i; }
+                }
             }
             out[v].w = I[bi];
         }
@@ -2047,9 +2136,9 @@ k4b_voxelize(float leaf_f, int B, const FlagRec* __restrict__ recs, const uint32
 cudaError_t launch_k4b(cudaStream_t st, float leaf, int B, const FlagRec* recs, const uint32_t* n_recs, uint32_t rec_capacity,
                        const uint32_t* cnt, const uint32_t* dst_start, const float4* qry_sorted, const float4* part_pts,
                        float4* vox_pts, uint32_t* vox_cnt, uint32_t* vox_start, unsigned char* gscratch, int grid) {
-    constexpr uint32_t SMEM_BYTES = 72 * 1024;
-    // 16 n (xyzi) + 4 n (key) + 4 (n+1) (voxel starts) + 4 np2 (<= 8n) <= 32 n + 16
-    const uint32_t cap = (SMEM_BYTES - 64) / 32u;
+    constexpr uint32_t SMEM_BYTES = 160 * 1024;     // one CTA per SM (a frame flags a few dozen bins): bins up to ~4500 points stay in shared memory
+    // 16 n (xyzi) + 4 n (key) + 4 (n+1) (voxel starts) + 4 np2 (<= 8n) + 4 n (voxel keys) <= 36 n + 16
+    const uint32_t cap = (SMEM_BYTES - 64) / 36u;
     cudaError_t e = ensure_dyn_smem(k4b_voxelize, SMEM_BYTES);
     if (e != cudaSuccess) return e;
     k4b_voxelize<<<grid, K4B_THREADS, SMEM_BYTES, st>>>(leaf, B, recs, n_recs, rec_capacity, cnt, dst_start, qry_sorted, part_pts,

@@ -48,6 +48,11 @@ cudaError_t launch_k2(cudaStream_t st, const ChunkDesc* chunks, uint32_t chunk_b
                       const uint32_t* flag_slot, const uint32_t* n_flagged, float4* out_pts, uint32_t* out_src, int B,
                       const uint32_t* list_idx, const uint32_t* list_cnt, int k1_warps /*warps of the K1 launch that wrote the lists (8 or 32)*/);
 
+// cloud mode: both clouds' stable scatters in one launch (chunk rows: map first, then query)
+cudaError_t launch_k2_both(cudaStream_t st, const ChunkDesc* chunks, uint32_t n_chunks_map, uint32_t n_chunks_qry, const uint32_t* ch_cnt, int B,
+                           const uint16_t* bin_map, const float4* map_pts, const uint32_t* dst_start_map, float4* out_map, uint32_t* src_map,
+                           const uint16_t* bin_qry, const float4* qry_pts, const uint32_t* dst_start_qry, float4* out_qry, uint32_t* src_qry);
+
 int k4_num_launches(bool with_class_c);
 // sorted_pts / sorted_src: K2's output (bins contiguous in source order + source index of every slot); in_pts is unused
 // since K2 also serves mask mode, kept in the signature for ABI stability of the launch wrapper.

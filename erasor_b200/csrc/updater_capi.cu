@@ -47,13 +47,16 @@ struct erasor_updater_ctx {
     Buf map_a, map_b;        size_t n_map = 0;
     Buf global_a;            size_t n_global = 0;      // large-scale: map_arranged_global_
     Buf complement;          size_t n_complement = 0;  // large-scale: map_arranged_complement_
-    Buf scan, qvox, voi, outskirts, tmp_arr, tmp_cmp, tmp_rej, part_tmp, vox_tmp, grid, counters, save_out;
+    Buf scan, qvox, voi, outskirts, tmp_rej, part_tmp, vox_tmp, grid, counters, save_out;
     size_t n_query = 0, n_voi = 0, n_out = 0, n_rej = 0;
     bool submap_uninit = true;
     double submap_cx = 0, submap_cy = 0;
     size_t num_pcs_init = 0;
     int stack_count = 0;
     uint64_t launches = 0;
+    uint32_t* h_words = nullptr;                     // pinned read-back of the two device counters (a copy into pageable memory would
+                                                     // block until the stream has drained and then some)
+    int sm_count = 148;
     uint64_t map_version = 0;                       // bumped whenever the map changes (processed node, reset)
     uint64_t save_version = ~0ull; float save_leaf = 0.0f; size_t save_n = 0;   // what save_out currently holds
 };
@@ -63,36 +66,61 @@ thread_local std::string g_uerr;
 #define UCK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { u->err = std::string(#call) + ": " + cudaGetErrorString(e__); return ERASOR_E_CUDA; } } while (0)
 #define ECK(call) do { int rc__ = (call); if (rc__ != ERASOR_OK) { u->err = std::string(#call) + ": " + erasor_last_error(u->er); return rc__; } } while (0)
 
-int d2h_u32(erasor_updater_ctx* u, const uint32_t* d, uint32_t* h) {
-    UCK(cudaMemcpyAsync(h, d, sizeof(uint32_t), cudaMemcpyDeviceToHost, u->st));
+// counters[0] = points selected by the partition, counters[1] = voxels: both read back with one synchronisation
+int read_counters(erasor_updater_ctx* u, size_t* n_sel, size_t* n_vox) {
+    UCK(cudaMemcpyAsync(u->h_words, u->counters.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, u->st));
     UCK(cudaStreamSynchronize(u->st));
+    if (n_sel) *n_sel = u->h_words[0];
+    if (n_vox) *n_vox = u->h_words[1];
+    return ERASOR_OK;
+}
+
+void no_partition(FusedJob& J) {
+    J.has_part = 0; J.P = PartPred{PART_RADIUS, 0, 0.0, 0.0, 0.0}; J.T_sel = Mat4{}; J.xform_sel = 0; J.pin = nullptr; J.pn = 0;
+    J.chunk_tmp = nullptr; J.d_total_sel = nullptr; J.out_sel = nullptr; J.out_rest = nullptr;
+}
+void no_voxelize(erasor_updater_ctx* u, FusedJob& J) {
+    J.vin = nullptr; J.vn = 0; J.leaf = 1.0f; J.grid = u->grid.as<VoxGrid>(); J.vtmp = u->vox_tmp.p; J.vout = nullptr;
+    J.d_n_out = u->counters.as<uint32_t>() + 1; J.T_out = Mat4{}; J.xform_out = 0;
+}
+// U1 job: stable partition of src[0..n) into sel / rest (both in order)
+int add_partition(erasor_updater_ctx* u, FusedJob& J, const PartPred& P, const Mat4& T, bool xform, const float4* src, size_t n, Buf& sel, Buf& rest) {
+    UCK(sel.ensure(sizeof(float4) * std::max<size_t>(n, 1)));
+    UCK(rest.ensure(sizeof(float4) * std::max<size_t>(n, 1)));
+    UCK(u->part_tmp.ensure(sizeof(uint32_t) * partition_tmp_words((uint32_t)n)));
+    J.has_part = 1; J.P = P; J.T_sel = T; J.xform_sel = xform ? 1 : 0; J.pin = src; J.pn = (uint32_t)n;
+    J.chunk_tmp = u->part_tmp.as<uint32_t>(); J.d_total_sel = u->counters.as<uint32_t>(); J.out_sel = sel.as<float4>(); J.out_rest = rest.as<float4>();
+    return ERASOR_OK;
+}
+// U3 job: voxelize_preserving_labels of src[0..n) at `leaf` into out, optionally followed by the affine T_out
+int add_voxelize(erasor_updater_ctx* u, FusedJob& J, const float4* src, size_t n, float leaf, Buf& out, const Mat4* T_out) {
+    UCK(out.ensure(sizeof(float4) * std::max<size_t>(n, 1)));
+    UCK(u->vox_tmp.ensure(voxelize_tmp_bytes((uint32_t)n)));
+    J.vin = src; J.vn = (uint32_t)n; J.leaf = leaf; J.grid = u->grid.as<VoxGrid>(); J.vtmp = u->vox_tmp.p; J.vout = out.as<float4>();
+    J.d_n_out = u->counters.as<uint32_t>() + 1; J.T_out = T_out ? *T_out : Mat4{}; J.xform_out = T_out ? 1 : 0;
+    return ERASOR_OK;
+}
+int launch_fused(erasor_updater_ctx* u, const FusedJob& J) {
+    u->launches += 1;
+    UCK(launch_node_fused(u->st, J, u->sm_count));
     return ERASOR_OK;
 }
 
 // stable partition of src[0..n) into sel / rest (both in order); returns the number selected
 int partition(erasor_updater_ctx* u, const PartPred& P, const Mat4& T, bool xform, const float4* src, size_t n, Buf& sel, Buf& rest, size_t* n_sel) {
-    UCK(sel.ensure(sizeof(float4) * std::max<size_t>(n, 1)));
-    UCK(rest.ensure(sizeof(float4) * std::max<size_t>(n, 1)));
-    UCK(u->part_tmp.ensure(sizeof(uint32_t) * partition_tmp_words((uint32_t)n)));
-    u->launches += 3;
-    UCK(launch_partition(u->st, P, T, xform, src, (uint32_t)n, u->part_tmp.as<uint32_t>(), u->counters.as<uint32_t>(), sel.as<float4>(), rest.as<float4>()));
-    uint32_t k = 0;
-    int rc = d2h_u32(u, u->counters.as<uint32_t>(), &k);
-    if (rc) return rc;
-    *n_sel = k;
-    return ERASOR_OK;
+    FusedJob J;
+    no_voxelize(u, J);
+    int rc = add_partition(u, J, P, T, xform, src, n, sel, rest);
+    if (rc || (rc = launch_fused(u, J))) return rc;
+    return read_counters(u, n_sel, nullptr);
 }
 
 int voxelize(erasor_updater_ctx* u, const float4* src, size_t n, float leaf, Buf& out, size_t* n_out) {
-    UCK(out.ensure(sizeof(float4) * std::max<size_t>(n, 1)));
-    UCK(u->vox_tmp.ensure(voxelize_tmp_bytes((uint32_t)n)));
-    u->launches += voxelize_num_launches();
-    UCK(launch_voxelize(u->st, src, (uint32_t)n, leaf, u->grid.as<VoxGrid>(), u->vox_tmp.p, out.as<float4>(), u->counters.as<uint32_t>() + 1));
-    uint32_t k = 0;
-    int rc = d2h_u32(u, u->counters.as<uint32_t>() + 1, &k);
-    if (rc) return rc;
-    *n_out = k;
-    return ERASOR_OK;
+    FusedJob J;
+    no_partition(J);
+    int rc = add_voxelize(u, J, src, n, leaf, out, nullptr);
+    if (rc || (rc = launch_fused(u, J))) return rc;
+    return read_counters(u, nullptr, n_out);
 }
 
 // set_submap + bookkeeping of reassign_submap (OfflineMapUpdater.cpp:332-379)
@@ -146,6 +174,8 @@ int erasor_updater_create(const erasor_updater_params_t* up, const erasor_params
     auto fail = [&](const char* what, cudaError_t ce) { g_uerr = std::string(what) + ": " + cudaGetErrorString(ce); erasor_updater_destroy(u); return ERASOR_E_CUDA; };
     cudaError_t e;
     if ((e = u->counters.ensure(64)) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = cudaMallocHost(reinterpret_cast<void**>(&u->h_words), 64)) != cudaSuccess) return fail("cudaMallocHost", e);
+    if ((e = cudaDeviceGetAttribute(&u->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return fail("cudaDeviceGetAttribute", e);
     if ((e = u->grid.ensure(sizeof(VoxGrid))) != cudaSuccess) return fail("cudaMalloc", e);
     // set_params (OfflineMapUpdater.cpp:89-104): tf_lidar2body_ = geoPose2eigen(pose) * Identity
     Mat4 G, I{};
@@ -167,9 +197,10 @@ void erasor_updater_destroy(erasor_updater_t u) {
     if (!u) return;
     cudaSetDevice(u->device);
     if (u->st) cudaStreamSynchronize(u->st);
-    Buf* bufs[] = {&u->map_a, &u->map_b, &u->global_a, &u->complement, &u->scan, &u->qvox, &u->voi, &u->outskirts, &u->tmp_arr, &u->tmp_cmp,
+    Buf* bufs[] = {&u->map_a, &u->map_b, &u->global_a, &u->complement, &u->scan, &u->qvox, &u->voi, &u->outskirts,
                    &u->tmp_rej, &u->part_tmp, &u->vox_tmp, &u->grid, &u->counters, &u->save_out};
     for (Buf* b : bufs) b->release();
+    if (u->h_words) cudaFreeHost(u->h_words);
     if (u->er) erasor_destroy(u->er);
     delete u;
 }
@@ -209,39 +240,43 @@ int erasor_updater_process_node(erasor_updater_t u, int seq, const double* odom7
         if (n_lidar) UCK(cudaMemcpyAsync(u->scan.p, lidar_xyzi, sizeof(float4) * n_lidar, cudaMemcpyHostToDevice, u->st));
         d_scan = u->scan.as<float4>();
     }
-    int rc = voxelize(u, d_scan, n_lidar, (float)u->up.query_voxel_size, u->qvox, &u->n_query);
-    if (rc) return rc;
-    u->launches++;
-    UCK(launch_affine_copy(u->st, u->tf_lidar2body, true, u->qvox.as<float4>(), u->qvox.as<float4>(), (uint32_t)u->n_query));
-    // 2. map VoI (:246-254)
+    // 1 + 2 in ONE cooperative launch: the scan's voxelisation + lidar -> body (:237-241) and, independent of it, the map's
+    //        VoI cut + origin -> body (fetch_VoI, :246-254, :381-438)
+    int rc;
     const double x_curr = u->tf_body2origin.m[3], y_curr = u->tf_body2origin.m[7];
     if (u->up.is_large_scale && (rc = reassign_submap(u, x_curr, y_curr))) return rc;
     Mat4 Tinv;
     mat_inv(u->tf_body2origin, Tinv);
     PartPred P{PART_RADIUS, 0, x_curr, y_curr, std::pow(u->up.max_range + 0.0, 2)};
-    if ((rc = partition(u, P, Tinv, true, u->map_a.as<float4>(), u->n_map, u->voi, u->outskirts, &u->n_voi))) return rc;
+    {
+        FusedJob J;
+        if ((rc = add_voxelize(u, J, d_scan, n_lidar, (float)u->up.query_voxel_size, u->qvox, &u->tf_lidar2body))) return rc;
+        if ((rc = add_partition(u, J, P, Tinv, true, u->map_a.as<float4>(), u->n_map, u->voi, u->outskirts))) return rc;
+        if ((rc = launch_fused(u, J))) return rc;
+        if ((rc = read_counters(u, &u->n_voi, &u->n_query))) return rc;
+    }
     u->n_out = u->n_map - u->n_voi;
     // 3. the path (:266-275)
-    ECK(erasor_set_inputs(u->er, u->voi.as<float>(), u->n_voi, u->qvox.as<float>(), u->n_query, ERASOR_PTR_DEVICE));
     if (u->up.version != 2 && u->up.version != 3) { u->err = "Other version is not implemented!"; return ERASOR_E_INVALID; }
+    ECK(erasor_set_inputs(u->er, u->voi.as<float>(), u->n_voi, u->qvox.as<float>(), u->n_query, ERASOR_PTR_DEVICE));
     ECK(erasor_compare(u->er, u->up.version, seq));
     size_t n_arr = 0, n_cmp = 0, n_rej = 0, n_crej = 0;
     ECK(erasor_get_output_sizes(u->er, &n_arr, &n_cmp, &n_rej, &n_crej));
-    UCK(u->tmp_arr.ensure(sizeof(float4) * std::max<size_t>(n_arr, 1)));
-    UCK(u->tmp_cmp.ensure(sizeof(float4) * std::max<size_t>(n_cmp, 1)));
-    UCK(u->tmp_rej.ensure(sizeof(float4) * std::max<size_t>(n_rej, 1)));
-    ECK(erasor_get_static_estimate(u->er, u->tmp_arr.as<float>(), n_arr, &n_arr, u->tmp_cmp.as<float>(), n_cmp, &n_cmp, ERASOR_PTR_DEVICE));
-    ECK(erasor_get_outliers(u->er, u->tmp_rej.as<float>(), n_rej, &n_rej, nullptr, 0, &n_crej, ERASOR_PTR_DEVICE));
-    // 4. map_filtered = static + complement, body -> origin, + outskirts (:281-290)
+    const float* d_arr = nullptr; const float* d_cmp = nullptr; const float* d_rej = nullptr;
+    ECK(erasor_device_outputs(u->er, &d_arr, &d_cmp, &d_rej, nullptr));
+    // 4. map_filtered = static + complement, body -> origin, + outskirts; map_rejected body -> origin (:281-290): one launch,
+    //    straight from the handle's output buffers (stream-ordered: the next node's set_inputs runs behind it)
     const size_t n_new = n_arr + n_cmp + u->n_out;
     UCK(u->map_b.ensure(sizeof(float4) * std::max<size_t>(n_new, 1)));
-    u->launches += 3;
-    UCK(launch_affine_copy(u->st, u->tf_body2origin, true, u->tmp_arr.as<float4>(), u->map_b.as<float4>(), (uint32_t)n_arr));
-    UCK(launch_affine_copy(u->st, u->tf_body2origin, true, u->tmp_cmp.as<float4>(), u->map_b.as<float4>() + n_arr, (uint32_t)n_cmp));
-    if (u->n_out) UCK(cudaMemcpyAsync(u->map_b.as<float4>() + n_arr + n_cmp, u->outskirts.p, sizeof(float4) * u->n_out, cudaMemcpyDeviceToDevice, u->st));
-    UCK(launch_affine_copy(u->st, u->tf_body2origin, true, u->tmp_rej.as<float4>(), u->tmp_rej.as<float4>(), (uint32_t)n_rej));   // :287
+    UCK(u->tmp_rej.ensure(sizeof(float4) * std::max<size_t>(n_rej, 1)));
+    const CopySeg segs[4] = {
+        {reinterpret_cast<const float4*>(d_arr), u->map_b.as<float4>(), (uint32_t)n_arr, 1},
+        {reinterpret_cast<const float4*>(d_cmp), u->map_b.as<float4>() + n_arr, (uint32_t)n_cmp, 1},
+        {u->outskirts.as<float4>(), u->map_b.as<float4>() + n_arr + n_cmp, (uint32_t)u->n_out, 0},
+        {reinterpret_cast<const float4*>(d_rej), u->tmp_rej.as<float4>(), (uint32_t)n_rej, 1}};
+    u->launches += 1;
+    UCK(launch_copy_segments(u->st, u->tf_body2origin, segs, 4));
     u->n_rej = n_rej;
-    UCK(cudaStreamSynchronize(u->st));
     std::swap(u->map_a, u->map_b);
     u->n_map = n_new;
     u->map_version++;
@@ -359,6 +394,16 @@ int erasor_updater_mapgen_node(erasor_updater_t u, const double* odom7, const fl
     if (cap < k) { u->err = "output buffer too small"; return ERASOR_E_CAPACITY; }
     if (k) UCK(cudaMemcpyAsync(out_xyzi, u->save_out.p, sizeof(float4) * k, ptr_kind == ERASOR_PTR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, u->st));
     UCK(cudaStreamSynchronize(u->st));
+    return ERASOR_OK;
+}
+
+int erasor_updater_get_fused_profile(erasor_updater_t u, uint64_t* ns16) {
+    if (!u || !ns16) return ERASOR_E_INVALID;
+    UCK(cudaSetDevice(u->device));
+    UCK(cudaStreamSynchronize(u->st));
+    VoxGrid g;
+    UCK(cudaMemcpy(&g, u->grid.p, sizeof(VoxGrid), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 16; ++i) ns16[i] = g.prof[i];
     return ERASOR_OK;
 }
 

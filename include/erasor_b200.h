@@ -110,6 +110,12 @@ int erasor_get_outliers(erasor_handle_t h, float* map_rejected_xyzi, size_t cap_
 /* ERASOR::ground_viz (public member, erasor.h:127): ground points of the flagged bins, the tail of `arranged`.
  * ground_xyzi may be NULL to query *n_ground. */
 int erasor_get_ground_viz(erasor_handle_t h, float* ground_xyzi, size_t cap, size_t* n_ground, int ptr_kind);
+/* Device-resident callers (the OfflineMapUpdater mirror, erasor_updater_*): device pointers to the four output clouds of the
+ * last compare, in place -- no copy, no synchronisation.  Sizes: erasor_get_output_sizes.  They live in the handle's own
+ * buffers on erasor_stream(h) and are valid until the next erasor_set_inputs / batch call on this handle; work that reads
+ * them must be ordered on that stream.  Any pointer may be NULL. */
+int erasor_device_outputs(erasor_handle_t h, const float** arranged, const float** complement, const float** map_rejected,
+                          const float** curr_rejected);
 /* replaces ERASOR::get_max_range() (erasor.cpp:628) */
 double erasor_get_max_range(erasor_handle_t h);
 
@@ -275,6 +281,11 @@ int  erasor_updater_mapgen_node(erasor_updater_t u, const double* odom7, const f
 /* the ERASOR handle inside the updater (for the parity taps above) */
 erasor_handle_t erasor_updater_erasor(erasor_updater_t u);
 uint64_t erasor_updater_kernel_launch_count(erasor_updater_t u);
+/* phase boundaries (ns, %globaltimer of CTA 0) of the last fused prologue launch -- the per-node cooperative kernel that
+ * voxelises the scan and cuts the VoI: [0] start, [1] min/max + partition count, [2] set-up + chunk offsets, [3] keys + partition
+ * scatter, [4+2p] histogram + offsets of radix pass p, [5+2p] its scatter, [12] sort done, [13] run heads counted, [14] heads
+ * scattered, [15] centroids + labels written. */
+int erasor_updater_get_fused_profile(erasor_updater_t u, uint64_t* ns16);
 
 #ifdef __cplusplus
 }

@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench
 from erasor_b200 import capi, params, synth
-p, map_world, maps, qs, idxs = bench.load_workload(0, 1, 20)
+p, map_world, _poses, _qs = bench.load_workload("seq05", 0, 1, 20)
 up, ep = params.updater_preset("seq_05"), params.preset("seq_05")
 scene = synth.Scene(seed=5, length=160.0, n_nodes=161, n_dynamic=12)
 scans = {k: scene.scan(k, seed_offset=17) for k in range(161) if (k + 1) % 8 == 0}
