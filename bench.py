@@ -25,6 +25,7 @@ cpu_baseline : the oracle port (oracle/, restated reference path: fetch_VoI + ER
         committed under profiles/r02/.  The driver's default stays on seq 05.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -198,7 +199,7 @@ def clocks_sampler_start(gpu_index: int):
     q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     try:
-        return subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "10", "-i", str(gpu_index)],
+        return subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(gpu_index)],
                                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
     except Exception:
         return None
@@ -378,6 +379,7 @@ def run_ours(args):
     n_copies = max(2, min(N_QUERY_COPIES, int(3e9 // max(1, 16 * NQ))))
     dQ = [torch.from_numpy(Q).to(dev) for _ in range(n_copies)]
     hQ = torch.from_numpy(Q).pin_memory()
+    hQ3 = torch.from_numpy(np.ascontiguousarray(Q[:, :3])).pin_memory()      # packed x y z: the masks never read the query's intensity
     hK = [torch.empty(NG, dtype=torch.uint8).pin_memory() for _ in range(L)]
     torch.cuda.synchronize()
 
@@ -398,6 +400,9 @@ def run_ours(args):
         lanes[lane].process_nodes_ptr(poses, dQ[i % n_copies].data_ptr(), qo, 0.0, 0, 0, capi.PTR_DEVICE, asynchronous=True)
 
     def submit_host(i, lane):
+        lanes[lane].process_nodes_ptr(poses, hQ3.data_ptr(), qo, 0.0, 0, hK[lane].data_ptr(), capi.PTR_HOST | capi.PTR_QUERY_XYZ, asynchronous=True)
+
+    def submit_host_xyzi(i, lane):
         lanes[lane].process_nodes_ptr(poses, hQ.data_ptr(), qo, 0.0, 0, hK[lane].data_ptr(), capi.PTR_HOST, asynchronous=True)
 
     def barrier():
@@ -423,12 +428,14 @@ def run_ours(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = sum(h.kernel_launch_count() for h in lanes)
+        gc.disable()                               # a collection inside a 2 ms timed region would be most of it
         e0.record(xs)                              # every lane is idle here
         for i in range(steps):
             lane = i % n_lanes
             lanes[lane].wait()                     # a handle carries one submission at a time
             submit(warmup + i, lane)
         wait_all()
+        gc.enable()
         e_steps = torch.cuda.Event(enable_timing=True)
         e_steps.record(xs)
         exchange()                                 # the job's one collective, inside the timed region
@@ -448,7 +455,7 @@ def run_ours(args):
     if sampler is not None:
         t_busy = time.perf_counter()
         i_busy = 0
-        while time.perf_counter() - t_busy < 0.3:        # untimed: gives nvidia-smi (10 ms period) samples under this load
+        while time.perf_counter() - t_busy < 0.6:        # untimed: gives nvidia-smi (50 ms period; faster polling stalls the launches it shares the driver with) samples under this load
             lanes[i_busy % L].wait()
             submit_resident(i_busy, i_busy % L)
             i_busy += 1
@@ -466,6 +473,7 @@ def run_ours(args):
     # --- e2e: host buffers through the same call ---
     ms_e2e_1, _, _ = timed(submit_host, args.steps, W, 1)
     ms_e2e, _, per_rank_e2e = timed(submit_host, args.steps, W, L)
+    ms_e2e_xyzi, _, _ = timed(submit_host_xyzi, args.steps, W, L)
     clocks = clocks_sampler_stop(sampler) if rank == 0 else None
 
     # final static map of the job (untimed repeat of one step + exchange) and per-node counters
@@ -549,9 +557,12 @@ def run_ours(args):
                       "note": "asynchronous submissions round-robin over `handles` C-ABI handles sharing one resident map: a batch's "
                               "R-GPF (latency-bound) runs under the next batch's binning; one_lane = dependent steps"},
             "e2e": {"value": scans * args.steps / (ms_e2e * 1e-3), "unit": "scans/s",
-                    "h2d_bytes_per_step": int(16 * NQ + 80 * F), "d2h_bytes_per_step": int(NG),
-                    "note": "pinned host poses + queries -> erasor_process_nodes_async(PTR_HOST) -> pinned host keep mask of the map, "
-                            f"every step; the map itself was uploaded once before the steps ({map_upload_ms:.1f} ms for {16 * NG} bytes, load_global_map)"},
+                    "h2d_bytes_per_step": int(12 * NQ + 80 * F), "d2h_bytes_per_step": int(NG),
+                    "value_xyzi_queries": scans * args.steps / (ms_e2e_xyzi * 1e-3), "h2d_bytes_per_step_xyzi_queries": int(16 * NQ + 80 * F),
+                    "note": "pinned host poses + queries (packed x y z, ERASOR_PTR_QUERY_XYZ: the masks never read the query's intensity) -> "
+                            "erasor_process_nodes_async(PTR_HOST) -> pinned host keep mask of the map, every step; value_xyzi_queries = the same "
+                            "call with 16-byte x y z i queries; "
+                            f"the map itself was uploaded once before the steps ({map_upload_ms:.1f} ms for {16 * NG} bytes, load_global_map)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": by_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                          "frac": by_kernel[dom]["frac"], "traffic": None,
@@ -643,7 +654,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES_PER_PASS, help="frames per step per GPU")
-    ap.add_argument("--lanes", type=int, default=3, help="C-ABI handles fed round-robin (overlapped batches)")
+    ap.add_argument("--lanes", type=int, default=4, help="C-ABI handles fed round-robin (overlapped batches)")
     ap.add_argument("--config", default="seq05", choices=sorted(CONFIGS))
     ap.add_argument("--no-offline-pass", action="store_true", help="skip the informational sequential-pass block")
     ap.add_argument("--no-sweep", action="store_true", help="skip the config-3 preset sweep block")

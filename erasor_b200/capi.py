@@ -18,6 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "liberasor_b200.so")
 
 PTR_HOST, PTR_DEVICE = 0, 1
+PTR_QUERY_XYZ = 16          # OR-able (mask modes): the query cloud is packed x y z, three floats per point
 CLOUD_MAP, CLOUD_QUERY = 0, 1
 OK, E_INVALID, E_CUDA, E_STATE, E_CAPACITY, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 
@@ -343,10 +344,13 @@ class Handle:
         self._ck(self.L.erasor_attach_map(self.h, m.h if m is not None else None))
         self._map = m
 
-    def process_nodes(self, poses7, query_xyzi, query_offsets, voi_max_range: float = 0.0, want_frame_keep: bool = False):
-        """Host-buffer node batch: returns (folded keep mask of the map after this batch, per-frame masks or None)."""
+    def process_nodes(self, poses7, query_xyzi, query_offsets, voi_max_range: float = 0.0, want_frame_keep: bool = False, packed_xyz: bool = False):
+        """Host-buffer node batch: returns (folded keep mask of the map after this batch, per-frame masks or None).
+        packed_xyz: ship the queries as packed x y z (ERASOR_PTR_QUERY_XYZ) -- the masks do not depend on the intensity."""
         P = np.ascontiguousarray(poses7, dtype=np.float64).reshape(-1, 7)
         q = _cloud(query_xyzi)
+        if packed_xyz:
+            q = np.ascontiguousarray(q[:, :3])
         qo = np.ascontiguousarray(query_offsets, dtype=np.uint64)
         F = len(qo) - 1
         assert len(P) == F
@@ -354,7 +358,8 @@ class Handle:
         keep = np.empty(n, dtype=np.uint8)
         fk = np.empty((F, n), dtype=np.uint8) if want_frame_keep else None
         self._ck(self.L.erasor_process_nodes(self.h, P.ctypes.data_as(POINTER(c_double)), q.ctypes.data, qo.ctypes.data_as(POINTER(c_uint64)), F,
-                                             float(voi_max_range), fk.ctypes.data if fk is not None else None, keep.ctypes.data, PTR_HOST))
+                                             float(voi_max_range), fk.ctypes.data if fk is not None else None, keep.ctypes.data,
+                                             PTR_HOST | (PTR_QUERY_XYZ if packed_xyz else 0)))
         self.n_frames = F
         return keep, fk
 

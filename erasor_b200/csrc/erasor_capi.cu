@@ -134,6 +134,7 @@ struct erasor_ctx {
     uint32_t rec_capacity = 0;
     const float4* cur_map = nullptr;
     const float4* cur_qry = nullptr;
+    bool     qry_xyz = false;                  // the staged query cloud is packed x y z (ERASOR_PTR_QUERY_XYZ, mask modes)
     std::vector<uint64_t> map_off, qry_off;
     int      desc_mode = -1;                   // mode the uploaded chunk descriptors were built for (-1: none; 0 cloud, 1 batch masks, 2 node masks)
     uint64_t desc_epoch = 0;                   // bumped whenever the descriptors are rebuilt (invalidates cached graphs)
@@ -351,14 +352,15 @@ int prepare_batch(erasor_ctx* h, const uint64_t* map_off, const uint64_t* qry_of
 }
 
 // one caller cloud -> device pointer (staged through `stage` when it lives in host memory)
-int stage_cloud(erasor_ctx* h, DevBuf& stage, const float* xyzi, size_t n, int ptr_kind, const float4** out) {
+int stage_cloud(erasor_ctx* h, DevBuf& stage, const float* xyzi, size_t n, int ptr_kind, const float4** out, size_t bytes_per_point = sizeof(float4)) {
     if (ptr_kind == ERASOR_PTR_DEVICE) {
-        if (n && (reinterpret_cast<uintptr_t>(xyzi) & 15)) { h->err = "device clouds must be 16-byte aligned (float4)"; return ERASOR_E_INVALID; }
+        const uintptr_t align = bytes_per_point == sizeof(float4) ? 15 : 3;
+        if (n && (reinterpret_cast<uintptr_t>(xyzi) & align)) { h->err = "device clouds must be 16-byte aligned (float4; packed xyz: 4-byte)"; return ERASOR_E_INVALID; }
         *out = reinterpret_cast<const float4*>(xyzi);
         return ERASOR_OK;
     }
     CK(stage.ensure(sizeof(float4) * std::max<size_t>(n, 1)));
-    if (n) CK(cudaMemcpyAsync(stage.p, xyzi, sizeof(float4) * n, cudaMemcpyHostToDevice, h->stream));
+    if (n) CK(cudaMemcpyAsync(stage.p, xyzi, bytes_per_point * n, cudaMemcpyHostToDevice, h->stream));
     *out = stage.as<float4>();
     return ERASOR_OK;
 }
@@ -366,7 +368,7 @@ int stage_cloud(erasor_ctx* h, DevBuf& stage, const float* xyzi, size_t n, int p
 int stage_inputs(erasor_ctx* h, const float* map_xyzi, const float* qry_xyzi, int ptr_kind) {
     int rc;
     if ((rc = stage_cloud(h, h->d_map_in, map_xyzi, h->NM, ptr_kind, &h->cur_map))) return rc;
-    return stage_cloud(h, h->d_qry_in, qry_xyzi, h->NQ, ptr_kind, &h->cur_qry);
+    return stage_cloud(h, h->d_qry_in, qry_xyzi, h->NQ, ptr_kind, &h->cur_qry, h->qry_xyz ? 3 * sizeof(float) : sizeof(float4));
 }
 
 int run_k1(erasor_ctx* h, int mode) {
@@ -384,7 +386,7 @@ int run_k1(erasor_ctx* h, int mode) {
                      h->d_bin_map.as<uint16_t>(), h->d_bin_qry.as<uint16_t>(), h->d_chcnt.as<uint32_t>(), h->d_zmin.as<uint32_t>(),
                      h->d_zmax.as<uint32_t>(), h->d_cnt.as<uint32_t>(), B, F, h->d_fence.as<unsigned long long>(),
                      mode == 2 ? h->d_poses.as<NodePose>() : nullptr, mode == 2 ? h->d_list_idx.as<uint32_t>() : nullptr,
-                     mode == 2 ? h->d_list_cnt.as<uint32_t>() : nullptr));
+                     mode == 2 ? h->d_list_cnt.as<uint32_t>() : nullptr, mode != 0 && h->qry_xyz));
     }
     return ERASOR_OK;
 }
@@ -596,6 +598,8 @@ int erasor_set_inputs(erasor_handle_t h, const float* map_voi_xyzi, size_t n_map
     if (h->pending && (rc = erasor_wait(h))) return rc;
     h->stage = 0;
     h->f0 = 0; h->stat_F = 1;
+    h->qry_xyz = false;
+    if (ptr_kind != ERASOR_PTR_HOST && ptr_kind != ERASOR_PTR_DEVICE) { h->err = "erasor_set_inputs: ptr_kind must be HOST or DEVICE (the cloud outputs carry the query's intensity)"; return ERASOR_E_INVALID; }
     const uint64_t mo[2] = {0, n_map}, qo[2] = {0, n_query};
     rc = prepare_batch(h, mo, qo, 1, 0);
     if (rc) return rc;
@@ -849,6 +853,7 @@ struct Submit {
     int             F = 0;
     uint8_t*        keep_mask = nullptr;    // mode 1: one byte per VoI point; mode 2: frame_keep [F][n_map] (nullable)
     int             ptr_kind = ERASOR_PTR_HOST;
+    bool            qry_xyz = false;        // the query cloud is packed x y z (ERASOR_PTR_QUERY_XYZ)
     const uint32_t* fold_index = nullptr;   // mode 1 fold (nullable)
     uint8_t*        fold_global = nullptr;
     size_t          fold_n = 0;
@@ -873,6 +878,7 @@ int submit(erasor_ctx* h, const Submit& S) {
     if (h->pending && (rc = erasor_wait(h))) return rc;      // one submission in flight per handle (buffers and staging are reused)
     h->stage = 0;
     h->f0 = S.f0;
+    h->qry_xyz = S.qry_xyz;
     if ((rc = prepare_batch(h, S.map_off, S.qry_off, S.F, S.mode))) return rc;
     const bool host = S.ptr_kind != ERASOR_PTR_DEVICE;
     const size_t n_keep = S.keep_mask ? h->NM : 0;          // bytes of the per-frame mask output
@@ -896,7 +902,7 @@ int submit(erasor_ctx* h, const Submit& S) {
             if ((r = stage_inputs(h, S.map_xyzi, S.qry_xyzi, S.ptr_kind))) return r;
         } else {
             h->cur_map = reinterpret_cast<const float4*>(h->map->d_pts);
-            if ((r = stage_cloud(h, h->d_qry_in, S.qry_xyzi, h->NQ, S.ptr_kind, &h->cur_qry))) return r;
+            if ((r = stage_cloud(h, h->d_qry_in, S.qry_xyzi, h->NQ, S.ptr_kind, &h->cur_qry, S.qry_xyz ? 3 * sizeof(float) : sizeof(float4)))) return r;
             CK(cudaMemcpyAsync(h->d_poses.p, h->h_pose.p, sizeof(NodePose) * (size_t)S.F, cudaMemcpyHostToDevice, h->stream));
         }
         uint8_t* d_keep = nullptr;
@@ -930,7 +936,7 @@ int submit(erasor_ctx* h, const Submit& S) {
         erasor_ctx::StepGraph key{};
         key.ptr[0] = S.map_xyzi; key.ptr[1] = S.qry_xyzi; key.ptr[2] = S.keep_mask; key.ptr[3] = S.fold_index; key.ptr[4] = S.fold_global;
         key.ptr[5] = S.keep_out; key.ptr[6] = S.mode == 2 ? (const void*)h->map : nullptr; key.ptr[7] = with_c ? (const void*)h : nullptr;
-        key.fold_n = S.fold_n; key.kind = S.ptr_kind; key.mode = S.mode; key.f0 = S.f0; key.epoch = h->desc_epoch; key.alloc = h->alloc_epoch;
+        key.fold_n = S.fold_n; key.kind = S.ptr_kind | (S.qry_xyz ? ERASOR_PTR_QUERY_XYZ : 0); key.mode = S.mode; key.f0 = S.f0; key.epoch = h->desc_epoch; key.alloc = h->alloc_epoch;
         auto same = [&](const erasor_ctx::StepGraph& g) {
             return std::equal(g.ptr, g.ptr + 8, key.ptr) && g.fold_n == key.fold_n && g.kind == key.kind && g.mode == key.mode && g.f0 == key.f0 &&
                    g.epoch == key.epoch && g.alloc == key.alloc;
@@ -998,6 +1004,9 @@ int process_frames_impl(erasor_handle_t h, const float* map_xyzi, const uint64_t
                         const uint32_t* fold_index, uint8_t* fold_global, size_t fold_n_global, bool async) {
     if (!h || !map_offsets || !query_offsets || !keep_mask) { if (h) h->err = "null argument"; return ERASOR_E_INVALID; }
     if (n_frames <= 0) { h->err = "n_frames must be positive"; return ERASOR_E_INVALID; }
+    const bool qxyz = (ptr_kind & ERASOR_PTR_QUERY_XYZ) != 0;
+    ptr_kind &= ~ERASOR_PTR_QUERY_XYZ;
+    if (ptr_kind != ERASOR_PTR_HOST && ptr_kind != ERASOR_PTR_DEVICE) { h->err = "bad ptr_kind"; return ERASOR_E_INVALID; }
     int rc;
     if (h->pending && (rc = erasor_wait(h))) return rc;
     h->stat_F = n_frames;
@@ -1006,7 +1015,7 @@ int process_frames_impl(erasor_handle_t h, const float* map_xyzi, const uint64_t
         const int f1 = sub_batch_end(h, map_offsets, query_offsets, f0, n_frames);
         if (f1 == f0) { h->err = "a single frame exceeds 2^32 points"; return ERASOR_E_INVALID; }
         Submit S;
-        S.mode = 1; S.F = f1 - f0; S.ptr_kind = ptr_kind; S.f0 = f0;
+        S.mode = 1; S.F = f1 - f0; S.ptr_kind = ptr_kind; S.f0 = f0; S.qry_xyz = qxyz;
         const uint64_t m0 = map_offsets[f0], q0 = query_offsets[f0];
         if (f0 == 0 && f1 == n_frames) { S.map_off = map_offsets; S.qry_off = query_offsets; }
         else {
@@ -1016,7 +1025,7 @@ int process_frames_impl(erasor_handle_t h, const float* map_xyzi, const uint64_t
             S.map_off = mo.data(); S.qry_off = qo.data();
         }
         S.map_xyzi = map_xyzi ? map_xyzi + 4 * m0 : nullptr;
-        S.qry_xyzi = query_xyzi ? query_xyzi + 4 * q0 : nullptr;
+        S.qry_xyzi = query_xyzi ? query_xyzi + (qxyz ? 3 : 4) * q0 : nullptr;
         S.keep_mask = keep_mask + m0;
         S.fold_index = fold_index ? fold_index + m0 : nullptr; S.fold_global = fold_global; S.fold_n = fold_n_global;
         if ((rc = submit(h, S))) return rc;
@@ -1031,6 +1040,9 @@ int process_nodes_impl(erasor_handle_t h, const double* poses7, const float* que
     if (!h || !poses7 || !query_offsets) { if (h) h->err = "null argument"; return ERASOR_E_INVALID; }
     if (!h->map) { h->err = "erasor_process_nodes: no map attached (erasor_attach_map)"; return ERASOR_E_STATE; }
     if (n_frames <= 0) { h->err = "n_frames must be positive"; return ERASOR_E_INVALID; }
+    const bool qxyz = (ptr_kind & ERASOR_PTR_QUERY_XYZ) != 0;
+    ptr_kind &= ~ERASOR_PTR_QUERY_XYZ;
+    if (ptr_kind != ERASOR_PTR_HOST && ptr_kind != ERASOR_PTR_DEVICE) { h->err = "bad ptr_kind"; return ERASOR_E_INVALID; }
     int rc;
     if (h->pending && (rc = erasor_wait(h))) return rc;
     const size_t N = h->map->n;
@@ -1057,9 +1069,9 @@ int process_nodes_impl(erasor_handle_t h, const double* poses7, const float* que
         poses.resize(F);
         for (int f = 0; f < F; ++f) node_pose_of(poses7 + 7 * (size_t)(f0 + f), range, poses[f]);
         Submit S;
-        S.mode = 2; S.F = F; S.ptr_kind = ptr_kind; S.f0 = f0;
+        S.mode = 2; S.F = F; S.ptr_kind = ptr_kind; S.f0 = f0; S.qry_xyz = qxyz;
         S.map_off = mo.data(); S.qry_off = qo.data();
-        S.qry_xyzi = query_xyzi ? query_xyzi + 4 * q0 : nullptr;
+        S.qry_xyzi = query_xyzi ? query_xyzi + (qxyz ? 3 : 4) * q0 : nullptr;
         S.keep_mask = frame_keep ? frame_keep + (size_t)f0 * N : nullptr;
         S.poses = poses.data();
         S.keep_out = (f1 == n_frames) ? keep_out : nullptr;

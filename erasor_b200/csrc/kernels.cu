@@ -158,7 +158,7 @@ k1_rpod_bin(BinTablesView T, const float4* __restrict__ map_pts, const float4* _
             const ChunkDesc* __restrict__ chunks, uint16_t* __restrict__ bin_map, uint16_t* __restrict__ bin_qry,
             uint32_t* __restrict__ ch_cnt, uint32_t* __restrict__ zmin, uint32_t* __restrict__ zmax, uint32_t* __restrict__ cnt_tab,
             int B, int F, unsigned long long* __restrict__ fence, const NodePose* __restrict__ poses,
-            uint32_t* __restrict__ list_idx, uint32_t* __restrict__ list_cnt) {
+            uint32_t* __restrict__ list_idx, uint32_t* __restrict__ list_cnt, int qry_xyz /*query cloud packed x y z (12 bytes per point)*/) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2*   s_ring = reinterpret_cast<float2*>(smem_raw);               // {up, dn} guard thresholds of r^2 per ring boundary
     uint32_t* s_cnt  = reinterpret_cast<uint32_t*>(s_ring + ((T.R + 2) & ~1));
@@ -239,10 +239,20 @@ k1_rpod_bin(BinTablesView T, const float4* __restrict__ map_pts, const float4* _
     for (uint32_t base = warp * (32u * UNROLL); base < cd.len; base += NW * (32u * UNROLL)) {
         float4 p[UNROLL];
         const bool full = base + 32u * UNROLL <= cd.len;          // warp-uniform
+        if (qry_xyz && cd.cloud == 1) {                            // CTA-uniform: packed x y z, three coalesced 4-byte loads per point
+            const float* __restrict__ q3 = reinterpret_cast<const float*>(qry_pts) + (size_t)cd.begin * 3u;
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const uint32_t i = base + u * 32u + lane;
+                p[u] = (full || i < cd.len) ? make_float4(__ldg(q3 + 3u * (size_t)i), __ldg(q3 + 3u * (size_t)i + 1u), __ldg(q3 + 3u * (size_t)i + 2u), 0.f)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const uint32_t i = base + u * 32u + lane;
             p[u] = (full || i < cd.len) ? ld_stream_f4(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
@@ -293,8 +303,9 @@ size_t k1_smem_bytes(int R, int B) {
 cudaError_t launch_k1(cudaStream_t st, const BinTablesView& T, const float4* map_pts, const float4* qry_pts,
                       const ChunkDesc* chunks, int n_chunks, uint16_t* bin_map, uint16_t* bin_qry, uint32_t* ch_cnt,
                       uint32_t* zmin, uint32_t* zmax, uint32_t* cnt_tab, int B, int F, unsigned long long* fence, const NodePose* poses,
-                      uint32_t* list_idx, uint32_t* list_cnt) {
+                      uint32_t* list_idx, uint32_t* list_cnt, bool qry_xyz) {
     if (n_chunks == 0) return cudaSuccess;
+    const int qx = qry_xyz ? 1 : 0;
     constexpr int UNROLL = 4;
     const size_t smem = k1_smem_bytes(T.R, B);
     cudaError_t e;
@@ -305,11 +316,11 @@ cudaError_t launch_k1(cudaStream_t st, const BinTablesView& T, const float4* map
         if (poses) {
             auto kern = k1_rpod_bin<THREADS, UNROLL, true, true>;
             if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
-            kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, poses, list_idx, list_cnt);
+            kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, poses, list_idx, list_cnt, qx);
         } else {
             auto kern = k1_rpod_bin<THREADS, UNROLL, true, false>;
             if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
-            kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, nullptr, nullptr, nullptr);
+            kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, nullptr, nullptr, nullptr, qx);
         }
         return cudaGetLastError();
     }
@@ -317,11 +328,11 @@ cudaError_t launch_k1(cudaStream_t st, const BinTablesView& T, const float4* map
     if (poses) {
         auto kern = k1_rpod_bin<THREADS, UNROLL, true, true>;
         if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
-        kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, poses, list_idx, list_cnt);
+        kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, poses, list_idx, list_cnt, qx);
     } else {
         auto kern = k1_rpod_bin<THREADS, UNROLL, true, false>;
         if ((e = ensure_dyn_smem(kern, smem)) != cudaSuccess) return e;
-        kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, nullptr, nullptr, nullptr);
+        kern<<<n_chunks, THREADS, smem, st>>>(T, map_pts, qry_pts, chunks, bin_map, bin_qry, ch_cnt, zmin, zmax, cnt_tab, B, F, fence, nullptr, nullptr, nullptr, qx);
     }
     return cudaGetLastError();
 }

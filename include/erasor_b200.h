@@ -59,7 +59,11 @@ typedef struct {
     int    skip_voxelize;          /* 1: leave out v3's in-bin voxelize_preserving_labels (erasor.cpp:526-528) */
 } erasor_params_t;
 
-enum { ERASOR_PTR_HOST = 0, ERASOR_PTR_DEVICE = 1 };
+enum { ERASOR_PTR_HOST = 0, ERASOR_PTR_DEVICE = 1,
+       /* OR-able onto either, mask modes only (erasor_process_frames* / erasor_process_nodes*): the QUERY cloud is packed
+        * x y z, three floats per point.  The masks never read the query's intensity (it only travels into the cloud outputs,
+        * erasor.cpp:526-563), and a caller that repacks pcl::PointXYZI (32 bytes) anyway ships a quarter less over PCIe. */
+       ERASOR_PTR_QUERY_XYZ = 16 };
 enum { ERASOR_CLOUD_MAP = 0, ERASOR_CLOUD_QUERY = 1 };
 
 enum {
@@ -197,7 +201,8 @@ int    erasor_attach_map(erasor_handle_t h, erasor_map_t m);
  *   - frame_keep (nullable): n_frames x n_map bytes, frame f's keep mask over the GLOBAL map indices
  *     (1 also for points outside the node's VoI);
  *   - keep_out (nullable): copy of the map's keep mask after this batch (n_map bytes).
- * query_xyzi / frame_keep / keep_out: host or device (ptr_kind); host buffers should be pinned. */
+ * query_xyzi / frame_keep / keep_out: host or device (ptr_kind); host buffers should be pinned.  With ERASOR_PTR_QUERY_XYZ
+ * in ptr_kind, query_xyzi holds 3 floats per point. */
 int erasor_process_nodes(erasor_handle_t h, const double* poses7, const float* query_xyzi, const uint64_t* query_offsets, int n_frames,
                          double voi_max_range, uint8_t* frame_keep, uint8_t* keep_out, int ptr_kind);
 int erasor_process_nodes_async(erasor_handle_t h, const double* poses7, const float* query_xyzi, const uint64_t* query_offsets, int n_frames,

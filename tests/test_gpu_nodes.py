@@ -73,6 +73,41 @@ def test_process_nodes_parity(capi, oracle_mod, small_workload, name, version):
     h.close(); m.close()
 
 
+def test_packed_xyz_queries(capi, small_workload):
+    """ERASOR_PTR_QUERY_XYZ: queries shipped as packed x y z (12 bytes per point) give the masks of the x y z i form -- host
+    buffers through the synchronous call, device buffers through the asynchronous one, and a sub-batch split in between."""
+    import torch
+    p = P.preset("seq_05").replace(skip_voxelize=1)
+    map_world = small_workload["map_world"]
+    poses, qs = _nodes(small_workload, range(6))
+    qo = np.cumsum([0] + [len(q) for q in qs]).astype(np.uint64)
+    Q = np.concatenate(qs)
+    m = capi.Map(map_world)
+    h = capi.Handle(p)
+    h.attach_map(m)
+    keep_ref, fk_ref = h.process_nodes(poses, Q, qo, want_frame_keep=True)
+    assert (fk_ref == 0).any()
+    m.reset_keep()
+    keep, fk = h.process_nodes(poses, Q, qo, want_frame_keep=True, packed_xyz=True)
+    assert np.array_equal(fk, fk_ref) and np.array_equal(keep, keep_ref)
+    # device pointers, asynchronous, queries at an address that is only 4-byte aligned
+    m.reset_keep()
+    dev = torch.device("cuda", 0)
+    buf = torch.zeros(3 * len(Q) + 1, dtype=torch.float32, device=dev)
+    buf[1:] = torch.from_numpy(np.ascontiguousarray(Q[:, :3])).to(dev).reshape(-1)
+    dfk = torch.empty((len(qs), len(map_world)), dtype=torch.uint8, device=dev)
+    dkeep = torch.empty(len(map_world), dtype=torch.uint8, device=dev)
+    P7 = np.ascontiguousarray(poses, dtype=np.float64)
+    h.process_nodes_ptr(P7, buf.data_ptr() + 4, qo, 0.0, dfk.data_ptr(), dkeep.data_ptr(), capi.PTR_DEVICE | capi.PTR_QUERY_XYZ, asynchronous=True)
+    h.wait()
+    assert np.array_equal(dfk.cpu().numpy(), fk_ref) and np.array_equal(dkeep.cpu().numpy(), keep_ref)
+    # cloud mode refuses the flag: its outputs carry the query's intensity
+    with pytest.raises(Exception):
+        h.L.erasor_set_inputs.restype
+        h._ck(h.L.erasor_set_inputs(h.h, Q.ctypes.data, 0, Q.ctypes.data, len(Q), capi.PTR_HOST | capi.PTR_QUERY_XYZ))
+    h.close(); m.close()
+
+
 def test_process_nodes_equals_process_frames(capi, oracle_mod, small_workload):
     """Same nodes through the batch entry point (VoIs cut by the oracle's fetch_VoI, shipped per frame) and through the
     map-resident one: identical rejected sets."""
