@@ -40,7 +40,7 @@ quick = len(sys.argv) > 3
 for L in ((1, 4) if quick else (1, 2, 3, 4, 6)):
     timed(sub_res, L, n_copies * L)
     r = [timed(sub_res, L, 2 * L) for _ in range(4 if quick else 10)]
-    print(f"resident lanes={L} us/step (events):", [round(a) for a, _ in r], "scans/s median", round(frames / np.median([a for a, _ in r]) * 1e6))
+    print(f"resident lanes={L} us/step (events):", [round(a) for a, _ in r], "wall:", [round(b) for _, b in r], "scans/s median", round(frames / np.median([a for a, _ in r]) * 1e6))
 for L in (() if quick else (1, 3, 4, 6)):
     timed(sub_host, L, 2 * L)
     r = [timed(sub_host, L, 2 * L) for _ in range(10)]
