@@ -199,7 +199,7 @@ def clocks_sampler_start(gpu_index: int):
     q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     try:
-        return subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(gpu_index)],
+        return subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(gpu_index)],
                                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
     except Exception:
         return None
@@ -455,7 +455,7 @@ def run_ours(args):
     if sampler is not None:
         t_busy = time.perf_counter()
         i_busy = 0
-        while time.perf_counter() - t_busy < 0.6:        # untimed: gives nvidia-smi (50 ms period; faster polling stalls the launches it shares the driver with) samples under this load
+        while time.perf_counter() - t_busy < 1.0:        # untimed: gives nvidia-smi (200 ms period, the recipe's; faster polling stalls the launches it shares the driver with) samples under this load
             lanes[i_busy % L].wait()
             submit_resident(i_busy, i_busy % L)
             i_busy += 1
@@ -468,11 +468,22 @@ def run_ours(args):
     kernel_ms = {k: v[0] / max(1, v[1]) for k, v in kt.items()}
     h0.reset_kernel_times(False)
     # --- value: resident inputs, one lane (dependent steps) and `L` overlapped lanes ---
+    # Every headline block of K steps is timed REPEATS times and the MEDIAN block is reported (all block times are in the line,
+    # `blocks_ms`): a block lasts 2-4 ms, and a single host-side hiccup (an nvidia-smi poll holding the driver, a descheduled
+    # launch thread) inside one would otherwise be the number.
+    REPEATS = 3
+    blocks = {}
+
+    def timed_median(name, submit, n_lanes):
+        runs = [timed(submit, args.steps, W, n_lanes) for _ in range(REPEATS)]
+        blocks[name] = [round(r[0], 4) for r in runs]
+        return sorted(runs, key=lambda r: r[0])[REPEATS // 2]
+
     ms_res_1, launches_1, _ = timed(submit_resident, args.steps, W, 1)
-    ms_res, launches, per_rank_res = timed(submit_resident, args.steps, W, L)
+    ms_res, launches, per_rank_res = timed_median("resident", submit_resident, L)
     # --- e2e: host buffers through the same call ---
     ms_e2e_1, _, _ = timed(submit_host, args.steps, W, 1)
-    ms_e2e, _, per_rank_e2e = timed(submit_host, args.steps, W, L)
+    ms_e2e, _, per_rank_e2e = timed_median("e2e", submit_host, L)
     ms_e2e_xyzi, _, _ = timed(submit_host_xyzi, args.steps, W, L)
     clocks = clocks_sampler_stop(sampler) if rank == 0 else None
 
@@ -552,6 +563,7 @@ def run_ours(args):
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 points, f64 index/SRT arithmetic", "data": "synthetic",
             "config": workload_config(args.config, p, NG, n_voi, qs, world),
+            "blocks_ms": {"repeats": REPEATS, "reported": "median block", **blocks},
             "lanes": {"handles": L, "value_one_lane": scans * args.steps / (ms_res_1 * 1e-3), "ms_per_step_one_lane": ms_res_1 / args.steps,
                       "e2e_one_lane": scans * args.steps / (ms_e2e_1 * 1e-3),
                       "note": "asynchronous submissions round-robin over `handles` C-ABI handles sharing one resident map: a batch's "

@@ -40,6 +40,30 @@ def test_voxelize_preserving_labels(oracle_mod, scene):
     u.close()
 
 
+def test_voxelize_large_cloud_and_key_widths(oracle_mod, scene):
+    """The fused kernel's radix sort beyond its comfortable sizes: 2.6 M points (segments longer than eight rows, several per
+    warp), a 31-bit key space (four 9-bit passes), a 9-bit one (one pass), duplicates across segment boundaries, and the
+    "leaf too small" overflow case (keys = cloud index)."""
+    from erasor_b200 import capi
+    ep, up = P.preset("seq_05"), P.updater_preset("seq_05")
+    u = capi.Updater(up, ep, scene["map"][:10])
+    rng = np.random.default_rng(11)
+    def cloud(n, span, zspan):
+        c = np.zeros((n, 4), dtype=np.float32)
+        c[:, 0:2] = rng.uniform(-span, span, size=(n, 2))
+        c[:, 2] = rng.uniform(-zspan, zspan, size=n)
+        c[:, 3] = rng.integers(0, 260, n)
+        return c
+    big = cloud(2_600_000, 60.0, 3.0)
+    big[1_000_000:1_300_000] = big[:300_000]                   # exact duplicates far apart in the cloud: same voxel, cloud-order sums
+    cases = ((big, 0.3), (cloud(200_000, 400.0, 19.0), 0.25), (cloud(40_000, 0.7, 0.1), 0.2), (cloud(30_000, 4000.0, 4000.0), 0.01))
+    for c, leaf in cases:
+        got = u.voxelize(c, leaf)
+        ref = oracle_mod.voxelize(c, leaf)
+        assert _same(got, ref), f"n={len(c)} leaf={leaf}: {got.shape} vs {ref.shape}"
+    u.close()
+
+
 @pytest.mark.parametrize("name,version,large", [("seq_05", 3, False), ("seq_00", 3, False), ("seq_05", 2, False), ("large_scale_05", 3, True)])
 def test_sequence_parity(oracle_mod, scene, name, version, large):
     from erasor_b200 import capi
