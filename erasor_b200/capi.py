@@ -32,7 +32,7 @@ EXPORTS = [
     "erasor_map_points_device", "erasor_attach_map", "erasor_process_nodes", "erasor_process_nodes_async", "erasor_get_node_stats",
     "erasor_comm_unique_id", "erasor_comm_init", "erasor_comm_destroy", "erasor_allgather_and_keep", "erasor_and_keep_masks",
     "erasor_get_kernel_time_ms", "erasor_reset_kernel_times", "erasor_get_rgpf_profile", "erasor_get_srt_profile",
-    "erasor_updater_create", "erasor_updater_destroy", "erasor_updater_reset", "erasor_updater_last_error", "erasor_updater_process_node",
+    "erasor_updater_create", "erasor_updater_destroy", "erasor_updater_reset", "erasor_updater_last_error", "erasor_updater_process_node", "erasor_updater_prefetch_scan",
     "erasor_updater_map_size", "erasor_updater_get_cloud", "erasor_updater_save_static_map", "erasor_updater_voxelize", "erasor_updater_mapgen_node",
     "erasor_updater_erasor", "erasor_updater_kernel_launch_count", "erasor_updater_get_fused_profile",
 ]
@@ -125,6 +125,7 @@ def _load():
     L.erasor_updater_last_error.restype = c_char_p
     L.erasor_updater_last_error.argtypes = [c_void_p]
     L.erasor_updater_process_node.argtypes = [c_void_p, c_int, POINTER(c_double), c_void_p, c_size_t, c_int, POINTER(c_int)]
+    L.erasor_updater_prefetch_scan.argtypes = [c_void_p, c_void_p, c_size_t, c_int]
     L.erasor_updater_map_size.argtypes = [c_void_p, POINTER(c_size_t)]
     L.erasor_updater_get_cloud.argtypes = [c_void_p, c_int, c_void_p, c_size_t, POINTER(c_size_t), c_int]
     L.erasor_updater_save_static_map.argtypes = [c_void_p, c_float, c_void_p, c_size_t, POINTER(c_size_t)]
@@ -537,6 +538,11 @@ class Updater:
         done = c_int(0)
         self._ck(self.L.erasor_updater_process_node(self.h, seq, o.ctypes.data_as(POINTER(c_double)), l.ctypes.data, len(l), PTR_HOST, ctypes.byref(done)))
         return bool(done.value)
+
+    def prefetch_scan_ptr(self, lidar_ptr: int, n: int, ptr_kind: int):
+        """Look-ahead: start the upload + voxelisation of the NEXT processed node's scan (consumed by the process_node_ptr call
+        that is given the same pointer and size)."""
+        self._ck(self.L.erasor_updater_prefetch_scan(self.h, c_void_p(lidar_ptr), n, ptr_kind))
 
     def process_node_ptr(self, seq: int, odom7, lidar_ptr: int, n: int, ptr_kind: int) -> bool:
         o = np.ascontiguousarray(odom7, dtype=np.float64)

@@ -54,6 +54,17 @@ struct erasor_updater_ctx {
     size_t num_pcs_init = 0;
     int stack_count = 0;
     uint64_t launches = 0;
+    // look-ahead (erasor_updater_prefetch_scan): scans of coming nodes are uploaded and voxelised on a second stream while the current
+    // node's path runs.  Two slots, so that the caller can hand in node k + 1's scan before it calls process_node for node k.
+    struct Lookahead {
+        Buf scan, qvox, vox_tmp, grid, counters;
+        uint32_t* h_words = nullptr;
+        cudaEvent_t ev = nullptr;
+        const float* ptr = nullptr; size_t n = 0; int kind = 0; bool valid = false; uint64_t ticket = 0;
+    };
+    cudaStream_t st2 = nullptr;
+    Lookahead la[2];
+    uint64_t la_ticket = 0;
     uint32_t* h_words = nullptr;                     // pinned read-back of the two device counters (a copy into pageable memory would
                                                      // block until the stream has drained and then some)
     int sm_count = 148;
@@ -100,9 +111,9 @@ int add_voxelize(erasor_updater_ctx* u, FusedJob& J, const float4* src, size_t n
     J.d_n_out = u->counters.as<uint32_t>() + 1; J.T_out = T_out ? *T_out : Mat4{}; J.xform_out = T_out ? 1 : 0;
     return ERASOR_OK;
 }
-int launch_fused(erasor_updater_ctx* u, const FusedJob& J) {
+int launch_fused(erasor_updater_ctx* u, const FusedJob& J, int max_ctas = 0) {
     u->launches += 1;
-    UCK(launch_node_fused(u->st, J, u->sm_count));
+    UCK(launch_node_fused(u->st, J, u->sm_count, max_ctas));
     return ERASOR_OK;
 }
 
@@ -175,6 +186,13 @@ int erasor_updater_create(const erasor_updater_params_t* up, const erasor_params
     cudaError_t e;
     if ((e = u->counters.ensure(64)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMallocHost(reinterpret_cast<void**>(&u->h_words), 64)) != cudaSuccess) return fail("cudaMallocHost", e);
+    if ((e = cudaStreamCreateWithFlags(&u->st2, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    for (auto& la : u->la) {
+        if ((e = cudaMallocHost(reinterpret_cast<void**>(&la.h_words), 64)) != cudaSuccess) return fail("cudaMallocHost", e);
+        if ((e = cudaEventCreateWithFlags(&la.ev, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+        if ((e = la.counters.ensure(64)) != cudaSuccess) return fail("cudaMalloc", e);
+        if ((e = la.grid.ensure(sizeof(VoxGrid))) != cudaSuccess) return fail("cudaMalloc", e);
+    }
     if ((e = cudaDeviceGetAttribute(&u->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return fail("cudaDeviceGetAttribute", e);
     if ((e = u->grid.ensure(sizeof(VoxGrid))) != cudaSuccess) return fail("cudaMalloc", e);
     // set_params (OfflineMapUpdater.cpp:89-104): tf_lidar2body_ = geoPose2eigen(pose) * Identity
@@ -197,6 +215,12 @@ void erasor_updater_destroy(erasor_updater_t u) {
     if (!u) return;
     cudaSetDevice(u->device);
     if (u->st) cudaStreamSynchronize(u->st);
+    if (u->st2) { cudaStreamSynchronize(u->st2); cudaStreamDestroy(u->st2); }
+    for (auto& la : u->la) {
+        if (la.ev) cudaEventDestroy(la.ev);
+        if (la.h_words) cudaFreeHost(la.h_words);
+        for (Buf* b : {&la.scan, &la.qvox, &la.vox_tmp, &la.grid, &la.counters}) b->release();
+    }
     Buf* bufs[] = {&u->map_a, &u->map_b, &u->global_a, &u->complement, &u->scan, &u->qvox, &u->voi, &u->outskirts,
                    &u->tmp_rej, &u->part_tmp, &u->vox_tmp, &u->grid, &u->counters, &u->save_out};
     for (Buf* b : bufs) b->release();
@@ -210,6 +234,8 @@ int erasor_updater_reset(erasor_updater_t u, const float* initial_map_xyzi, size
     if (!u || (n_map && !initial_map_xyzi)) { if (u) u->err = "null argument"; return ERASOR_E_INVALID; }
     UCK(cudaSetDevice(u->device));
     UCK(cudaStreamSynchronize(u->st));
+    UCK(cudaStreamSynchronize(u->st2));
+    for (auto& la : u->la) la.valid = false;
     Buf& dst = u->up.is_large_scale ? u->global_a : u->map_a;
     UCK(dst.ensure(sizeof(float4) * std::max<size_t>(n_map, 1)));
     if (n_map) UCK(cudaMemcpyAsync(dst.p, initial_map_xyzi, sizeof(float4) * n_map, cudaMemcpyHostToDevice, u->st));
@@ -234,8 +260,11 @@ int erasor_updater_process_node(erasor_updater_t u, int seq, const double* odom7
     UCK(cudaSetDevice(u->device));
     pose_to_mat(odom7, u->tf_body2origin);                                                    // :219
     // 1. query: voxelize_preserving_labels, lidar -> body (:237-241)
+    erasor_updater_ctx::Lookahead* la = nullptr;
+    for (auto& c : u->la) if (c.valid && c.ptr == lidar_xyzi && c.n == n_lidar && c.kind == ptr_kind && (!la || c.ticket < la->ticket)) la = &c;
+    const bool prefetched = la != nullptr;
     const float4* d_scan = reinterpret_cast<const float4*>(lidar_xyzi);
-    if (ptr_kind != ERASOR_PTR_DEVICE) {
+    if (!prefetched && ptr_kind != ERASOR_PTR_DEVICE) {
         UCK(u->scan.ensure(sizeof(float4) * std::max<size_t>(n_lidar, 1)));
         if (n_lidar) UCK(cudaMemcpyAsync(u->scan.p, lidar_xyzi, sizeof(float4) * n_lidar, cudaMemcpyHostToDevice, u->st));
         d_scan = u->scan.as<float4>();
@@ -248,7 +277,19 @@ int erasor_updater_process_node(erasor_updater_t u, int seq, const double* odom7
     Mat4 Tinv;
     mat_inv(u->tf_body2origin, Tinv);
     PartPred P{PART_RADIUS, 0, x_curr, y_curr, std::pow(u->up.max_range + 0.0, 2)};
-    {
+    if (prefetched) {
+        // the scan was voxelised ahead of time on the second stream (erasor_updater_prefetch_scan): only the map's VoI cut is left
+        FusedJob J;
+        no_voxelize(u, J);
+        if ((rc = add_partition(u, J, P, Tinv, true, u->map_a.as<float4>(), u->n_map, u->voi, u->outskirts))) return rc;
+        // (a cooperative grid must be resident as a whole: leave the quarter of the SMs a look-ahead for the next node may be holding)
+        if ((rc = launch_fused(u, J, u->sm_count - std::max(1, u->sm_count / 4)))) return rc;
+        UCK(cudaEventSynchronize(la->ev));                      // the look-ahead's counters are in its pinned words
+        if ((rc = read_counters(u, &u->n_voi, nullptr))) return rc;
+        u->n_query = la->h_words[1];
+        std::swap(u->qvox, la->qvox);
+        la->valid = false;
+    } else {
         FusedJob J;
         if ((rc = add_voxelize(u, J, d_scan, n_lidar, (float)u->up.query_voxel_size, u->qvox, &u->tf_lidar2body))) return rc;
         if ((rc = add_partition(u, J, P, Tinv, true, u->map_a.as<float4>(), u->n_map, u->voi, u->outskirts))) return rc;
@@ -281,6 +322,34 @@ int erasor_updater_process_node(erasor_updater_t u, int seq, const double* odom7
     u->n_map = n_new;
     u->map_version++;
     if (processed) *processed = 1;
+    return ERASOR_OK;
+}
+
+// Look-ahead for callers that know the coming nodes' scans (file-based / offline runs): upload + voxelize_preserving_labels
+// + lidar -> body of a scan on a second stream, on a quarter of the SMs, while the current node's path runs.  Two slots.
+int erasor_updater_prefetch_scan(erasor_updater_t u, const float* lidar_xyzi, size_t n_lidar, int ptr_kind) {
+    if (!u || (n_lidar && !lidar_xyzi)) { if (u) u->err = "null argument"; return ERASOR_E_INVALID; }
+    UCK(cudaSetDevice(u->device));
+    // a free slot, else the older of the two (its look-ahead is dropped)
+    erasor_updater_ctx::Lookahead* la = !u->la[0].valid ? &u->la[0] : (!u->la[1].valid ? &u->la[1] : (u->la[0].ticket < u->la[1].ticket ? &u->la[0] : &u->la[1]));
+    if (la->valid) { UCK(cudaEventSynchronize(la->ev)); la->valid = false; }
+    const float4* d_scan = reinterpret_cast<const float4*>(lidar_xyzi);
+    if (ptr_kind != ERASOR_PTR_DEVICE) {
+        UCK(la->scan.ensure(sizeof(float4) * std::max<size_t>(n_lidar, 1)));
+        if (n_lidar) UCK(cudaMemcpyAsync(la->scan.p, lidar_xyzi, sizeof(float4) * n_lidar, cudaMemcpyHostToDevice, u->st2));
+        d_scan = la->scan.as<float4>();
+    }
+    UCK(la->qvox.ensure(sizeof(float4) * std::max<size_t>(n_lidar, 1)));
+    UCK(la->vox_tmp.ensure(voxelize_tmp_bytes((uint32_t)n_lidar)));
+    FusedJob J;
+    no_partition(J);
+    J.vin = d_scan; J.vn = (uint32_t)n_lidar; J.leaf = (float)u->up.query_voxel_size; J.grid = la->grid.as<VoxGrid>(); J.vtmp = la->vox_tmp.p;
+    J.vout = la->qvox.as<float4>(); J.d_n_out = la->counters.as<uint32_t>() + 1; J.T_out = u->tf_lidar2body; J.xform_out = 1;
+    u->launches += 1;
+    UCK(launch_node_fused(u->st2, J, u->sm_count, std::max(1, u->sm_count / 4)));
+    UCK(cudaMemcpyAsync(la->h_words, la->counters.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, u->st2));
+    UCK(cudaEventRecord(la->ev, u->st2));
+    la->ptr = lidar_xyzi; la->n = n_lidar; la->kind = ptr_kind; la->valid = true; la->ticket = ++u->la_ticket;
     return ERASOR_OK;
 }
 

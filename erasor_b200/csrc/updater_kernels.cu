@@ -570,7 +570,7 @@ size_t voxelize_tmp_bytes(uint32_t n) {
     return sizeof(uint32_t) * ((size_t)4 * n + 2 * (size_t)RD * nseg + RD + partition_tmp_words(n) + 2 * ((size_t)n + 2) + 64 + 6 * (size_t)kFusedMaxGrid);
 }
 
-cudaError_t launch_node_fused(cudaStream_t st, const FusedJob& J, int sm_count) {
+cudaError_t launch_node_fused(cudaStream_t st, const FusedJob& J, int sm_count, int max_ctas) {
     constexpr size_t SMEM = sizeof(uint32_t) * FW * RD;
     static int max_ctas_per_sm = -1;
     if (max_ctas_per_sm < 0) {
@@ -586,6 +586,7 @@ cudaError_t launch_node_fused(cudaStream_t st, const FusedJob& J, int sm_count) 
     uint32_t G = (work + FT - 1) / FT;
     const uint32_t cap = (uint32_t)std::min<long long>((long long)sm_count * max_ctas_per_sm, (long long)kFusedMaxGrid);
     G = G < 1u ? 1u : (G > cap ? cap : G);
+    if (max_ctas > 0 && G > (uint32_t)max_ctas) G = (uint32_t)max_ctas;      // look-ahead jobs leave most SMs to the current node's path
     FusedJob jj = J;
     void* args[] = {&jj};
     return cudaLaunchCooperativeKernel((const void*)k_node_fused, dim3(G), dim3(FT), args, SMEM, st);

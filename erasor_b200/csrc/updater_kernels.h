@@ -42,7 +42,7 @@ struct FusedJob {
 };
 size_t partition_tmp_words(uint32_t n);
 size_t voxelize_tmp_bytes(uint32_t n);
-cudaError_t launch_node_fused(cudaStream_t st, const FusedJob& job, int sm_count);
+cudaError_t launch_node_fused(cudaStream_t st, const FusedJob& job, int sm_count, int max_ctas = 0 /*0: as many as the job wants, up to one per SM*/);
 
 cudaError_t launch_affine_copy(cudaStream_t st, const Mat4& T, bool do_transform, const float4* in, float4* out, uint32_t n);
 

@@ -271,6 +271,13 @@ const char* erasor_updater_last_error(erasor_updater_t u);
  * removal_interval-th call), 0 for the reference's "PASS!". */
 int  erasor_updater_process_node(erasor_updater_t u, int seq, const double* odom7, const float* lidar_xyzi, size_t n_lidar, int ptr_kind,
                                  int* processed);
+/* Optional look-ahead for callers that know the coming nodes' scans (file-based / offline runs: the reference replays a rosbag,
+ * OfflineMapUpdater.cpp:203): starts a scan's upload, voxelize_preserving_labels and lidar -> body (:237-241) on a second stream,
+ * so that it runs under the path of the node being processed.  Two look-aheads can be pending: hand in node k + 1's scan, then
+ * call erasor_updater_process_node for node k.  A process_node call given the same (pointer, n, ptr_kind) consumes the
+ * look-ahead -- results are identical with and without; one that matches nothing runs the usual way.  The scan buffer must
+ * stay valid and unchanged until it has been consumed. */
+int  erasor_updater_prefetch_scan(erasor_updater_t u, const float* lidar_xyzi, size_t n_lidar, int ptr_kind);
 int  erasor_updater_map_size(erasor_updater_t u, size_t* n);
 /* clouds of the last processed node (parity taps): 0 map_arranged_, 1 map_voi_ (body), 2 query_voi_ (body),
  * 5 map_rejected_ (origin), 7 map_outskirts_, 8 map_arranged_complement_ (large-scale).  xyzi may be NULL to query *n. */

@@ -92,3 +92,30 @@ def test_sequence_parity(oracle_mod, scene, name, version, large):
     assert len(o.cloud(o.TOTAL_MAP_REJECTED)[0]) > 0, "the sequence must reject something"
     assert _same(u.save_static_map(0.2), o.save_static_map(0.2))
     u.close()
+
+
+def test_lookahead_gives_the_same_maps(oracle_mod, scene):
+    """erasor_updater_prefetch_scan: scans handed in one node ahead (upload + voxelisation on the second stream) -- every cloud
+    identical to the oracle's caller loop, also when a look-ahead is never consumed (wrong scan) or two are pending."""
+    from erasor_b200 import capi
+    ep, up = P.preset("seq_05"), P.updater_preset("seq_05")
+    up.removal_interval = 2
+    o = oracle_mod.OracleUpdater(up, ep, scene["map"])
+    u = capi.Updater(up, ep, scene["map"])
+    scans = [np.ascontiguousarray(s, dtype=np.float32) for s in scene["scans"]]
+    proc = [k for k in range(len(scans)) if (k + 1) % up.removal_interval == 0]
+    nxt = {a: b for a, b in zip(proc, proc[1:])}
+    u.prefetch_scan_ptr(scans[proc[0]].ctypes.data, len(scans[proc[0]]), capi.PTR_HOST)
+    for k, pose in enumerate(scene["poses"]):
+        a = o.callback_node(k, pose, scans[k])
+        if k in nxt and k != proc[2]:                      # one node gets no look-ahead: the usual path in between
+            u.prefetch_scan_ptr(scans[nxt[k]].ctypes.data, len(scans[nxt[k]]), capi.PTR_HOST)
+        if k == proc[4]:                                   # a look-ahead nobody consumes (a scan that is never processed)
+            u.prefetch_scan_ptr(scans[0].ctypes.data, len(scans[0]), capi.PTR_HOST)
+        b = u.process_node_ptr(k, pose, scans[k].ctypes.data, len(scans[k]), capi.PTR_HOST)
+        assert a == b
+        if a:
+            assert _same(u.cloud(u.QUERY_VOI), o.cloud(o.QUERY_VOI)[0]), f"node {k}: query_voi"
+            assert _same(u.cloud(u.MAP_ARRANGED), o.cloud(o.MAP_ARRANGED)[0]), f"node {k}: map_arranged"
+    assert _same(u.save_static_map(0.2), o.save_static_map(0.2))
+    u.close()
