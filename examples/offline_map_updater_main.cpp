@@ -41,11 +41,20 @@ int main(int argc, char** argv) {
         cfg.initial_map_path = data_dir + "/dense_global_map.pcd";
         OfflineMapUpdater updater(cfg);
         const auto poses = load_all_poses(data_dir + "/poses_lidar2body.csv");
-        for (int i = init_idx; i < (int)poses.size(); ++i) {
-            char name[64];
-            std::snprintf(name, sizeof(name), "/pcds/%06d.pcd", i);
-            const PointCloud src = load_pcd(data_dir + name);
-            updater.callback_node(i, poses[i].data(), src);
+        // Scans come from files, so the next one is known: it is loaded before the current node is processed and, when that next
+        // call will process its node (removal_interval), handed to the updater's look-ahead -- its upload and voxelisation
+        // then run under the current node's path.
+        auto scan_path = [&](int i) { char name[64]; std::snprintf(name, sizeof(name), "/pcds/%06d.pcd", i); return data_dir + name; };
+        const int n_nodes = (int)poses.size();
+        PointCloud cur, nxt;
+        if (init_idx < n_nodes) cur = load_pcd(scan_path(init_idx));
+        for (int i = init_idx; i < n_nodes; ++i) {
+            if (i + 1 < n_nodes) {
+                nxt = load_pcd(scan_path(i + 1));
+                if (updater.processes_call(2)) updater.prefetch(nxt);
+            }
+            updater.callback_node(i, poses[i].data(), cur);
+            std::swap(cur, nxt);
         }
         updater.save_static_map(0.2f);
         std::cout << "Static map building complete!" << std::endl;

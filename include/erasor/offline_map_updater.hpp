@@ -167,11 +167,18 @@ public:
     // replaces callback_node(const erasor::node::ConstPtr&) (:203-330): odom = {x y z qx qy qz qw} body -> origin,
     // lidar in the lidar frame.  Returns true when the node was processed, false for "PASS!".
     bool callback_node(int seq, const double odom[7], const PointCloud& lidar) {
+        ++calls_;
         int processed = 0;
         check(erasor_updater_process_node(u_, seq, odom, reinterpret_cast<const float*>(lidar.data()), lidar.size(), ERASOR_PTR_HOST, &processed));
         if (cfg_.verbose) std::printf(processed ? "\033[01;32m%dth frame\033[0m is comming\n" : "\033[1;32m PASS! \033[0m\n", seq);
         return processed != 0;
     }
+    // Look-ahead (no counterpart in the reference, which receives its nodes one ROS message at a time): hand in the scan of a COMING
+    // callback_node call so that its upload and voxelisation (:237-241) run under the current node's path.  `lidar` must stay
+    // alive and unchanged until that call; results are identical with and without.
+    void prefetch(const PointCloud& lidar) { check(erasor_updater_prefetch_scan(u_, reinterpret_cast<const float*>(lidar.data()), lidar.size(), ERASOR_PTR_HOST)); }
+    // will the k-th callback_node call from now (k = 1: the next one) process its node, or "PASS!" (removal_interval, :328)?
+    bool processes_call(int k) const { return (calls_ + k) % cfg_.updater.removal_interval == 0; }
     // replaces save_static_map(float voxel_size) (:174-196)
     void save_static_map(float voxel_size) {
         PointCloud map_to_be_saved = static_map(voxel_size);
@@ -205,6 +212,7 @@ private:
     }
     Config cfg_;
     erasor_updater_t u_ = nullptr;
+    long long calls_ = 0;          // callback_node calls so far (the updater's stack_count, :206)
 };
 
 }  // namespace erasor_b200
