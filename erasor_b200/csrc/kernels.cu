@@ -1171,47 +1171,6 @@ constexpr uint32_t K4_PAD = 0xFFFFFFFFu;
 template <int G> __device__ __forceinline__ void group_sync() { if (G == 32) __syncwarp(); else __syncthreads(); }
 template <int G> __device__ __forceinline__ int  group_tid() { return (G == 32) ? (threadIdx.x & 31) : threadIdx.x; }
 
-// in-place bitonic sort of ORD[0..np2) (np2 a power of two) by key(ORD[.]) ascending, ties by the value itself;
-// K4_PAD sorts last.  Each thread stages up to 8 pairs per pass: all loads first, then all keys, then the swaps, so
-// the shared-memory latencies of different pairs overlap.  Stages with j <= 32 only touch 64-element blocks owned
-// by one warp, so they synchronise with __syncwarp instead of the group barrier.
-template <int G, class KeyF>
-__device__ __forceinline__ void block_bitonic(uint32_t* __restrict__ ORD, uint32_t np2, KeyF key) {
-    const int tid = group_tid<G>();
-    const uint32_t half = np2 >> 1;
-    for (uint32_t k = 2; k <= np2; k <<= 1) {
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t t0 = tid; t0 < half; t0 += 8u * G) {
-                uint32_t a[8], b[8], pi[8];
-                bool ok[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const uint32_t t = t0 + (uint32_t)u * G;
-                    ok[u] = t < half;
-                    pi[u] = ((t & ~(j - 1u)) << 1) | (t & (j - 1u));   // j is a power of two
-                    a[u] = ok[u] ? ORD[pi[u]] : 0u;
-                    b[u] = ok[u] ? ORD[pi[u] + j] : 0u;
-                }
-                decltype(key(0u)) ka[8], kb[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) { ka[u] = key(ok[u] ? a[u] : K4_PAD); kb[u] = key(ok[u] ? b[u] : K4_PAD); }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    if (ok[u]) {
-                        const bool a_after_b = (ka[u] > kb[u]) || (ka[u] == kb[u] && a[u] > b[u]);
-                        const bool b_after_a = (kb[u] > ka[u]) || (kb[u] == ka[u] && b[u] > a[u]);
-                        const bool sw = ((pi[u] & k) == 0) ? a_after_b : b_after_a;
-                        if (sw) { ORD[pi[u]] = b[u]; ORD[pi[u] + j] = a[u]; }
-                    }
-                }
-            }
-            if (G == 32 || j <= 32) __syncwarp(); else __syncthreads();
-        }
-        if (G != 32 && k >= 64) __syncthreads();   // next k starts with j = k: partners leave the warp's 64-element block
-    }
-    if (G != 32) __syncthreads();
-}
-
 // ordered compaction of indices i in [0,n) with pred(i) into out[]; returns count (all threads of the group).
 template <int G, class Pred>
 __device__ __forceinline__ uint32_t k4_compact(uint32_t n, uint32_t* out, uint32_t* s_warp /*[G/32 + 1], unused for G == 32*/, Pred pred) {
