@@ -4,13 +4,7 @@
 #   config 5  40 x 360 bins, 262144-point scans, 2 M-point resident map (per-rank share of the frame-sharded job)
 #   dense     the seq-05 twin at the size SURVEY 8 estimates for the real sequence
 mkdir -p gpurun_out
-python scripts/config4_largescale.py 50000000 5 > gpurun_out/config4_largescale.json 2> gpurun_out/config4.err; tail -c 1500 gpurun_out/config4_largescale.json; echo
-for k in k1_rpod_bin k2_srt_scatter "k4_rgpf<.int.1024"; do
-  name=$(echo "$k" | tr -d '<> ,.' )
-  ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$k" -s 2 -c 1 -f -o gpurun_out/prof_config4_$name \
-      python scripts/config4_largescale.py 50000000 1 > gpurun_out/ncu_config4_$name.log 2>&1
-  tail -1 gpurun_out/ncu_config4_$name.log
-done
+bash scripts/run_config4.sh
 python bench.py --config synthetic40x360 --frames 32 --steps 8 --warmup 3 --lanes 3 --no-offline-pass --no-sweep > gpurun_out/config5_n1.json 2> gpurun_out/config5_n1.err
 echo "config5 rc=$?"; tail -2 gpurun_out/config5_n1.err; python -c "
 import json; d=json.load(open('gpurun_out/config5_n1.json')); print('config5 N=1 value=%.0f e2e=%.0f ms/step=%.3f parity=%s' % (d['value'], d['e2e']['value'], d['ms_per_step'], d['parity_spot_check']), d['quality_final_map'], {k: v['avg_launch_ms'] for k, v in d['roofline']['by_kernel'].items()})"
