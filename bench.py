@@ -504,10 +504,10 @@ def run_ours(args):
         blocks[name] = [round(r[0], 4) for r in runs]
         return sorted(runs, key=lambda r: r[0])[REPEATS // 2]
 
-    ms_res_1, launches_1, _ = timed(submit_resident, args.steps, W, 1)
+    ms_res_1, launches_1, _ = timed_median("resident_one_lane", submit_resident, 1)
     ms_res, launches, per_rank_res = timed_median("resident", submit_resident, L)
     # --- e2e: host buffers through the same call ---
-    ms_e2e_1, _, _ = timed(submit_host, args.steps, W, 1)
+    ms_e2e_1, _, _ = timed_median("e2e_one_lane", submit_host, 1)
     ms_e2e, _, per_rank_e2e = timed_median("e2e", submit_host, L)
     ms_e2e_xyzi, _, _ = timed(submit_host_xyzi, args.steps, W, L)
     clocks = clocks_sampler_stop(sampler) if rank == 0 else None
