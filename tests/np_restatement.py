@@ -117,3 +117,48 @@ def status_v2(p, mmn, mmx, mcnt, qmn, qmx, qcnt):
             else:
                 st[b] = MERGE
     return st, flag
+
+
+# ------------------------------------------------------------------------------------------------
+# erasor_utils::voxelize_preserving_labels (reference erasor_utils.cpp:80-114): pcl::VoxelGrid<PointXYZI> with a cubic leaf
+# (PCL 1.8: downsample_all_data, no minimum points per voxel), then the intensity of the nearest source point (1-NN) copied
+# onto every centroid.  A second, structurally different reading -- float32 numpy arrays, np.unique instead of a sort of
+# (key, index) pairs, a brute-force distance matrix instead of a search grid -- with the same two pinned choices as the oracle
+# (members summed in cloud order; 1-NN ties to the lowest index).  For small clouds (the 1-NN is O(voxels x points)).
+# ------------------------------------------------------------------------------------------------
+def voxelize_preserving_labels(cloud, leaf_size):
+    f32 = np.float32
+    c = np.ascontiguousarray(cloud, dtype=f32).reshape(-1, 4)
+    n = len(c)
+    if n == 0:
+        return np.zeros((0, 4), dtype=f32)
+    leaf = f32(leaf_size)
+    inv = f32(1.0) / leaf
+    xyz = c[:, :3]
+    mn, mx = xyz.min(axis=0), xyz.max(axis=0)                       # getMinMax3D
+    d = ((mx - mn) * inv).astype(np.int64) + 1                      # truncation like the reference's int64 cast
+    if int(d[0]) * int(d[1]) * int(d[2]) > 2147483647:             # "Leaf size is too small for the input dataset"
+        vox = c.copy()
+    else:
+        min_b = np.floor(mn * inv).astype(np.int32)
+        max_b = np.floor(mx * inv).astype(np.int32)
+        div_b = max_b - min_b + 1
+        ijk = (np.floor(xyz * inv) - min_b.astype(f32)).astype(np.int32)            # float subtraction, then the int cast
+        key = (ijk[:, 0].astype(np.int64) + ijk[:, 1].astype(np.int64) * int(div_b[0]) +
+               ijk[:, 2].astype(np.int64) * int(div_b[0]) * int(div_b[1])).astype(np.int32).astype(np.uint32)   # int32 arithmetic, unsigned order
+        keys, inverse = np.unique(key, return_inverse=True)          # ascending voxel key = output order
+        vox = np.zeros((len(keys), 4), dtype=f32)
+        cnt = np.zeros(len(keys), dtype=np.int64)
+        for i in range(n):                                           # cloud order: sequential float32 sums per voxel
+            v = inverse[i]
+            vox[v] += c[i]
+            cnt[v] += 1
+        vox /= cnt.astype(f32)[:, None]
+    out = vox.copy()
+    for v in range(len(vox)):                                        # exact 1-NN, ties to the lowest cloud index
+        dx = vox[v, 0] - xyz[:, 0]
+        dy = vox[v, 1] - xyz[:, 1]
+        dz = vox[v, 2] - xyz[:, 2]
+        d2 = (dx * dx + dy * dy) + dz * dz                           # float32, the association of pcl's squared distance
+        out[v, 3] = c[int(np.argmin(d2)), 3]                         # argmin returns the first minimum
+    return out

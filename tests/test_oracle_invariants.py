@@ -166,3 +166,22 @@ def test_voxelize_preserving_labels(oracle_mod):
         dd = ((out[i, 0] - pts[:, 0]) ** 2 + (out[i, 1] - pts[:, 1]) ** 2).astype(np.float32) + ((out[i, 2] - pts[:, 2]) ** 2).astype(np.float32)
         assert out[i, 3] == pts[np.argmin(dd), 3]
     assert len(oracle_mod.voxelize(pts[:0], 0.2)) == 0
+
+
+@pytest.mark.parametrize("seed,n,span,leaf", [(1, 1500, 6.0, 0.2), (2, 2500, 3.0, 0.05), (3, 800, 40.0, 0.4), (4, 1, 1.0, 0.2), (5, 600, 3000.0, 0.001)])
+def test_oracle_voxelize_matches_the_numpy_restatement(oracle_mod, seed, n, span, leaf):
+    """erasor_utils::voxelize_preserving_labels (erasor_utils.cpp:80-114): the C++ oracle (sorted (key, index) pairs, grid-accelerated
+    1-NN) against a structurally different numpy reading (np.unique, sequential float32 sums, brute-force 1-NN) -- bit for bit,
+    including the "leaf too small" overflow case (seed 5) and duplicated points."""
+    rng = np.random.default_rng(seed)
+    c = np.zeros((n, 4), dtype=np.float32)
+    c[:, :3] = rng.uniform(-span, span, size=(n, 3)).astype(np.float32)
+    c[:, 2] *= 0.2
+    c[:, 3] = rng.integers(0, 260, n).astype(np.float32)
+    if n > 100:
+        c[n // 2:n // 2 + 40] = c[:40]                             # exact duplicates far apart in the cloud
+        c[-20:, :3] = c[100:120, :3]                               # same position, different label: 1-NN ties to the lowest index
+    got = oracle_mod.voxelize(c, leaf)
+    ref = NP.voxelize_preserving_labels(c, leaf)
+    assert got.shape == ref.shape
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), f"differs in {np.count_nonzero(got.view(np.uint32) != ref.view(np.uint32))} words"
