@@ -276,7 +276,8 @@ int  erasor_updater_process_node(erasor_updater_t u, int seq, const double* odom
  * so that it runs under the path of the node being processed.  Two look-aheads can be pending: hand in node k + 1's scan, then
  * call erasor_updater_process_node for node k.  A process_node call given the same (pointer, n, ptr_kind) consumes the
  * look-ahead -- results are identical with and without; one that matches nothing runs the usual way.  The scan buffer must
- * stay valid and unchanged until it has been consumed. */
+ * stay valid and unchanged until it has been consumed; a DEVICE scan must be complete (its producer synchronised) before the
+ * call, because the look-ahead reads it on the updater's own second stream. */
 int  erasor_updater_prefetch_scan(erasor_updater_t u, const float* lidar_xyzi, size_t n_lidar, int ptr_kind);
 int  erasor_updater_map_size(erasor_updater_t u, size_t* n);
 /* clouds of the last processed node (parity taps): 0 map_arranged_, 1 map_voi_ (body), 2 query_voi_ (body),
